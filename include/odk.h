@@ -1,0 +1,172 @@
+/*
+ * odk.h -- C ABI of libodk.so: the B200 (sm_100a) kernels for the dense per-anchor hot path of
+ * DavidPetrus/ood_object_detection (an effdet fork).
+ *
+ * The reference has no FFI layer: its boundary for this path is the python API of
+ * effdet/anchors.py, effdet/loss.py, effdet/bench.py and effdet/soft_nms.py.  Every entry point
+ * below replaces the torch/torchvision op sequence behind one of those functions; the python
+ * shims in ood_object_detection_b200/ keep the reference signatures and call these through ctypes
+ * (INTEGRATION.md shows the binding).  Citations are relative to the reference root.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every DEVICE buffer (inputs, outputs, workspace) is owned
+ *     by the caller; the library never allocates, frees or retains device memory;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
+ *   - pyramid geometry: `level_hw[l]` = H_l*W_l for l in [0, num_levels) (HOST array),
+ *     `na` = anchors per location (9).  A = na * sum(level_hw).  Reference anchor order
+ *     (anchors.py:264-299): r = off_l + (y*W_l + x)*na + a.
+ *   - "planar" order used by odk_assign/odk_loss for per-anchor integers: p = off_l + a*HW_l +
+ *     (y*W_l + x), the order of the NCHW head outputs; the per-image stride is
+ *     odk_planar_stride(A) (A rounded up to 4).
+ *   - `cls_levels` / `box_levels`: HOST arrays of num_levels DEVICE pointers to contiguous
+ *     NCHW fp32 tensors [B, na*C, H_l, W_l] / [B, na*4, H_l, W_l] (efficientdet.py:410-414).
+ *   - return 0 on success, <0 for argument errors, >0 = cudaError_t of a failed launch;
+ *     odk_last_error() returns a thread-local message.  No exceptions cross the ABI.
+ */
+#ifndef ODK_H_
+#define ODK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODK_MAX_LEVELS 8
+#define ODK_VERSION 1
+
+/* error codes */
+#define ODK_OK 0
+#define ODK_EINVAL (-1)
+#define ODK_EWORKSPACE (-2)
+#define ODK_EUNSUPPORTED (-3)
+
+int odk_version(void);
+const char *odk_last_error(void);
+/* per-image stride (elements) of planar per-anchor arrays */
+int64_t odk_planar_stride(int64_t A);
+
+/* ---- target assignment -------------------------------------------------------------------
+ * Replaces AnchorLabeler.batch_label_anchors' per-image loop (anchors.py:393-434):
+ * IouSimilarity.compare (region_similarity_calculator.py:59-73), ArgMaxMatcher.match with
+ * force_match_for_each_row (argmax_matcher.py:105-146), thresholds matched == unmatched ==
+ * match_thr (anchors.py:321-325).
+ *   anchors   [A,4] yxyx fp32, reference order
+ *   gt_boxes  [B,Mmax,4] yxyx fp32; gt_labels [B,Mmax] int32 (1-based classes)
+ *   gt_count  [B] int32 or NULL (= Mmax rows each)
+ *   filter_valid != 0: rows with label < 0 are skipped (anchors.py:405-408)
+ * Outputs: match [B, odk_planar_stride(A)] int32, planar order: gt row (index into the
+ * UNFILTERED Mmax rows) or -1; num_pos [B] fp32 (anchors.py:434).
+ * Workspace: odk_assign_workspace_bytes(B, Mmax).
+ */
+size_t odk_assign_workspace_bytes(int B, int Mmax);
+int odk_assign(const float *anchors, const float *gt_boxes, const int32_t *gt_labels, const int32_t *gt_count, int B,
+               int Mmax, const int32_t *level_hw, int num_levels, int na, float match_thr, int filter_valid,
+               int32_t *match, float *num_pos, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Pairwise IoU matrix out[n,m] of yxyx boxes: IouSimilarity.compare
+ * (region_similarity_calculator.py:59-101), same fp32 operation order. */
+int odk_iou_matrix(const float *boxes1, int n, const float *boxes2, int m, float *out, void *stream);
+
+/* Materialises the reference's target tensors from `match` (matcher.py:170-179,
+ * box_coder.py:81-110, target_assigner.py:168-220, anchors.py:416-432):
+ *   cls_targets: one int64 block per level, [B, H_l, W_l, na], blocks concatenated
+ *                (block l starts at element B*off_l);  value = label-1, background -1
+ *   box_targets: same blocking, fp32 [B, H_l, W_l, na*4]
+ */
+int odk_targets(const float *anchors, const float *gt_boxes, const int32_t *gt_labels, int B, int Mmax,
+                const int32_t *level_hw, int num_levels, int na, const int32_t *match, int64_t *cls_targets,
+                float *box_targets, void *stream);
+
+/* ---- detection loss ----------------------------------------------------------------------
+ * Replaces loss_fn (loss.py:224-298): one_hot (:182-186), new_focal_loss (:49-95) or
+ * focal_loss_legacy (:15-47), huber/_box_loss (:104-118,:171-179), the per-level loop and sums.
+ * Targets come either from odk_assign (`match` != NULL: class and encoded box are recomputed on
+ * the fly, nothing per-anchor but `match` is read) or from reference-layout tensors
+ * (`cls_targets`/`box_targets` blocks as written by odk_targets; `match` == NULL).
+ *   normalizer  device fp32 scalar = sum(num_positives)+1 (loss.py:261)
+ *   out         device fp32 [3] = total, cls_loss, box_loss (loss.py:295-298)
+ *   grad_cls_levels / grad_box_levels: HOST arrays of DEVICE pointers (same shapes as the
+ *   inputs) receiving d total / d input, or NULL for forward only.
+ * Workspace: odk_loss_workspace_bytes().
+ */
+typedef struct odk_loss_params {
+    float alpha;
+    float gamma;
+    float delta;
+    float box_loss_weight;
+    float label_smoothing;
+    int32_t legacy_focal;
+} odk_loss_params;
+
+size_t odk_loss_workspace_bytes(void);
+int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B, int C, const int32_t *level_hw,
+             int num_levels, int na, const int32_t *match, const float *anchors, const float *gt_boxes,
+             const int32_t *gt_labels, int Mmax, const int64_t *cls_targets, const float *box_targets,
+             const float *normalizer, const odk_loss_params *params, float *out, void *const *grad_cls_levels,
+             void *const *grad_box_levels, void *workspace, size_t workspace_bytes, void *stream);
+
+/* In-place `buf[i] *= *scale` over n floats; returns immediately on device when *scale == 1.
+ * Used by the autograd shim when the upstream gradient of the loss is not 1. */
+int odk_scale_inplace(float *buf, int64_t n, const float *scale, void *stream);
+
+/* ---- post-process: top-k -------------------------------------------------------------------
+ * Replaces _post_process (bench.py:12-56): concat/permute of the levels, torch.topk over
+ * [B, A*C] (k = K, sorted descending; ties broken by ascending flat index), index split and
+ * the three gathers.  Outputs: cls_topk [B,K] fp32 (the selected logit), box_topk [B,K,4],
+ * indices [B,K] int64 (anchor = flat // C), classes [B,K] int64 (flat % C).
+ * Workspace: odk_topk_workspace_bytes(B, K).
+ */
+size_t odk_topk_workspace_bytes(int B, int K);
+int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B, int C, const int32_t *level_hw,
+             int num_levels, int na, int K, float *cls_topk, float *box_topk, int64_t *indices, int64_t *classes,
+             void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- post-process: detections ---------------------------------------------------------------
+ * Replaces _batch_detection / generate_detections (bench.py:59-76, anchors.py:95-172):
+ * anchor gather, decode_box_outputs (anchors.py:51-85), optional clip (anchors.py:88-92),
+ * sigmoid, score > score_min filter, then either torchvision batched_nms (coordinate trick,
+ * iou > nms_thr) or batched_soft_nms (soft_nms.py:115-169, gaussian), first max_det kept,
+ * class+1, optional rescale.
+ *   cls_topk [B,N] logits, box_topk [B,N,4], indices/classes [B,N] int64 (odk_topk layout)
+ *   img_scale [B] or NULL; img_size [B,2] or NULL (clip only when both given)
+ * Outputs: dets [B,max_det,6] (x0,y0,x1,y1,score,class; zero padded), count [B] int32,
+ * src [B,max_det] int32 = position in the N list each detection came from (-1 padded).
+ */
+typedef struct odk_detect_params {
+    int32_t max_det;
+    int32_t soft_nms;       /* 0: hard NMS, 1: gaussian soft-NMS */
+    float score_min;        /* 0.01 (anchors.py:141) */
+    double nms_iou;         /* 0.3  (anchors.py:150) */
+    float soft_sigma;       /* 0.5  */
+    float soft_iou;         /* 0.3  (unused by the gaussian method) */
+    float soft_score_thr;   /* 0.001 */
+} odk_detect_params;
+
+int odk_detect(const float *cls_topk, const float *box_topk, const int64_t *indices, const int64_t *classes, int B,
+               int N, const float *anchors, int64_t A, const float *img_scale, const float *img_size,
+               const odk_detect_params *params, float *dets, int32_t *count, int32_t *src, void *stream);
+
+/* Stand-alone soft_nms (soft_nms.py:42-112) on one box set [n,4] xyxy: runs until no box is
+ * left or max_rounds is reached.  idx_out [n] int64, score_out [n] fp32, count [1] int32. */
+int odk_soft_nms(const float *boxes, const float *scores, int n, int method_gaussian, float sigma, float iou_thr,
+                 float score_thr, int max_rounds, int64_t *idx_out, float *score_out, int32_t *count, void *stream);
+
+/* Stand-alone greedy NMS with torchvision::nms semantics on [n,4] xyxy (scores need not be
+ * sorted).  keep [n] int64 in descending score order, count [1] int32. */
+size_t odk_nms_workspace_bytes(int n);
+int odk_nms(const float *boxes, const float *scores, int n, double iou_thr, int64_t *keep, int32_t *count,
+            void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- OOD score --------------------------------------------------------------------------------
+ * Not in the reference.  For anchor_idx [B,D] int64 (entries < 0 skipped ->
+ * outputs 0): energy = -T*logsumexp(logits[anchor,:]/T), max_logit = max_c logits[anchor,c],
+ * read in place from the NCHW levels (the row the reference gathers at bench.py:51-52). */
+int odk_ood(const void *const *cls_levels, int B, int C, const int32_t *level_hw, int num_levels, int na,
+            const int64_t *anchor_idx, int D, float temperature, float *energy, float *max_logit, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODK_H_ */

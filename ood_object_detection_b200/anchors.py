@@ -1,0 +1,322 @@
+"""Anchors, AnchorLabeler and detection generation with the reference's API, running on libodk.
+
+Mirrors effdet/anchors.py of the reference (same names, argument meaning and results):
+``Anchors`` (:191-302), ``AnchorLabeler`` (:305-438), ``decode_box_outputs`` (:51-85),
+``clip_boxes_xyxy`` (:88-92), ``generate_detections`` (:95-172), ``get_feat_sizes`` (:175-188).
+The per-image python loops and the torch/torchvision op chains behind them are replaced by the
+sm_100a kernels of libodk.so (odk_assign, odk_targets, odk_detect).
+"""
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .object_detection import ArgMaxMatcher, FasterRcnnBoxCoder, IouSimilarity, TargetAssigner
+
+MIN_CLASS_SCORE = -5.0
+_DUMMY_DETECTION_SCORE = -1e5
+
+
+def get_feat_sizes(image_size: Tuple[int, int], max_level: int):
+    """Feature-map (H, W) for levels 0..max_level; each level halves, rounding up."""
+    sizes = [tuple(image_size)]
+    for _ in range(max_level):
+        h, w = sizes[-1]
+        sizes.append(((h - 1) // 2 + 1, (w - 1) // 2 + 1))
+    return sizes
+
+
+class Anchors(nn.Module):
+    """Multiscale RetinaNet anchors (reference effdet/anchors.py:191-302).
+
+    ``boxes`` is the [A, 4] yxyx fp32 table in the reference order
+    level -> y -> x -> (scale octave, aspect); it is computed on the host in float64 and rounded
+    to fp32 once, exactly as the reference does, because the labeler's IoU thresholds are
+    sensitive to the last bit.
+    """
+
+    def __init__(self, min_level, max_level, num_scales, aspect_ratios, anchor_scale, image_size: Tuple[int, int]):
+        super().__init__()
+        self.min_level = min_level
+        self.max_level = max_level
+        self.num_scales = num_scales
+        self.aspect_ratios = aspect_ratios
+        n_levels = max_level - min_level + 1
+        if isinstance(anchor_scale, Sequence):
+            assert len(anchor_scale) == n_levels
+            self.anchor_scales = anchor_scale
+        else:
+            self.anchor_scales = [anchor_scale] * n_levels
+        assert isinstance(image_size, Sequence) and len(image_size) == 2
+        assert image_size[0] % 2 ** max_level == 0, 'Image size must be divisible by 2 ** max_level (128)'
+        assert image_size[1] % 2 ** max_level == 0, 'Image size must be divisible by 2 ** max_level (128)'
+        self.image_size = tuple(image_size)
+        self.feat_sizes = get_feat_sizes(image_size, max_level)
+        self.config = self._generate_configs()
+        self.register_buffer('boxes', self._generate_boxes())
+
+    @classmethod
+    def from_config(cls, config, img_size=None, min_level=0):
+        size = config.image_size if img_size is None else (img_size, img_size)
+        return cls(config.min_level + min_level, config.max_level, config.num_scales, config.aspect_ratios,
+                   config.anchor_scale, size)
+
+    def _generate_configs(self):
+        """{level: [(stride_yx, octave_scale, aspect, anchor_scale), ...]} like the reference."""
+        base = self.feat_sizes[0]
+        cfg = {}
+        for level in range(self.min_level, self.max_level + 1):
+            fs = self.feat_sizes[level]
+            stride = (base[0] // fs[0], base[1] // fs[1])
+            scale = self.anchor_scales[level - self.min_level]
+            cfg[level] = [(stride, octave / float(self.num_scales), aspect, scale)
+                          for octave in range(self.num_scales) for aspect in self.aspect_ratios]
+        return cfg
+
+    def _generate_boxes(self):
+        per_level = []
+        for level_cfg in self.config.values():
+            shapes = []
+            for stride, octave_scale, aspect, anchor_scale in level_cfg:
+                size_x = anchor_scale * stride[1] * 2 ** octave_scale
+                size_y = anchor_scale * stride[0] * 2 ** octave_scale
+                if isinstance(aspect, Sequence):
+                    ax, ay = aspect[0], aspect[1]
+                else:
+                    ax = np.sqrt(aspect)
+                    ay = 1.0 / ax
+                half_x, half_y = size_x * ax / 2.0, size_y * ay / 2.0
+                cx = np.arange(stride[1] / 2, self.image_size[1], stride[1])
+                cy = np.arange(stride[0] / 2, self.image_size[0], stride[0])
+                gx, gy = np.meshgrid(cx, cy)
+                gx, gy = gx.ravel(), gy.ravel()
+                shapes.append(np.stack([gy - half_y, gx - half_x, gy + half_y, gx + half_x], axis=1))
+            # [HW, shapes, 4] -> rows ordered (y, x, shape)
+            per_level.append(np.stack(shapes, axis=1).reshape(-1, 4))
+        return torch.from_numpy(np.concatenate(per_level, axis=0)).float()
+
+    def get_anchors_per_location(self):
+        return self.num_scales * len(self.aspect_ratios)
+
+    # ---- libodk geometry -------------------------------------------------------------------
+    def level_hw(self):
+        return [self.feat_sizes[l][0] * self.feat_sizes[l][1] for l in range(self.min_level, self.max_level + 1)]
+
+    def level_offsets(self):
+        na, off, out = self.get_anchors_per_location(), 0, []
+        for hw in self.level_hw():
+            out.append(off)
+            off += hw * na
+        out.append(off)
+        return out
+
+
+class LabelBatch:
+    """Device-resident result of the assignment kernels for one batch.
+
+    ``match`` ([B, Apad] int32, planar order) is all the fused loss needs; the reference-layout
+    target tensors are only materialised on demand (``targets()``)."""
+
+    def __init__(self, labeler, gt_boxes, gt_labels, match, num_positives):
+        self.labeler = labeler
+        self.gt_boxes = gt_boxes
+        self.gt_labels = gt_labels
+        self.match = match
+        self.num_positives = num_positives
+        self._targets = None
+
+    def targets(self):
+        if self._targets is None:
+            self._targets = self.labeler._materialize(self)
+        return self._targets
+
+
+class AnchorLabeler(object):
+    """Labeler for multiscale anchor boxes (reference effdet/anchors.py:305-438).
+
+    Inputs must live on (or are moved to) the CUDA device holding ``anchors.boxes``; the
+    reference's per-image python loop is one odk_assign + one odk_targets launch sequence.
+    """
+
+    def __init__(self, anchors, num_classes: int, match_threshold: float = 0.5):
+        similarity_calc = IouSimilarity()
+        matcher = ArgMaxMatcher(match_threshold, unmatched_threshold=match_threshold,
+                                negatives_lower_than_unmatched=True, force_match_for_each_row=True)
+        box_coder = FasterRcnnBoxCoder()
+        self.target_assigner = TargetAssigner(similarity_calc, matcher, box_coder)
+        self.anchors = anchors
+        self.match_threshold = match_threshold
+        self.num_classes = num_classes
+        self.indices_cache = {}
+
+    # ---- helpers ---------------------------------------------------------------------------
+    def _device(self):
+        dev = self.anchors.boxes.device
+        if dev.type != 'cuda':
+            raise RuntimeError('AnchorLabeler: anchors.boxes must be on a CUDA device (call anchors.cuda()); '
+                               'there is no CPU fallback')
+        return dev
+
+    def _pack(self, gt_boxes, gt_classes, filter_valid):
+        """-> gt_boxes [B,M,4] fp32, labels [B,M] int32, count [B] int32 or None, on device."""
+        dev = self._device()
+        if isinstance(gt_boxes, torch.Tensor) and gt_boxes.dim() == 3:
+            boxes = gt_boxes.to(dev, torch.float32).contiguous()
+            cls = gt_classes if isinstance(gt_classes, torch.Tensor) else torch.stack(list(gt_classes))
+            labels = cls.to(dev).reshape(boxes.shape[0], -1).to(torch.int32).contiguous()
+            return boxes, labels, None
+        lens = [int(b.shape[0]) for b in gt_boxes]
+        B, M = len(lens), max([1] + lens)
+        boxes = torch.zeros((B, M, 4), dtype=torch.float32, device=dev)
+        labels = torch.full((B, M), -1, dtype=torch.int32, device=dev)
+        for i, n in enumerate(lens):
+            if n:
+                if gt_boxes[i].dtype != torch.float32:
+                    raise ValueError('Invalid tensor type: should be tf.float32')  # BoxList contract
+                boxes[i, :n] = gt_boxes[i].to(dev)
+                labels[i, :n] = gt_classes[i].to(dev).to(torch.int32)
+        count = torch.tensor(lens, dtype=torch.int32, device=dev)
+        return boxes, labels, count
+
+    def _relabel_task_cls(self, gt_boxes, gt_classes, task_cls):
+        # reference anchors.py:396-403: every gt overlapping a task-class gt by IoU > 0.9 takes
+        # the task class; the caller's class tensors are modified in place.
+        from .object_detection import BoxList
+        for i in range(len(gt_boxes)):
+            task_mask = gt_classes[i] == task_cls
+            if (~task_mask).sum() > 0:
+                sims = self.target_assigner._similarity_calc.compare(BoxList(gt_boxes[i][task_mask]), BoxList(gt_boxes[i]))
+                overlapping, _ = (sims > 0.9).max(0) if sims.shape[0] > 0 else (torch.zeros_like(task_mask), None)
+                gt_classes[i][overlapping] = task_cls
+
+    def assign(self, gt_boxes, gt_classes, filter_valid=True, task_cls=None) -> LabelBatch:
+        """Run the assignment kernels; the result feeds either ``targets()`` or the fused loss."""
+        if task_cls is not None:
+            self._relabel_task_cls(gt_boxes, gt_classes, task_cls)
+        boxes, labels, count = self._pack(gt_boxes, gt_classes, filter_valid)
+        dev = boxes.device
+        B, M = boxes.shape[0], boxes.shape[1]
+        lib = _lib.lib()
+        anc = self.anchors.boxes
+        A = anc.shape[0]
+        apad = lib.odk_planar_stride(A)
+        match = torch.empty((B, apad), dtype=torch.int32, device=dev)
+        num_pos = torch.empty((B,), dtype=torch.float32, device=dev)
+        ws_bytes = lib.odk_assign_workspace_bytes(B, M)
+        ws = torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=dev)
+        hw = self.anchors.level_hw()
+        with torch.cuda.device(dev):
+            _lib.check(lib.odk_assign(_lib.ptr(anc), _lib.ptr(boxes), _lib.ptr(labels), _lib.ptr(count), B, M,
+                                      _lib.int_array(hw), len(hw), self.anchors.get_anchors_per_location(),
+                                      float(np.float32(self.match_threshold)), int(bool(filter_valid)),
+                                      _lib.ptr(match), _lib.ptr(num_pos), _lib.ptr(ws), ws.numel() * 8,
+                                      _lib.stream_ptr(dev)))
+        return LabelBatch(self, boxes, labels, match, num_pos)
+
+    def _materialize(self, lb: LabelBatch):
+        lib = _lib.lib()
+        dev = lb.match.device
+        B, M = lb.gt_boxes.shape[0], lb.gt_boxes.shape[1]
+        A = self.anchors.boxes.shape[0]
+        na = self.anchors.get_anchors_per_location()
+        cls_flat = torch.empty((B * A,), dtype=torch.int64, device=dev)
+        box_flat = torch.empty((B * A * 4,), dtype=torch.float32, device=dev)
+        hw = self.anchors.level_hw()
+        with torch.cuda.device(dev):
+            _lib.check(lib.odk_targets(_lib.ptr(self.anchors.boxes), _lib.ptr(lb.gt_boxes), _lib.ptr(lb.gt_labels), B, M,
+                                       _lib.int_array(hw), len(hw), na, _lib.ptr(lb.match), _lib.ptr(cls_flat),
+                                       _lib.ptr(box_flat), _lib.stream_ptr(dev)))
+        cls_out, box_out = [], []
+        offs = self.anchors.level_offsets()
+        for i, level in enumerate(range(self.anchors.min_level, self.anchors.max_level + 1)):
+            h, w = self.anchors.feat_sizes[level]
+            lo, hi = B * offs[i], B * offs[i + 1]
+            cls_out.append(cls_flat[lo:hi].view(B, h, w, na))
+            box_out.append(box_flat[lo * 4:hi * 4].view(B, h, w, na * 4))
+        return cls_out, box_out
+
+    # ---- reference API -----------------------------------------------------------------------
+    def label_anchors(self, gt_boxes, gt_classes, filter_valid=True):
+        """One image: ([H_l, W_l, na] int64 per level, [H_l, W_l, na*4] fp32 per level, num_positives)."""
+        lb = self.assign([gt_boxes], [gt_classes.reshape(-1)], filter_valid=filter_valid)
+        cls_t, box_t = lb.targets()
+        return [c[0] for c in cls_t], [b[0] for b in box_t], lb.num_positives[0]
+
+    def batch_label_anchors(self, gt_boxes, gt_classes, filter_valid=True, task_cls=None):
+        """([B, H_l, W_l, na] int64 per level, [B, H_l, W_l, na*4] fp32 per level, num_positives [B])."""
+        assert len(gt_boxes) == len(gt_classes)
+        lb = self.assign(gt_boxes, gt_classes, filter_valid=filter_valid, task_cls=task_cls)
+        cls_t, box_t = lb.targets()
+        return cls_t, box_t, lb.num_positives
+
+
+# ------------------------------------------------------------------------------- detections
+def decode_box_outputs(rel_codes, anchors, output_xyxy: bool = False):
+    """Relative box codes -> absolute boxes (reference effdet/anchors.py:51-85).
+
+    Plain elementwise torch on whatever device the inputs live on; the fused decode used by
+    the detection path is inside odk_detect."""
+    ycenter_a = (anchors[:, 0] + anchors[:, 2]) / 2
+    xcenter_a = (anchors[:, 1] + anchors[:, 3]) / 2
+    ha = anchors[:, 2] - anchors[:, 0]
+    wa = anchors[:, 3] - anchors[:, 1]
+    ty, tx, th, tw = rel_codes.unbind(dim=1)
+    w = torch.exp(tw) * wa
+    h = torch.exp(th) * ha
+    yc = ty * ha + ycenter_a
+    xc = tx * wa + xcenter_a
+    ymin, xmin, ymax, xmax = yc - h / 2., xc - w / 2., yc + h / 2., xc + w / 2.
+    order = [xmin, ymin, xmax, ymax] if output_xyxy else [ymin, xmin, ymax, xmax]
+    return torch.stack(order, dim=1)
+
+
+def clip_boxes_xyxy(boxes: torch.Tensor, size: torch.Tensor):
+    """Clamp xyxy boxes to [0, size] (reference effdet/anchors.py:88-92)."""
+    return boxes.clamp(min=0).min(torch.cat([size, size], dim=0))
+
+
+def detect_batch(cls_topk, box_topk, anchor_boxes, indices, classes, img_scale=None, img_size=None,
+                 max_det_per_image: int = 100, soft_nms: bool = False):
+    """Batched odk_detect: -> dets [B, D, 6] zero padded, count [B] int32, src [B, D] int32."""
+    lib = _lib.lib()
+    _lib.require_cuda(cls_topk, 'cls_outputs')
+    dev = cls_topk.device
+    B, N = indices.shape[0], indices.shape[1]
+    cls_topk = cls_topk.reshape(B, N).float().contiguous()
+    box_topk = box_topk.reshape(B, N, 4).float().contiguous()
+    indices = indices.to(torch.int64).contiguous()
+    classes = classes.to(torch.int64).contiguous()
+    anchor_boxes = anchor_boxes.to(dev, torch.float32).contiguous()
+    D = int(max_det_per_image)
+    dets = torch.empty((B, D, 6), dtype=torch.float32, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    src = torch.empty((B, D), dtype=torch.int32, device=dev)
+    scale = None if img_scale is None else img_scale.to(dev, torch.float32).reshape(B).contiguous()
+    size = None if img_size is None else img_size.to(dev, torch.float32).reshape(B, 2).contiguous()
+    params = _lib.DetectParams(D, int(bool(soft_nms)), float(np.float32(0.01)), 0.3, 0.5, 0.3, float(np.float32(0.001)))
+    with torch.cuda.device(dev):
+        _lib.check(lib.odk_detect(_lib.ptr(cls_topk), _lib.ptr(box_topk), _lib.ptr(indices), _lib.ptr(classes), B, N,
+                                  _lib.ptr(anchor_boxes), anchor_boxes.shape[0], _lib.ptr(scale), _lib.ptr(size),
+                                  params, _lib.ptr(dets), _lib.ptr(count), _lib.ptr(src), _lib.stream_ptr(dev)))
+    return dets, count, src
+
+
+def generate_detections(cls_outputs, box_outputs, anchor_boxes, indices, classes,
+                        img_scale: Optional[torch.Tensor], img_size: Optional[torch.Tensor],
+                        max_det_per_image: int = 100, soft_nms: bool = False):
+    """One image's detections [n <= max_det, 6] = x0, y0, x1, y1, score, class (1-based).
+
+    Same contract as the reference (effdet/anchors.py:95-172): inputs are the per-image slices of
+    ``_post_process``; rows are NOT padded.  The row count is data dependent, so this call reads
+    one int back from the device (the reference syncs several times per image)."""
+    assert box_outputs.shape[-1] == 4
+    assert anchor_boxes.shape[-1] == 4
+    assert cls_outputs.shape[-1] == 1
+    scale = None if img_scale is None else img_scale.reshape(1)
+    size = None if img_size is None else img_size.reshape(1, 2)
+    dets, count, _ = detect_batch(cls_outputs.reshape(1, -1), box_outputs.reshape(1, -1, 4), anchor_boxes,
+                                  indices.reshape(1, -1), classes.reshape(1, -1), scale, size,
+                                  max_det_per_image, soft_nms)
+    return dets[0, :int(count.item())]

@@ -1,0 +1,126 @@
+// Shared host/device helpers for libodk (sm_100a).  See include/odk.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/odk.h"
+
+namespace odk {
+
+// Pyramid geometry, passed by value to kernels (fits the 4 KB param space easily).
+struct Geo {
+    int nlev;
+    int na;                         // anchors per location
+    int hw[ODK_MAX_LEVELS];         // H_l * W_l
+    int off[ODK_MAX_LEVELS + 1];    // na * sum_{l'<l} hw[l']  (same base in reference and planar order)
+    int A;                          // anchors per image
+    int Apad;                       // planar per-image stride (A rounded up to 4)
+};
+
+int set_error(int code, const char *fmt, ...);
+int check_launch(const char *what);
+int make_geo(Geo *g, const int32_t *level_hw, int num_levels, int na);
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// planar index p (off_l + a*HW + s) -> level, and reference index r (off_l + s*na + a)
+__device__ __forceinline__ int geo_level(const Geo &g, int idx) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < ODK_MAX_LEVELS; ++i)
+        if (i < g.nlev && idx >= g.off[i]) l = i;
+    return l;
+}
+__device__ __forceinline__ int planar_to_ref(const Geo &g, int p, int &l) {
+    l = geo_level(g, p);
+    int loc = p - g.off[l];
+    int a = loc / g.hw[l];
+    int s = loc - a * g.hw[l];
+    return g.off[l] + s * g.na + a;
+}
+__device__ __forceinline__ int ref_to_planar(const Geo &g, int r, int &l) {
+    l = geo_level(g, r);
+    int loc = r - g.off[l];
+    int s = loc / g.na;
+    int a = loc - s * g.na;
+    return g.off[l] + a * g.hw[l] + s;
+}
+
+// IoU exactly as the reference forms it (region_similarity_calculator.py:48-73): separately
+// rounded fp32 ops, no FMA contraction, IEEE division.  g/a are yxyx.
+__device__ __forceinline__ float iou_ref(float gy0, float gx0, float gy1, float gx1, float garea, float ay0,
+                                         float ax0, float ay1, float ax1, float aarea) {
+    float h = fmaxf(__fsub_rn(fminf(gy1, ay1), fmaxf(gy0, ay0)), 0.0f);
+    float w = fmaxf(__fsub_rn(fminf(gx1, ax1), fmaxf(gx0, ax0)), 0.0f);
+    float inter = __fmul_rn(h, w);
+    if (inter == 0.0f) return 0.0f;
+    float uni = __fsub_rn(__fadd_rn(garea, aarea), inter);
+    return __fdiv_rn(inter, uni);
+}
+__device__ __forceinline__ float area_ref(float y0, float x0, float y1, float x1) {
+    return __fmul_rn(__fsub_rn(y1, y0), __fsub_rn(x1, x0));
+}
+
+// Faster-RCNN encode of gt box g against anchor a (box_list.py:152-164, box_coder.py:92-110).
+__device__ __forceinline__ float4 encode_ref(float4 g, float4 a) {
+    const float eps = 1e-8f;
+    float wa = __fsub_rn(a.w, a.y), ha = __fsub_rn(a.z, a.x);
+    float yca = __fadd_rn(a.x, __fdiv_rn(ha, 2.0f)), xca = __fadd_rn(a.y, __fdiv_rn(wa, 2.0f));
+    float w = __fsub_rn(g.w, g.y), h = __fsub_rn(g.z, g.x);
+    float yc = __fadd_rn(g.x, __fdiv_rn(h, 2.0f)), xc = __fadd_rn(g.y, __fdiv_rn(w, 2.0f));
+    ha = __fadd_rn(ha, eps); wa = __fadd_rn(wa, eps); h = __fadd_rn(h, eps); w = __fadd_rn(w, eps);
+    float4 t;
+    t.x = __fdiv_rn(__fsub_rn(yc, yca), ha);
+    t.y = __fdiv_rn(__fsub_rn(xc, xca), wa);
+    t.z = logf(__fdiv_rn(h, ha));
+    t.w = logf(__fdiv_rn(w, wa));
+    return t;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// streaming 128-bit load: read once, do not pollute L1
+__device__ __forceinline__ float4 ld_stream4(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream1(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream4(float *p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream1(float *p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+#endif  // __CUDACC__
+}  // namespace odk

@@ -1,0 +1,192 @@
+"""GPU parity: odk_assign / odk_targets / odk_loss (through the effdet-API shims and the C ABI)
+against the CPU oracle and the reference goldens.  Bars: assignments / class targets /
+num_positives bit-exact; encoded boxes, losses and gradients within 1e-5 relative (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def make_labeler(size, scale=4.0, num_classes=90, thr=0.5):
+    from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
+    anc = Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size)).to(dev())
+    return anc, AnchorLabeler(anc, num_classes, match_threshold=thr)
+
+
+def flat_targets(cls_t, box_t):
+    B = cls_t[0].shape[0]
+    c = torch.cat([t.reshape(B, -1) for t in cls_t], 1).cpu().numpy()
+    b = torch.cat([t.reshape(B, -1, 4) for t in box_t], 1).cpu().numpy()
+    return c, b
+
+
+def check_against_oracle(anc, lab, gb_list, gc_list, **kw):
+    gbt = [torch.from_numpy(np.asarray(b, np.float32).reshape(-1, 4)).to(dev()) for b in gb_list]
+    gct = [torch.from_numpy(np.asarray(c)).to(dev()) for c in gc_list]
+    cls_t, box_t, npos = lab.batch_label_anchors(gbt, gct, **kw)
+    assert cls_t[0].dtype == torch.int64 and box_t[0].dtype == torch.float32
+    c, b = flat_targets(cls_t, box_t)
+    oc, ob, onp, _, ocls = orc.batch_label_anchors(anc.boxes.cpu().numpy(), gb_list, gc_list,
+                                                    match_threshold=lab.match_threshold, **kw)
+    np.testing.assert_array_equal(c, oc)
+    np.testing.assert_array_equal(npos.cpu().numpy(), onp)
+    assert ((b != 0) == (ob != 0)).all()
+    np.testing.assert_allclose(b, ob, rtol=RTOL, atol=1e-7)
+    return c, b, npos, gct
+
+
+@pytest.mark.parametrize('tag,kw', [('empty', {}), ('zero_iou', {}), ('identical', {}), ('tiny', {}),
+                                    ('padded_float', {}), ('collide', {}), ('nofilter', {'filter_valid': False})])
+def test_labeler_kat(golden, tag, kw):
+    g = golden('labeler')
+    anc, lab = make_labeler(512)
+    c, b, npos, _ = check_against_oracle(anc, lab, [g[f'kat_{tag}_boxes']], [g[f'kat_{tag}_classes']], **kw)
+    pos = np.nonzero(c[0] != -1)[0]
+    np.testing.assert_array_equal(pos, g[f'kat_{tag}_pos_idx'])
+    np.testing.assert_array_equal(c[0][pos], g[f'kat_{tag}_pos_cls'])
+    np.testing.assert_allclose(b[0][pos], g[f'kat_{tag}_pos_box'], rtol=RTOL, atol=1e-7)
+    np.testing.assert_array_equal(npos.cpu().numpy(), g[f'kat_{tag}_npos'])
+
+
+@pytest.mark.parametrize('tag,size,m,seed,integer', [('r256_m10', 256, 10, 11, False), ('r256_m100', 256, 100, 12, False),
+                                                     ('r256_int', 256, 24, 13, True), ('r512_m10', 512, 10, 14, False)])
+def test_labeler_golden_dense_tensor_input(golden, tag, size, m, seed, integer):
+    """[B, M, 4] / [B, M] tensor input with -1 padded classes (the collate format)."""
+    g = golden('labeler')
+    anc, lab = make_labeler(size)
+    gb, _ = synth.gt_boxes(seed, 3, size, m, 90, integer=integer)
+    gc = g[f'{tag}_gc']
+    cls_t, box_t, npos = lab.batch_label_anchors(torch.from_numpy(gb).to(dev()), torch.from_numpy(gc).to(dev()))
+    c, b = flat_targets(cls_t, box_t)
+    np.testing.assert_array_equal(c, g[f'{tag}_cls'].astype(np.int64))
+    np.testing.assert_array_equal(npos.cpu().numpy(), g[f'{tag}_npos'])
+    np.testing.assert_allclose(b, g[f'{tag}_box'], rtol=RTOL, atol=1e-7)
+    assert ((b != 0) == (g[f'{tag}_box'] != 0)).all()
+
+
+@pytest.mark.parametrize('thr', [0.4, 0.7])
+def test_labeler_thresholds(golden, thr):
+    g = golden('labeler')
+    anc, lab = make_labeler(256, thr=thr)
+    gb, gc = synth.gt_boxes(15, 2, 256, 20, 90)
+    c, b, npos, _ = check_against_oracle(anc, lab, list(gb), list(gc))
+    np.testing.assert_array_equal(c, g[f'thr{int(thr * 10)}_cls'].astype(np.int64))
+
+
+def test_labeler_task_cls(golden):
+    g = golden('labeler')
+    anc, lab = make_labeler(256)
+    c, b, npos, gct = check_against_oracle(anc, lab, list(g['task_boxes']), list(g['task_classes_in']), task_cls=5)
+    np.testing.assert_array_equal(gct[0].cpu().numpy(), g['task_classes_out'][0])  # mutated in place like the reference
+    np.testing.assert_array_equal(c, g['task_cls'].astype(np.int64))
+
+
+@pytest.mark.parametrize('name,B,m', [('d0', 4, 10), ('d0', 2, 100), ('d3', 2, 37), ('d7', 2, 100)])
+def test_labeler_model_shapes(name, B, m):
+    """Full-size anchor tables, ragged lists incl. an empty image and degenerate boxes."""
+    size, scale = synth.MODEL_SHAPES[name]
+    anc, lab = make_labeler(size, scale)
+    gb, gc = synth.gt_boxes(900 + B + m, B, size, m, 90)
+    gbl, gcl = [gb[i] for i in range(B)], [gc[i] for i in range(B)]
+    gbl[0], gcl[0] = gbl[0][:0], gcl[0][:0]                      # no gt at all
+    gbl[1] = gbl[1].copy()
+    gbl[1][0] = [10, 10, 10, 10]                                 # zero-area box -> forced onto anchor 0
+    gbl[1][1] = [size * 4, size * 4, size * 5, size * 5]         # outside the image
+    check_against_oracle(anc, lab, gbl, gcl)
+
+
+def test_target_assigner_api():
+    """effdet.object_detection API: arbitrary anchor BoxList through TargetAssigner.assign."""
+    from ood_object_detection_b200.object_detection import BoxList
+    anc, lab = make_labeler(256)
+    gb, gc = synth.gt_boxes(77, 1, 256, 9, 90)
+    cls_t, reg_t, match = lab.target_assigner.assign(BoxList(anc.boxes), BoxList(torch.from_numpy(gb[0]).to(dev())),
+                                                     torch.from_numpy(gc[0]).to(dev()))
+    oc, ob, onp, om, _ = orc.batch_label_anchors(anc.boxes.cpu().numpy(), [gb[0]], [gc[0]])
+    np.testing.assert_array_equal(match.match_results.cpu().numpy(), om[0])
+    np.testing.assert_array_equal(cls_t.cpu().numpy() - 1, oc[0])
+    np.testing.assert_allclose(reg_t.cpu().numpy(), ob[0], rtol=RTOL, atol=1e-7)
+    sim = lab.target_assigner._similarity_calc.compare(BoxList(torch.from_numpy(gb[0]).to(dev())), BoxList(anc.boxes))
+    np.testing.assert_array_equal(sim.cpu().numpy(), orc.iou_matrix(gb[0], anc.boxes.cpu().numpy()))
+    with pytest.raises(ValueError):
+        BoxList(torch.zeros(3, 5))
+    with pytest.raises(ValueError):
+        lab.target_assigner.assign(anc.boxes, BoxList(anc.boxes))
+
+
+# ------------------------------------------------------------------------------------------ loss
+def t(x, grad=False):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev()).requires_grad_(grad)
+
+
+LOSS_TAGS = ['new_c90', 'new_c1', 'new_smooth', 'legacy', 'legacy_g0', 'new_256']
+
+
+@pytest.mark.parametrize('tag', LOSS_TAGS)
+def test_loss_golden(golden, tag):
+    """loss_fn on reference-layout targets vs the reference's own values and autograd grads."""
+    from ood_object_detection_b200.loss import loss_fn
+    from test_oracle_golden import loss_case
+    g = golden('loss')
+    c = loss_case(g, tag)
+    co, bo = [t(x, True) for x in c['co']], [t(x, True) for x in c['bo']]
+    cls_t, box_t = [t(x) for x in c['cls_t']], [t(x) for x in c['box_t']]
+    tot, cl, bl = loss_fn(co, bo, cls_t, box_t, t(c['npos']), c['C'], c['alpha'], c['gamma'], c['delta'], c['w'],
+                          c['sm'], c['legacy'])
+    np.testing.assert_allclose([tot.item(), cl.item(), bl.item()], g[f'{tag}_loss'], rtol=RTOL)
+    tot.backward()
+    _, _, _, ogc, ogb = orc.loss_fn(c['co'], c['bo'], c['cls_t'], c['box_t'], c['npos'], c['C'], c['alpha'], c['gamma'],
+                                    c['delta'], c['w'], c['sm'], c['legacy'], want_grad=True)
+    for l in range(5):
+        np.testing.assert_allclose(bo[l].grad.cpu().numpy(), g[f'{tag}_gbox{l}'], rtol=RTOL, atol=1e-9)
+        np.testing.assert_allclose(co[l].grad.cpu().numpy(), ogc[l], rtol=2e-5, atol=1e-9)
+        if f'{tag}_gcls{l}' in g:
+            np.testing.assert_allclose(co[l].grad.cpu().numpy(), g[f'{tag}_gcls{l}'], rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize('name,B,C,m,legacy,sm', [('d0', 4, 90, 10, False, 0.0), ('d0', 2, 20, 30, True, 0.0),
+                                                  ('d0', 2, 7, 10, False, 0.1), ('d3', 2, 90, 20, False, 0.0),
+                                                  ('d0', 3, 1, 10, False, 0.0)])
+def test_loss_fused_vs_oracle(name, B, C, m, legacy, sm):
+    """labeler + fused loss (targets never materialised) == oracle labeler + oracle loss, and
+    == our own unfused path; D3's 7x7 level exercises the scalar (HW % 4 != 0) code path."""
+    from ood_object_detection_b200.loss import loss_fn, loss_fn_fused
+    size, scale = synth.MODEL_SHAPES[name]
+    anc, lab = make_labeler(size, scale, C)
+    gb, gc = synth.gt_boxes(300 + B + C, B, size, m, C)
+    co_np, bo_np = synth.head_outputs(400 + B + C, B, size, C, tie_free=False)
+    kw = dict(num_classes=C, alpha=0.25, gamma=1.5, delta=0.1, box_loss_weight=50.0, label_smoothing=sm, legacy_focal=legacy)
+    oc, ob, onp, _, _ = orc.batch_label_anchors(anc.boxes.cpu().numpy(), list(gb), list(gc))
+    fhw = synth.feat_hw(size)
+    ref = orc.loss_fn(co_np, bo_np, orc.split_levels(oc, fhw), orc.split_levels(ob, fhw), onp, C, 0.25, 1.5, 0.1, 50.0,
+                      sm, legacy, want_grad=True)
+    co, bo = [t(x, True) for x in co_np], [t(x, True) for x in bo_np]
+    lb = lab.assign(torch.from_numpy(gb).to(dev()), torch.from_numpy(gc).to(dev()))
+    tot, cl, bl = loss_fn_fused(co, bo, lb, **kw)
+    np.testing.assert_allclose([tot.item(), cl.item(), bl.item()], ref[:3], rtol=RTOL)
+    (tot * 2.0).backward()                      # upstream gradient != 1 exercises odk_scale_inplace
+    for l in range(5):
+        np.testing.assert_allclose(co[l].grad.cpu().numpy(), 2.0 * ref[3][l], rtol=2e-5, atol=1e-9)
+        np.testing.assert_allclose(bo[l].grad.cpu().numpy(), 2.0 * ref[4][l], rtol=2e-5, atol=1e-9)
+    # unfused path on materialised targets gives the same numbers
+    cls_t, box_t = lb.targets()
+    with torch.no_grad():
+        tot2, cl2, bl2 = loss_fn([x.detach() for x in co], [x.detach() for x in bo], cls_t, box_t, lb.num_positives, **kw)
+    np.testing.assert_allclose([tot2.item(), cl2.item(), bl2.item()], [tot.item(), cl.item(), bl.item()], rtol=1e-6)
+
+
+def test_loss_requires_cuda():
+    from ood_object_detection_b200.loss import loss_fn
+    x = [torch.zeros(1, 9, 4, 4)]
+    with pytest.raises(RuntimeError):
+        loss_fn(x, [torch.zeros(1, 36, 4, 4)], [torch.zeros(1, 4, 4, 9, dtype=torch.long)], [torch.zeros(1, 4, 4, 36)],
+                torch.ones(1), 1, 0.25, 1.5, 0.1, 50.0)
