@@ -1,0 +1,189 @@
+"""Task benches with the reference's API (effdet/bench.py), post-processing on libodk.
+
+``_post_process`` (reference :12-56), ``_batch_detection`` (:59-76), ``DetBenchPredict`` (:79-103),
+``DetBenchTrain`` (:106-145) and ``unwrap_bench`` (:148-156) keep their signatures.  The level
+concat/permute copy, ``torch.topk`` and the gathers become one odk_topk call that reads the NCHW
+head outputs in place; the per-image python loop of ``_batch_detection`` becomes one odk_detect
+launch (one CTA per image).  ``DetBenchTrain`` with its own labeler never materialises the target
+tensors: odk_assign's ``match`` feeds the fused loss directly.
+"""
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .anchors import Anchors, AnchorLabeler, detect_batch, generate_detections  # noqa: F401
+from .loss import DetectionLoss
+from .ood import ood_scores
+
+
+def _prep_levels(outputs, num_levels):
+    outs = []
+    for t in outputs[:num_levels]:
+        _lib.require_cuda(t, 'head output')
+        if t.dtype != torch.float32:
+            t = t.float()
+        outs.append(t if t.is_contiguous() else t.contiguous())
+    return outs
+
+
+def _post_process(
+        cls_outputs: List[torch.Tensor],
+        box_outputs: List[torch.Tensor],
+        num_levels: int,
+        num_classes: int,
+        max_detection_points: int = 5000,
+):
+    """Top-k over all levels' class logits.
+
+    cls_outputs[l] [B, na*C, H_l, W_l], box_outputs[l] [B, na*4, H_l, W_l] (NCHW head outputs).
+    Returns (cls [B, K, 1] selected logits, box [B, K, 4], indices [B, K] int64 anchor index,
+    classes [B, K] int64), sorted by descending logit like ``torch.topk``; ties are broken by
+    ascending flat index (the reference leaves their order unspecified).
+    """
+    lib = _lib.lib()
+    cls_l = _prep_levels(cls_outputs, num_levels)
+    box_l = _prep_levels(box_outputs, num_levels)
+    dev = cls_l[0].device
+    B = cls_l[0].shape[0]
+    na = box_l[0].shape[1] // 4
+    K = int(max_detection_points)
+    hw = [c.shape[2] * c.shape[3] for c in cls_l]
+    total = na * sum(hw) * num_classes
+    if K > total:
+        raise RuntimeError(f'selected index k out of range (k={K}, A*C={total})')
+    cls_k = torch.empty((B, K, 1), dtype=torch.float32, device=dev)
+    box_k = torch.empty((B, K, 4), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, K), dtype=torch.int64, device=dev)
+    klass = torch.empty((B, K), dtype=torch.int64, device=dev)
+    ws_bytes = lib.odk_topk_workspace_bytes(B, K)
+    ws = torch.empty(((ws_bytes + 15) // 16 * 2,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.odk_topk(_lib.ptr_array(cls_l), _lib.ptr_array(box_l), B, int(num_classes), _lib.int_array(hw),
+                                num_levels, na, K, _lib.ptr(cls_k), _lib.ptr(box_k), _lib.ptr(idx), _lib.ptr(klass),
+                                _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr(dev)))
+    return cls_k, box_k, idx, klass
+
+
+def _batch_detection(
+        batch_size: int, class_out, box_out, anchor_boxes, indices, classes,
+        img_scale: Optional[torch.Tensor] = None,
+        img_size: Optional[torch.Tensor] = None,
+        max_det_per_image: int = 100,
+        soft_nms: bool = False,
+        pad: bool = False,
+):
+    """Detections for a batch -> [B, max_det, 6].
+
+    The reference stacks the per-image results and therefore raises when an image yields fewer
+    than ``max_det_per_image`` rows (bench.py:76, padding is disabled at anchors.py:167-171);
+    that behaviour is kept.  ``pad=True`` (extension) returns zero-padded rows instead and skips
+    the device->host count check."""
+    dets, count, _ = detect_batch(class_out[:batch_size], box_out[:batch_size], anchor_boxes, indices[:batch_size],
+                                  classes[:batch_size], img_scale, img_size, max_det_per_image, soft_nms)
+    if not pad and int(count.min().item()) < max_det_per_image:
+        raise RuntimeError('stack expects each tensor to be equal size: an image produced fewer than '
+                           f'max_det_per_image={max_det_per_image} detections (use pad=True for zero padding)')
+    return dets
+
+
+class DetBenchPredict(nn.Module):
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+        self.config = model.config
+        self.num_levels = model.config.num_levels
+        self.num_classes = model.config.num_classes
+        self.anchors = Anchors.from_config(model.config)
+        self.max_detection_points = model.config.max_detection_points
+        self.max_det_per_image = model.config.max_det_per_image
+        self.soft_nms = model.config.soft_nms
+        self.pad_detections = False
+
+    def forward(self, x, img_info: Optional[Dict[str, torch.Tensor]] = None):
+        class_out, box_out = self.model(x)
+        class_out, box_out, indices, classes = _post_process(
+            class_out, box_out, num_levels=self.num_levels, num_classes=self.num_classes,
+            max_detection_points=self.max_detection_points)
+        if img_info is None:
+            img_scale, img_size = None, None
+        else:
+            img_scale, img_size = img_info['img_scale'], img_info['img_size']
+        return _batch_detection(
+            x.shape[0], class_out, box_out, self.anchors.boxes, indices, classes,
+            img_scale, img_size, max_det_per_image=self.max_det_per_image, soft_nms=self.soft_nms,
+            pad=self.pad_detections)
+
+    def forward_with_ood(self, x, img_info: Optional[Dict[str, torch.Tensor]] = None, temperature: float = 1.0):
+        """Extension (north_star piece 4): padded detections plus per-detection energy / max-logit."""
+        class_out_l, box_out_l = self.model(x)
+        return detect_with_ood(class_out_l, box_out_l, self.anchors.boxes, self.num_levels, self.num_classes,
+                               self.max_detection_points, self.max_det_per_image, self.soft_nms,
+                               None if img_info is None else img_info['img_scale'],
+                               None if img_info is None else img_info['img_size'], temperature)
+
+
+def detect_with_ood(cls_outputs, box_outputs, anchor_boxes, num_levels, num_classes, max_detection_points=5000,
+                    max_det_per_image=100, soft_nms=False, img_scale=None, img_size=None, temperature=1.0):
+    """Whole post-process in four launches: top-k -> detections -> OOD scores.
+
+    Returns dict(detections [B, D, 6] zero padded, count [B] int32, energy [B, D], max_logit [B, D]);
+    OOD scores are computed over the C raw logits of each detection's source anchor."""
+    cls_k, box_k, idx, klass = _post_process(cls_outputs, box_outputs, num_levels, num_classes, max_detection_points)
+    dets, count, src = detect_batch(cls_k, box_k, anchor_boxes, idx, klass, img_scale, img_size, max_det_per_image,
+                                    soft_nms)
+    anchor_of_det = torch.gather(idx, 1, src.clamp(min=0).long())
+    anchor_of_det = torch.where(src >= 0, anchor_of_det, torch.full_like(anchor_of_det, -1))
+    energy, max_logit = ood_scores(cls_outputs, anchor_of_det, num_levels, num_classes, temperature)
+    return {'detections': dets, 'count': count, 'energy': energy, 'max_logit': max_logit, 'anchor': anchor_of_det}
+
+
+class DetBenchTrain(nn.Module):
+    def __init__(self, model, create_labeler=True):
+        super().__init__()
+        self.model = model
+        self.config = model.config
+        self.num_levels = model.config.num_levels
+        self.num_classes = model.config.num_classes
+        self.anchors = Anchors.from_config(model.config)
+        self.max_detection_points = model.config.max_detection_points
+        self.max_det_per_image = model.config.max_det_per_image
+        self.soft_nms = model.config.soft_nms
+        self.anchor_labeler = None
+        if create_labeler:
+            self.anchor_labeler = AnchorLabeler(self.anchors, self.num_classes, match_threshold=0.5)
+        self.loss_fn = DetectionLoss(model.config)
+        self.pad_detections = False
+
+    def forward(self, x, target: Dict[str, torch.Tensor]):
+        class_out, box_out = self.model(x)
+        if self.anchor_labeler is None:
+            # target should contain pre-computed anchor labels if labeler not present in bench
+            assert 'label_num_positives' in target
+            cls_targets = [target[f'label_cls_{l}'] for l in range(self.num_levels)]
+            box_targets = [target[f'label_bbox_{l}'] for l in range(self.num_levels)]
+            num_positives = target['label_num_positives']
+            loss, class_loss, box_loss = self.loss_fn(class_out, box_out, cls_targets, box_targets, num_positives)
+        else:
+            label_batch = self.anchor_labeler.assign(target['bbox'], target['cls'])
+            loss, class_loss, box_loss = self.loss_fn.forward_fused(class_out, box_out, label_batch)
+        output = {'loss': loss, 'class_loss': class_loss, 'box_loss': box_loss}
+        if not self.training:
+            class_out_pp, box_out_pp, indices, classes = _post_process(
+                class_out, box_out, num_levels=self.num_levels, num_classes=self.num_classes,
+                max_detection_points=self.max_detection_points)
+            output['detections'] = _batch_detection(
+                x.shape[0], class_out_pp, box_out_pp, self.anchors.boxes, indices, classes,
+                target['img_scale'], target['img_size'],
+                max_det_per_image=self.max_det_per_image, soft_nms=self.soft_nms, pad=self.pad_detections)
+        return output
+
+
+def unwrap_bench(model):
+    """Strip DDP / EMA (``.module``) and bench (``.model``) wrappers."""
+    if hasattr(model, 'module'):
+        return unwrap_bench(model.module)
+    if hasattr(model, 'model'):
+        return unwrap_bench(model.model)
+    return model

@@ -1,0 +1,466 @@
+// Global top-k over [B, A*C] class logits read in place from the NCHW pyramid levels (K3).
+// Replaces _post_process (reference effdet/bench.py:12-56).  See include/odk.h (odk_topk).
+//
+// HBM-bound design: the logits are streamed ONCE.
+//   P0  sample   : ~1/64 of each image (pseudo-random 512-byte units of every channel plane) is
+//                  histogrammed on the top 12 bits of an order-preserving key;
+//   P1  collect  : every CTA derives, from the sample histogram, a threshold bin that keeps
+//                  between K and kCap elements with overwhelming probability, then streams its
+//                  share of the image with 128-bit loads and appends (key, flat index) of the few
+//                  elements above the threshold (~1.5*K per image) to a candidate list;
+//   P2  select   : one CTA per image bitonic-sorts the candidates in shared memory on the 64-bit
+//                  composite key (value desc, flat index asc), emits the top K and gathers the box
+//                  regressions.  If the candidate count is not in [K, kCap] it raises a flag;
+//   P3  exact    : flagged images only (never for i.i.d. logits; e.g. constant inputs): an
+//                  8-CTA thread-block cluster per image runs an exact MSD radix select on the
+//                  composite key (histograms merged through distributed shared memory), collects
+//                  and sorts.  Unflagged clusters exit immediately.
+// Composite key: hi32 = order-preserving map of the fp32 logit, lo32 = ~flat_index, so keys are
+// unique and "largest key first" is torch.topk's order with ties broken by ascending index.
+#include <cooperative_groups.h>
+#include <string.h>
+
+#include "odk_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace odk {
+
+constexpr int kTopkThreads = 256;
+constexpr int kSelThreads = 1024;
+constexpr int kCap = 16384;            // candidate capacity per image (128 KB of 64-bit keys)
+constexpr int kHistBins = 4096;        // top 12 bits of the value key
+constexpr int kSampleShift = 6;        // sample 1 / 64 of the 512-byte units
+constexpr int kSegVec = 1024;          // vec4 units per task segment
+constexpr int kClusterSize = 8;
+constexpr int kRadixBits = 11;
+
+struct TopkArgs {
+    Geo g;
+    const float *cls[ODK_MAX_LEVELS];
+    const float *box[ODK_MAX_LEVELS];
+    int vec[ODK_MAX_LEVELS];      // 4 or 1
+    int nvec[ODK_MAX_LEVELS];     // vector units per plane
+    int nseg[ODK_MAX_LEVELS];     // task segments per plane
+    int task_off[ODK_MAX_LEVELS + 1];
+    int B, C, K, planes;          // planes = na * C channel planes per level
+    long long N;                  // elements per image = A * C
+    unsigned *hist;               // [B][kHistBins]
+    unsigned *cnt;                // [B]
+    unsigned *flag;               // [B]
+    unsigned long long *cand;     // [B][kCap]
+    float *out_val;               // [B][K]
+    float *out_box;               // [B][K][4]
+    long long *out_idx;           // [B][K]
+    long long *out_cls;           // [B][K]
+};
+
+__device__ __forceinline__ unsigned vkey_of(float x) {
+    const unsigned u = __float_as_uint(x);
+    return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float val_of(unsigned k) {
+    const unsigned u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+    return __uint_as_float(u);
+}
+
+struct Task {
+    const float *base;   // first element of the plane
+    int u0, u1;          // vector-unit range of this segment
+    int vec;
+    unsigned fbase;      // flat index of position 0 of this plane: (off_l + a) * C + c
+};
+
+__device__ __forceinline__ Task decode_task(const TopkArgs &A, int b, int t) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < ODK_MAX_LEVELS; ++i)
+        if (i < A.g.nlev && t >= A.task_off[i]) l = i;
+    const int local = t - A.task_off[l];
+    const int ch = local / A.nseg[l];
+    const int sg = local - ch * A.nseg[l];
+    const int a = ch / A.C, c = ch - a * A.C;
+    Task k;
+    k.base = A.cls[l] + ((size_t)b * A.planes + ch) * A.g.hw[l];
+    k.vec = A.vec[l];
+    k.u0 = sg * kSegVec;
+    k.u1 = min(A.nvec[l], k.u0 + kSegVec);
+    k.fbase = (unsigned)(A.g.off[l] + a) * (unsigned)A.C + (unsigned)c;
+    return k;
+}
+
+// Visit every element of a task with the warp; f(value, position_in_plane, active_lane_mask) is
+// called per element (the mask is only meaningful in SAMPLE mode).
+// SAMPLE: only pseudo-randomly chosen warp iterations (1 / 2^kSampleShift of them).
+template <bool SAMPLE, class F>
+__device__ __forceinline__ void visit_task(const Task &k, int t, int lane, F f) {
+    if (k.vec == 4) {
+        if (!SAMPLE) {
+            int u = k.u0 + lane;
+            for (; u + 96 < k.u1; u += 128) {   // 4 independent 128-bit loads in flight per lane
+                const float4 v0 = ld_stream4(k.base + (size_t)u * 4);
+                const float4 v1 = ld_stream4(k.base + (size_t)(u + 32) * 4);
+                const float4 v2 = ld_stream4(k.base + (size_t)(u + 64) * 4);
+                const float4 v3 = ld_stream4(k.base + (size_t)(u + 96) * 4);
+                f(v0.x, u * 4, 0u); f(v0.y, u * 4 + 1, 0u); f(v0.z, u * 4 + 2, 0u); f(v0.w, u * 4 + 3, 0u);
+                f(v1.x, u * 4 + 128, 0u); f(v1.y, u * 4 + 129, 0u); f(v1.z, u * 4 + 130, 0u); f(v1.w, u * 4 + 131, 0u);
+                f(v2.x, u * 4 + 256, 0u); f(v2.y, u * 4 + 257, 0u); f(v2.z, u * 4 + 258, 0u); f(v2.w, u * 4 + 259, 0u);
+                f(v3.x, u * 4 + 384, 0u); f(v3.y, u * 4 + 385, 0u); f(v3.z, u * 4 + 386, 0u); f(v3.w, u * 4 + 387, 0u);
+            }
+            for (; u < k.u1; u += 32) {
+                const float4 v = ld_stream4(k.base + (size_t)u * 4);
+                f(v.x, u * 4, 0u); f(v.y, u * 4 + 1, 0u); f(v.z, u * 4 + 2, 0u); f(v.w, u * 4 + 3, 0u);
+            }
+        } else {
+            for (int u = k.u0; u < k.u1; u += 32) {
+                const unsigned h = ((unsigned)t * 2654435761u) ^ ((unsigned)(u >> 5) * 2246822519u);
+                if (((h >> 13) & ((1u << kSampleShift) - 1u)) != 0u) continue;   // warp-uniform
+                const unsigned mask = __ballot_sync(0xffffffffu, u + lane < k.u1);
+                if (u + lane < k.u1) {
+                    const float4 v = ld_stream4(k.base + (size_t)(u + lane) * 4);
+                    const int s = (u + lane) * 4;
+                    f(v.x, s, mask); f(v.y, s + 1, mask); f(v.z, s + 2, mask); f(v.w, s + 3, mask);
+                }
+            }
+        }
+    } else {
+        for (int u = k.u0; u < k.u1; u += 32) {
+            if (SAMPLE) {
+                const unsigned h = ((unsigned)t * 2654435761u) ^ ((unsigned)(u >> 5) * 2246822519u);
+                if (((h >> 13) & ((1u << kSampleShift) - 1u)) != 0u) continue;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, u + lane < k.u1);
+            if (u + lane < k.u1) f(ld_stream1(k.base + u + lane), u + lane, mask);
+        }
+    }
+}
+
+// ---- P0: sample histogram ----------------------------------------------------------------
+__global__ void __launch_bounds__(kTopkThreads) topk_sample_kernel(const __grid_constant__ TopkArgs A) {
+    __shared__ unsigned s_hist[kHistBins];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < kHistBins; i += kTopkThreads) s_hist[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int W = gridDim.x * (kTopkThreads / 32);
+    const int ntasks = A.task_off[A.g.nlev];
+    for (int t = blockIdx.x * (kTopkThreads / 32) + (threadIdx.x >> 5); t < ntasks; t += W) {
+        const Task k = decode_task(A, b, t);
+        visit_task<true>(k, t, lane, [&](float x, int, unsigned mask) {
+            // aggregate equal bins across the warp first: logits crowd into a few exponent bins
+            const unsigned bin = vkey_of(x) >> 20;
+            const unsigned peers = __match_any_sync(mask, bin);
+            if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
+        });
+    }
+    __syncthreads();
+    unsigned *gh = A.hist + (size_t)b * kHistBins;
+    for (int i = threadIdx.x; i < kHistBins; i += kTopkThreads)
+        if (s_hist[i]) atomicAdd(gh + i, s_hist[i]);
+}
+
+// Threshold bin from the sample histogram: the highest bin t whose suffix count reaches the
+// sample rank m that puts (m - 5*sqrt(m)) * 2^kSampleShift >= K.  Runs in every collect CTA.
+__device__ unsigned pick_threshold(const unsigned *__restrict__ gh, int K, long long N, unsigned *s_scan /*[256]*/) {
+    if (N <= kCap) return 0u;   // everything fits: keep all elements
+    const float kr = (float)K / (float)(1 << kSampleShift);
+    const float rt = 0.5f * (5.0f + sqrtf(25.0f + 4.0f * kr));
+    const unsigned m_target = (unsigned)ceilf(rt * rt) + 1u;
+    // each thread owns 16 consecutive bins, highest bins first
+    const int tid = threadIdx.x;
+    const int hi = kHistBins - 1 - tid * 16;
+    unsigned mine = 0;
+    for (int i = 0; i < 16; ++i) mine += __ldcg(gh + hi - i);
+    s_scan[tid] = mine;
+    __syncthreads();
+    // inclusive scan over threads (thread 0 holds the top bins)
+    for (int o = 1; o < kTopkThreads; o <<= 1) {
+        unsigned v = tid >= o ? s_scan[tid - o] : 0u;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    __shared__ unsigned s_thr;
+    if (tid == 0) s_thr = 0u;   // sample too small to reach the rank: keep everything (flag decides)
+    __syncthreads();
+    const unsigned before = s_scan[tid] - mine;
+    if (before < m_target && s_scan[tid] >= m_target) {
+        unsigned run = before;
+        for (int i = 0; i < 16; ++i) {
+            run += __ldcg(gh + hi - i);
+            if (run >= m_target) { s_thr = (unsigned)(hi - i) << 20; break; }
+        }
+    }
+    __syncthreads();
+    return s_thr;
+}
+
+// ---- P1: single streaming pass, keep elements at or above the threshold bin ---------------
+__global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const __grid_constant__ TopkArgs A) {
+    __shared__ unsigned s_scan[kTopkThreads];
+    const int b = blockIdx.y;
+    const unsigned thr = pick_threshold(A.hist + (size_t)b * kHistBins, A.K, A.N, s_scan);
+    const int lane = threadIdx.x & 31;
+    const int W = gridDim.x * (kTopkThreads / 32);
+    const int ntasks = A.task_off[A.g.nlev];
+    unsigned *cnt = A.cnt + b;
+    unsigned long long *cand = A.cand + (size_t)b * kCap;
+    const unsigned stride = (unsigned)A.planes;
+    for (int t = blockIdx.x * (kTopkThreads / 32) + (threadIdx.x >> 5); t < ntasks; t += W) {
+        const Task k = decode_task(A, b, t);
+        visit_task<false>(k, t, lane, [&](float x, int s, unsigned) {
+            const unsigned vk = vkey_of(x);
+            if (vk >= thr) {
+                const unsigned flat = k.fbase + (unsigned)s * stride;
+                const unsigned pos = atomicAdd(cnt, 1u);
+                if (pos < (unsigned)kCap) cand[pos] = ((unsigned long long)vk << 32) | (unsigned long long)(~flat);
+            }
+        });
+    }
+}
+
+// ---- P2: sort candidates, emit top K + gathers ----------------------------------------------
+__device__ void bitonic_sort_desc(unsigned long long *s, int P) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int hi = lo | j;
+                const unsigned long long x = s[lo], y = s[hi];
+                const bool desc = (lo & k) == 0;
+                if ((x < y) == desc) { s[lo] = y; s[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ void emit_topk(const TopkArgs &A, int b, const unsigned long long *s) {
+    const Geo &g = A.g;
+    for (int q = threadIdx.x; q < A.K; q += blockDim.x) {
+        const unsigned long long key = s[q];
+        const unsigned flat = ~(unsigned)(key & 0xFFFFFFFFull);
+        const int anchor = (int)(flat / (unsigned)A.C);
+        const int c = (int)(flat - (unsigned)anchor * (unsigned)A.C);
+        const size_t o = (size_t)b * A.K + q;
+        A.out_val[o] = val_of((unsigned)(key >> 32));
+        A.out_idx[o] = anchor;      // bench.py:45
+        A.out_cls[o] = c;           // bench.py:46
+        const int l = geo_level(g, anchor);
+        const int loc = anchor - g.off[l];
+        const int sp = loc / g.na, a = loc - sp * g.na;
+        const float *bp = A.box[l] + ((size_t)(b * g.na + a) * 4) * g.hw[l] + sp;
+        float4 r;
+        r.x = __ldg(bp); r.y = __ldg(bp + g.hw[l]); r.z = __ldg(bp + 2 * (size_t)g.hw[l]); r.w = __ldg(bp + 3 * (size_t)g.hw[l]);
+        reinterpret_cast<float4 *>(A.out_box)[o] = r;   // bench.py:48-49
+    }
+}
+
+__device__ void sort_and_emit(const TopkArgs &A, int b, int n, unsigned long long *s) {
+    int P = 2;
+    while (P < n) P <<= 1;
+    const unsigned long long *cand = A.cand + (size_t)b * kCap;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s[i] = i < n ? __ldcg(cand + i) : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(s, P);
+    emit_topk(A, b, s);
+}
+
+__global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const __grid_constant__ TopkArgs A) {
+    extern __shared__ __align__(16) unsigned long long s_keys[];
+    const int b = blockIdx.x;
+    const unsigned n = A.cnt[b];
+    if (n < (unsigned)A.K || n > (unsigned)kCap) {
+        if (threadIdx.x == 0) A.flag[b] = 1u;
+        return;
+    }
+    sort_and_emit(A, b, (int)n, s_keys);
+}
+
+// ---- P3: exact radix select for flagged images (8-CTA cluster per image) ---------------------
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSelThreads)
+topk_exact_kernel(const __grid_constant__ TopkArgs A) {
+    extern __shared__ __align__(16) unsigned long long s_keys[];   // rank 0: sort buffer
+    __shared__ unsigned s_hist[1 << kRadixBits];
+    __shared__ unsigned long long s_prefix;   // decided high bits, already shifted into place
+    __shared__ unsigned s_need;               // rank still to find inside the prefix
+    __shared__ int s_done;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int b = blockIdx.x / kClusterSize;
+    const unsigned rank = cluster.block_rank();
+    if (A.flag[b] == 0u) return;   // uniform across the cluster
+
+    const int lane = threadIdx.x & 31;
+    const int W = kClusterSize * (kSelThreads / 32);
+    const int wid = rank * (kSelThreads / 32) + (threadIdx.x >> 5);
+    const int ntasks = A.task_off[A.g.nlev];
+    const unsigned stride = (unsigned)A.planes;
+    if (threadIdx.x == 0) { s_prefix = 0ull; s_need = (unsigned)A.K; s_done = 0; }
+    unsigned long long lower = 0ull;   // collect every key >= lower
+    int shift = 64;
+    for (int level = 0; level < 6; ++level) {
+        const int bits = shift >= kRadixBits ? kRadixBits : shift;
+        shift -= bits;
+        for (int i = threadIdx.x; i < (1 << kRadixBits); i += kSelThreads) s_hist[i] = 0;
+        cluster.sync();   // also orders the state written by rank 0 in the previous round
+        const unsigned long long prefix = *cluster.map_shared_rank(&s_prefix, 0);
+        const int pshift = shift + bits;
+        for (int t = wid; t < ntasks; t += W) {
+            const Task k = decode_task(A, b, t);
+            visit_task<false>(k, t, lane, [&](float x, int s, unsigned) {
+                const unsigned flat = k.fbase + (unsigned)s * stride;
+                const unsigned long long key = ((unsigned long long)vkey_of(x) << 32) | (unsigned long long)(~flat);
+                const bool in = pshift >= 64 ? true : ((key >> pshift) == (prefix >> pshift));
+                if (in) atomicAdd(&s_hist[(unsigned)(key >> shift) & ((1u << bits) - 1u)], 1u);
+            });
+        }
+        cluster.sync();
+        if (rank == 0) {
+            // merge the 8 histograms into mine through distributed shared memory
+            for (int i = threadIdx.x; i < (1 << kRadixBits); i += kSelThreads) {
+                unsigned v = s_hist[i];
+                for (unsigned r = 1; r < kClusterSize; ++r) v += cluster.map_shared_rank(s_hist, r)[i];
+                s_hist[i] = v;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned need = s_need, run = 0;
+                int bin = (1 << bits) - 1;
+                for (; bin > 0; --bin) {
+                    if (run + s_hist[bin] >= need) break;
+                    run += s_hist[bin];
+                }
+                const unsigned in_bin = s_hist[bin];
+                s_prefix = prefix | ((unsigned long long)bin << shift);
+                s_need = need - run;
+                // everything above the chosen bin plus the bin itself fits -> stop refining
+                const unsigned taken = (unsigned)A.K - need + run;
+                s_done = (taken + in_bin <= (unsigned)kCap) || shift == 0;
+            }
+        }
+        cluster.sync();
+        lower = *cluster.map_shared_rank(&s_prefix, 0);
+        if (*cluster.map_shared_rank(&s_done, 0)) break;
+    }
+    // collect
+    if (rank == 0 && threadIdx.x == 0) A.cnt[b] = 0u;
+    cluster.sync();
+    unsigned long long *cand = A.cand + (size_t)b * kCap;
+    for (int t = wid; t < ntasks; t += W) {
+        const Task k = decode_task(A, b, t);
+        visit_task<false>(k, t, lane, [&](float x, int s, unsigned) {
+            const unsigned flat = k.fbase + (unsigned)s * stride;
+            const unsigned long long key = ((unsigned long long)vkey_of(x) << 32) | (unsigned long long)(~flat);
+            if (key >= lower) {
+                const unsigned pos = atomicAdd(A.cnt + b, 1u);
+                if (pos < (unsigned)kCap) cand[pos] = key;
+            }
+        });
+    }
+    __threadfence();
+    cluster.sync();
+    if (rank == 0) {
+        const unsigned n = *(volatile unsigned *)(A.cnt + b);
+        sort_and_emit(A, b, (int)min(n, (unsigned)kCap), s_keys);
+    }
+    cluster.sync();   // keep peers' shared memory alive until rank 0 is done with DSMEM
+}
+
+static size_t topk_ws_layout(int B, size_t *o_hist, size_t *o_cnt, size_t *o_flag, size_t *o_cand) {
+    size_t off = 0;
+    *o_hist = off; off += (size_t)B * kHistBins * sizeof(unsigned);
+    *o_cnt = off; off += (((size_t)B * sizeof(unsigned)) + 15) & ~(size_t)15;
+    *o_flag = off; off += (((size_t)B * sizeof(unsigned)) + 15) & ~(size_t)15;
+    const size_t zero_bytes = off;
+    *o_cand = off; off += (size_t)B * kCap * sizeof(unsigned long long);
+    (void)zero_bytes;
+    return off;
+}
+
+}  // namespace odk
+
+extern "C" {
+
+size_t odk_topk_workspace_bytes(int B, int K) {
+    (void)K;
+    if (B < 1) return 0;
+    size_t a, b, c, d;
+    return odk::topk_ws_layout(B, &a, &b, &c, &d);
+}
+
+int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B, int C, const int32_t *level_hw,
+             int num_levels, int na, int K, float *cls_topk, float *box_topk, int64_t *indices, int64_t *classes,
+             void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace odk;
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+    TopkArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = make_geo(&a.g, level_hw, num_levels, na);
+    if (rc) return rc;
+    if (!cls_levels || !box_levels || !cls_topk || !box_topk || !indices || !classes)
+        return set_error(ODK_EINVAL, "odk_topk: null pointer");
+    if (B < 1 || C < 1 || K < 1) return set_error(ODK_EINVAL, "odk_topk: B, C, K must be positive");
+    if (B > 65535) return set_error(ODK_EUNSUPPORTED, "odk_topk: batch > 65535");
+    a.N = (long long)a.g.A * C;
+    if (a.N > 0xFFFFFFFFll) return set_error(ODK_EUNSUPPORTED, "odk_topk: A*C does not fit 32 bits");
+    if ((long long)K > a.N) return set_error(ODK_EINVAL, "odk_topk: K=%d exceeds A*C=%lld (selected index k out of range)", K, a.N);
+    if (K > kCap / 2) return set_error(ODK_EUNSUPPORTED, "odk_topk: K > %d not supported", kCap / 2);
+    if ((size_t)B * na * (size_t)C > 0x7fffffffull) return set_error(ODK_EUNSUPPORTED, "odk_topk: B*na*C overflows int");
+    if (((uintptr_t)box_topk | (uintptr_t)workspace) & 15) return set_error(ODK_EINVAL, "odk_topk: box_topk / workspace must be 16-byte aligned");
+    if (!workspace || workspace_bytes < odk_topk_workspace_bytes(B, K))
+        return set_error(ODK_EWORKSPACE, "odk_topk: workspace too small (%zu < %zu)", workspace_bytes, odk_topk_workspace_bytes(B, K));
+    a.B = B; a.C = C; a.K = K; a.planes = na * C;
+    int toff = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        a.cls[l] = (const float *)cls_levels[l];
+        a.box[l] = (const float *)box_levels[l];
+        if (!a.cls[l] || !a.box[l]) return set_error(ODK_EINVAL, "odk_topk: null level pointer (level %d)", l);
+        a.vec[l] = (a.g.hw[l] % 4 == 0 && ((uintptr_t)a.cls[l] & 15) == 0) ? 4 : 1;
+        a.nvec[l] = a.g.hw[l] / a.vec[l];
+        a.nseg[l] = (a.nvec[l] + kSegVec - 1) / kSegVec;
+        a.task_off[l] = toff;
+        toff += a.planes * a.nseg[l];
+    }
+    for (int l = num_levels; l <= ODK_MAX_LEVELS; ++l) a.task_off[l] = toff;
+    size_t o_hist, o_cnt, o_flag, o_cand;
+    topk_ws_layout(B, &o_hist, &o_cnt, &o_flag, &o_cand);
+    char *ws = (char *)workspace;
+    a.hist = (unsigned *)(ws + o_hist); a.cnt = (unsigned *)(ws + o_cnt); a.flag = (unsigned *)(ws + o_flag);
+    a.cand = (unsigned long long *)(ws + o_cand);
+    a.out_val = cls_topk; a.out_box = box_topk; a.out_idx = (long long *)indices; a.out_cls = (long long *)classes;
+
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(ws, 0, o_cand, st);   // histograms, counters, flags
+    if (e != cudaSuccess) return set_error((int)e, "odk_topk memset: %s", cudaGetErrorString(e));
+
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms < 1) sms = 148;
+        cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * 8);
+        cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * 8);
+    }
+    const int warps_per_cta = kTopkThreads / 32;
+    int per_image = (sms * 8 + B - 1) / B;                       // ~8 resident CTAs per SM chip-wide
+    const int max_useful = (toff + warps_per_cta - 1) / warps_per_cta;
+    if (per_image > max_useful) per_image = max_useful;
+    if (per_image < 1) per_image = 1;
+    dim3 grid(per_image, B);
+    if (a.N > kCap) {
+        topk_sample_kernel<<<grid, kTopkThreads, 0, st>>>(a);
+        rc = check_launch("odk_topk/sample");
+        if (rc) return rc;
+    }
+    topk_collect_kernel<<<grid, kTopkThreads, 0, st>>>(a);
+    rc = check_launch("odk_topk/collect");
+    if (rc) return rc;
+    topk_select_kernel<<<B, kSelThreads, kCap * 8, st>>>(a);
+    rc = check_launch("odk_topk/select");
+    if (rc) return rc;
+    topk_exact_kernel<<<B * kClusterSize, kSelThreads, kCap * 8, st>>>(a);
+    return check_launch("odk_topk/exact");
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+"""GPU parity: odk_topk / odk_detect / odk_soft_nms / odk_nms / odk_ood (through the effdet-API shims
+and the C ABI) against the reference goldens and the CPU oracle.  Bars: top-k indices, classes and
+kept-detection order bit-exact; boxes / scores / soft scores / OOD scores within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import oracle as orc
+from test_oracle_golden import PP_TAGS, pp_inputs
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+DEV = 'cuda:0'
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def anchors_t(size, scale=4.0):
+    return t(orc.anchor_boxes(3, 7, 3, synth.ASPECTS, scale, (size, size)))
+
+
+@pytest.mark.parametrize('tag', PP_TAGS)
+def test_post_process_golden(golden, tag):
+    from ood_object_detection_b200.bench import _post_process
+    g = golden('postprocess')
+    size, B, C, K, D, co, bo = pp_inputs(g, tag)
+    cls_k, box_k, idx, klass = _post_process([t(x) for x in co], [t(x) for x in bo], 5, C, K)
+    assert cls_k.shape == (B, K, 1) and idx.dtype == torch.int64 and klass.dtype == torch.int64
+    np.testing.assert_array_equal(idx.cpu().numpy(), g[f'{tag}_idx'].astype(np.int64))
+    np.testing.assert_array_equal(klass.cpu().numpy(), g[f'{tag}_klass'].astype(np.int64))
+    np.testing.assert_array_equal(cls_k.cpu().numpy(), g[f'{tag}_cls'])
+    np.testing.assert_array_equal(box_k.cpu().numpy(), g[f'{tag}_box'])
+
+
+@pytest.mark.parametrize('name,B,C,K,sparse', [('d0', 4, 90, 5000, False), ('d0', 2, 90, 5000, True),
+                                               ('d3', 2, 90, 5000, False), ('d0', 3, 1, 2000, False),
+                                               ('d0', 1, 400, 5000, False)])
+def test_post_process_vs_oracle(name, B, C, K, sparse):
+    from ood_object_detection_b200.bench import _post_process
+    size, _ = synth.MODEL_SHAPES[name]
+    co, bo = (synth.planted_outputs if sparse else synth.head_outputs)(600 + B + C, B, size, C)
+    ref = orc.post_process(co, bo, 5, C, K)
+    got = _post_process([t(x) for x in co], [t(x) for x in bo], 5, C, K)
+    for r, g_ in zip(ref, got):
+        np.testing.assert_array_equal(g_.cpu().numpy(), r)
+
+
+def test_post_process_degenerate_inputs():
+    """Inputs the sampled threshold cannot handle go through the exact radix-select path:
+    all-equal logits (pure index ties), heavily quantised logits, one huge outlier cluster."""
+    from ood_object_detection_b200.bench import _post_process
+    size, B, C, K = 256, 4, 20, 3000
+    co, bo = synth.head_outputs(71, B, size, C, tie_free=False)
+    for c in co:
+        c[0] = -4.5                                            # constant image
+        c[1] = np.round(c[1] * 2) / 2                          # ~20 distinct values
+        c[2] = np.where(c[2] > -4.6, np.float32(1.25), c[2])   # half the image tied at the top
+    ref = orc.post_process(co, bo, 5, C, K)
+    got = _post_process([t(x) for x in co], [t(x) for x in bo], 5, C, K)
+    for r, g_ in zip(ref, got):
+        np.testing.assert_array_equal(g_.cpu().numpy(), r)
+    # sortedness / membership properties on the constant image: first K flat indices
+    flat = got[2][0].cpu().numpy() * C + got[3][0].cpu().numpy()
+    np.testing.assert_array_equal(flat, np.arange(K))
+
+
+def test_post_process_errors():
+    from ood_object_detection_b200.bench import _post_process
+    co, bo = synth.head_outputs(1, 1, 128, 1)
+    with pytest.raises(RuntimeError):
+        _post_process([t(x) for x in co], [t(x) for x in bo], 5, 1, 5000)   # k > A*C like torch.topk
+    with pytest.raises(RuntimeError):
+        _post_process([torch.from_numpy(x) for x in co], [torch.from_numpy(x) for x in bo], 5, 1, 100)   # CPU tensors
+
+
+@pytest.mark.parametrize('tag', PP_TAGS)
+@pytest.mark.parametrize('soft', [False, True])
+@pytest.mark.parametrize('scaled', [False, True])
+def test_generate_detections_golden(golden, tag, soft, scaled):
+    from ood_object_detection_b200.anchors import generate_detections
+    g = golden('postprocess')
+    size, B, C, K, D, co, bo = pp_inputs(g, tag)
+    anc = anchors_t(size)
+    for i in range(B):
+        scale = t(np.float32(1.0 + 0.25 * i)) if scaled else None
+        isz = t(np.array([size * 1.1, size * 0.9], np.float32)) if scaled else None
+        det = generate_detections(t(g[f'{tag}_cls'][i]), t(g[f'{tag}_box'][i]), anc, t(g[f'{tag}_idx'][i].astype(np.int64)),
+                                  t(g[f'{tag}_klass'][i].astype(np.int64)), scale, isz, max_det_per_image=D, soft_nms=soft)
+        ref = g[f'{tag}_det_b{i}_{"soft" if soft else "hard"}{"_scaled" if scaled else ""}']
+        det = det.cpu().numpy()
+        assert det.shape == ref.shape
+        np.testing.assert_array_equal(det[:, 5], ref[:, 5])
+        np.testing.assert_allclose(det[:, :5], ref[:, :5], rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize('soft', [False, True])
+def test_batch_detection_full_chain_vs_oracle(soft):
+    """D0, B=4: _post_process -> _batch_detection (one launch) == oracle per-image chain; kept
+    source positions bit-exact."""
+    from ood_object_detection_b200.anchors import detect_batch
+    from ood_object_detection_b200.bench import _post_process, _batch_detection
+    size, B, C, K, D = 512, 4, 90, 5000, 100
+    co, bo = synth.planted_outputs(81, B, size, C)
+    anc_np = orc.anchor_boxes(3, 7, 3, synth.ASPECTS, 4.0, (size, size))
+    cls_k, box_k, idx, klass = _post_process([t(x) for x in co], [t(x) for x in bo], 5, C, K)
+    dets, count, src = detect_batch(cls_k, box_k, t(anc_np), idx, klass, None, None, D, soft)
+    o_cls, o_box, o_idx, o_klass = orc.post_process(co, bo, 5, C, K)
+    for i in range(B):
+        ref, rsrc = orc.generate_detections(o_cls[i], o_box[i], anc_np, o_idx[i], o_klass[i], None, None, D, soft,
+                                            return_src=True)
+        n = int(count[i].item())
+        assert n == ref.shape[0]
+        np.testing.assert_array_equal(src[i, :n].cpu().numpy(), rsrc)
+        np.testing.assert_allclose(dets[i, :n].cpu().numpy(), ref, rtol=RTOL, atol=1e-6)
+        assert (dets[i, n:] == 0).all() and (src[i, n:] == -1).all()
+    if int(count.min().item()) < D:
+        with pytest.raises(RuntimeError):
+            _batch_detection(B, cls_k, box_k, t(anc_np), idx, klass, max_det_per_image=D, soft_nms=soft)
+    padded = _batch_detection(B, cls_k, box_k, t(anc_np), idx, klass, max_det_per_image=D, soft_nms=soft, pad=True)
+    assert padded.shape == (B, D, 6)
+
+
+def test_generate_detections_unsorted_and_empty():
+    """API inputs need not be sorted (torchvision sorts by score itself) and may all fail the filter."""
+    from ood_object_detection_b200.anchors import generate_detections
+    size, N, C = 256, 700, 12
+    anc_np = orc.anchor_boxes(3, 7, 3, synth.ASPECTS, 4.0, (size, size))
+    rs = np.random.RandomState(5)
+    idx = rs.randint(0, anc_np.shape[0], N).astype(np.int64)
+    klass = rs.randint(0, C, N).astype(np.int64)
+    cls = (rs.standard_normal((N, 1)) * 2.0 - 2.0).astype(np.float32)
+    box = (rs.standard_normal((N, 4)) * 0.3).astype(np.float32)
+    for soft in (False, True):
+        ref = orc.generate_detections(cls, box, anc_np, idx, klass, None, None, 50, soft)
+        got = generate_detections(t(cls), t(box), t(anc_np), t(idx), t(klass), None, None, 50, soft).cpu().numpy()
+        assert got.shape == ref.shape
+        np.testing.assert_array_equal(got[:, 5], ref[:, 5])
+        np.testing.assert_allclose(got[:, :5], ref[:, :5], rtol=RTOL, atol=1e-6)
+        none = generate_detections(t(cls - 20), t(box), t(anc_np), t(idx), t(klass), None, None, 50, soft)
+        assert none.shape == (0, 6)
+
+
+@pytest.mark.parametrize('tag,n,seed,gauss', [('g300', 300, 41, True), ('l300', 300, 42, False), ('g1500', 1500, 43, True)])
+def test_soft_nms_module(golden, tag, n, seed, gauss):
+    from ood_object_detection_b200 import soft_nms as S
+    g = golden('softnms')
+    boxes, scores, classes = synth.nms_candidates(seed, n, 512, 10)
+    i1, s1 = S.soft_nms(t(boxes), t(scores), gauss, 0.5, 0.5, 0.005)
+    np.testing.assert_array_equal(i1.cpu().numpy(), g[f'{tag}_plain_idx'].astype(np.int64))
+    np.testing.assert_allclose(s1.cpu().numpy(), g[f'{tag}_plain_sc'], rtol=RTOL)
+    i2, s2 = S.batched_soft_nms(t(boxes), t(scores), t(classes), gauss, 0.5, 0.3, 0.001)
+    np.testing.assert_array_equal(i2.cpu().numpy(), g[f'{tag}_batched_idx'].astype(np.int64))
+    np.testing.assert_allclose(s2.cpu().numpy(), g[f'{tag}_batched_sc'], rtol=RTOL)
+    np.testing.assert_array_equal(S.batched_nms(t(boxes), t(scores), t(classes), 0.3).cpu().numpy(),
+                                  g[f'{tag}_hard_keep'].astype(np.int64))
+    np.testing.assert_array_equal(S.nms(t(boxes), t(scores), 0.5).cpu().numpy(),
+                                  g[f'{tag}_hard_keep_plain'].astype(np.int64))
+    e_i, e_s = S.batched_soft_nms(t(boxes[:0]), t(scores[:0]), t(classes[:0]))
+    assert e_i.numel() == 0 and e_s.numel() == 0
+
+
+def test_nms_large_vs_oracle():
+    from ood_object_detection_b200 import soft_nms as S
+    boxes, scores, classes = synth.nms_candidates(9, 5000, 896, 90, n_clusters=300)
+    np.testing.assert_array_equal(S.batched_nms(t(boxes), t(scores), t(classes), 0.3).cpu().numpy(),
+                                  orc.batched_nms(boxes, scores, classes, 0.3))
+    i, s = S.batched_soft_nms(t(boxes), t(scores), t(classes), True, 0.5, 0.3, 0.001)
+    oi, os_ = orc.batched_soft_nms(boxes, scores, classes, True, 0.5, 0.3, 0.001)
+    np.testing.assert_array_equal(i.cpu().numpy(), oi)
+    np.testing.assert_allclose(s.cpu().numpy(), os_, rtol=RTOL)
+
+
+def test_ood_scores_and_fused_entry():
+    from ood_object_detection_b200.bench import detect_with_ood
+    size, B, C, K, D = 256, 3, 30, 2000, 40
+    co, bo = synth.planted_outputs(91, B, size, C, n_obj=20)
+    anc_np = orc.anchor_boxes(3, 7, 3, synth.ASPECTS, 4.0, (size, size))
+    out = detect_with_ood([t(x) for x in co], [t(x) for x in bo], t(anc_np), 5, C, K, D, False, temperature=1.0)
+    o_cls, o_box, o_idx, o_klass = orc.post_process(co, bo, 5, C, K)
+    for i in range(B):
+        ref, rsrc = orc.generate_detections(o_cls[i], o_box[i], anc_np, o_idx[i], o_klass[i], None, None, D, False,
+                                            return_src=True)
+        n = int(out['count'][i].item())
+        assert n == ref.shape[0]
+        np.testing.assert_allclose(out['detections'][i, :n].cpu().numpy(), ref, rtol=RTOL, atol=1e-6)
+        anchors_i = o_idx[i][rsrc]
+        np.testing.assert_array_equal(out['anchor'][i, :n].cpu().numpy(), anchors_i)
+        rows = orc.gather_logit_rows(co, anchors_i[None].repeat(B, 0), C)[i]
+        e, m = orc.ood_scores(rows, 1.0)
+        np.testing.assert_allclose(out['energy'][i, :n].cpu().numpy(), e, rtol=RTOL)
+        np.testing.assert_array_equal(out['max_logit'][i, :n].cpu().numpy(), m)
+        assert (out['energy'][i, n:] == 0).all()
+    # temperature and the torch definition
+    from ood_object_detection_b200.ood import ood_scores
+    e2, _ = ood_scores([t(x) for x in co], out['anchor'], 5, C, temperature=2.5)
+    allc = torch.cat([t(c).permute(0, 2, 3, 1).reshape(B, -1, C) for c in co], 1)
+    rows = torch.gather(allc, 1, out['anchor'].clamp(min=0)[:, :, None].expand(-1, -1, C))
+    ref = -2.5 * torch.logsumexp(rows / 2.5, dim=2)
+    ok = out['anchor'] >= 0
+    np.testing.assert_allclose(e2[ok].cpu().numpy(), ref[ok].cpu().numpy(), rtol=RTOL)
