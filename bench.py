@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the dense per-anchor hot path (BASELINE.json metric: images/sec).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload at every N (weak scaling, one process per GPU): BASELINE.json configs[1] --
+EfficientDet-D0 512x512 (49104 anchors, 90 classes), batch 64 per GPU, 10 gt boxes per image,
+training-target path = AnchorLabeler assignment + fused focal/Huber loss (forward, the pass
+the reference's DetBenchTrain.forward runs).  A "step" is one pass of that path over one batch of
+synthetic head outputs; inputs are resident in HBM for `value` (1.18 GB per step, far larger
+than the 126 MB L2, so nothing is served from cache between steps) and start in pinned HOST
+memory for `e2e`.  `--impl reference` times the CPU restatement of the reference path
+(oracle/, OpenMP over all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import numpy as np  # noqa: E402
+
+SIZE, SCALE, NUM_CLASSES, BATCH, NUM_GT = 512, 4.0, 90, 64, 10
+LOSS_KW = dict(num_classes=NUM_CLASSES, alpha=0.25, gamma=1.5, delta=0.1, box_loss_weight=50.0)
+WORKLOAD = 'D0-512 A=49104 C=90 B=64/GPU M=10: AnchorLabeler + fused focal/huber loss (fwd)'
+METRIC = 'images/sec labeler+loss (D0 512x512 batch 64 training-target path)'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# --------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_rate(batch, reps):
+    """images/s of the oracle (CPU restatement of anchors.py:384-438 + loss.py:224-298)."""
+    import synth
+    from oracle import oracle as orc
+    anchors = orc.anchor_boxes(3, 7, 3, synth.ASPECTS, SCALE, (SIZE, SIZE))
+    gb, gc = synth.gt_boxes(7, batch, SIZE, NUM_GT, NUM_CLASSES)
+    co, bo = synth.head_outputs(8, batch, SIZE, NUM_CLASSES, tie_free=False)
+    fhw = synth.feat_hw(SIZE)
+    best = float('inf')
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cls_t, box_t, npos, _, _ = orc.batch_label_anchors(anchors, list(gb), list(gc))
+        orc.loss_fn(co, bo, orc.split_levels(cls_t, fhw), orc.split_levels(box_t, fhw), npos, NUM_CLASSES,
+                    LOSS_KW['alpha'], LOSS_KW['gamma'], LOSS_KW['delta'], LOSS_KW['box_loss_weight'])
+        best = min(best, time.perf_counter() - t0)
+    return batch / best, orc.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    sample_b = 8
+    cpu_reference_rate(sample_b, 1)  # warm (page-in, thread pool)
+    times = []
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_rate(sample_b, 1)
+    t0 = time.perf_counter()
+    threads = 1
+    for _ in range(args.steps):
+        _, threads = cpu_reference_rate(sample_b, 1)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    times.append(dt)
+    value = sample_b / dt
+    sample = f'D0-512 C=90 M=10 labeler+loss fwd on B={sample_b} images per step (of the B=64 workload)'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'reference_sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU every few ms through NVML while running."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, 'nvmlClocksEventReasonHwSlowdown', getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8)): 'hw_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40)): 'hw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20)): 'sw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonSwPowerCap', getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)): 'sw_power_cap',
+        }
+        getter = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = getter(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+# --------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import synth
+    from ood_object_detection_b200 import _lib
+    from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
+    from ood_object_detection_b200.loss import loss_fn_fused
+    from ood_object_detection_b200.distributed import global_normalizer, reduce_losses
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the hot path only exists as sm_100a kernels')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.lib()
+
+    # ---- synthetic inputs of the named shape, generated on the device (SURVEY 8d recipe) ----
+    g = torch.Generator(device=dev)
+    g.manual_seed(1 + rank)
+    anchors = Anchors(3, 7, 3, synth.ASPECTS, SCALE, (SIZE, SIZE)).to(dev)
+    labeler = AnchorLabeler(anchors, NUM_CLASSES, match_threshold=0.5)
+    feat = synth.feat_hw(SIZE)
+    cls_out = [torch.randn((BATCH, 9 * NUM_CLASSES, h, w), generator=g, device=dev) * 1.5 - 4.6 for h, w in feat]
+    box_out = [torch.randn((BATCH, 36, h, w), generator=g, device=dev) * 0.2 for h, w in feat]
+    gb_np, gc_np = synth.gt_boxes(100 + rank, BATCH, SIZE, NUM_GT, NUM_CLASSES)
+    gt_boxes, gt_cls = torch.from_numpy(gb_np).to(dev), torch.from_numpy(gc_np).to(dev)
+    A = anchors.boxes.shape[0]
+    bytes_loss = BATCH * A * (4 * NUM_CLASSES + 16)          # A*(4C+16) bytes per image, forward
+
+    def step(record=None):
+        lb = labeler.assign(gt_boxes, gt_cls)
+        if world > 1:
+            norm = global_normalizer(lb.num_positives)
+        else:
+            norm = None
+        if record is not None:
+            record[0].record()
+        out = loss_fn_fused(cls_out, box_out, lb, normalizer=norm, **LOSS_KW)
+        if record is not None:
+            record[1].record()
+        if world > 1:
+            out = reduce_losses(*out)
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step()
+        sync_all()
+        if sampler:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for i in range(args.steps):
+            last = step(ev[i])
+        t_end.record()
+        sync_all()
+        total_ms = t_start.elapsed_time(t_end)
+        # keep the same load running (untimed) until the sampler has seen the GPU under it
+        if sampler and sampler.ok:
+            t0 = time.time()
+            while len(sampler.samples) < 12 and time.time() - t0 < 2.0:
+                for _ in range(20):
+                    step()
+                torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        loss_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+        # ---- forward + gradient in the same pass (what a training step needs), untimed extra ----
+        co_g = [c.requires_grad_(True) for c in cls_out]
+        bo_g = [b.requires_grad_(True) for b in box_out]
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nfb = max(3, min(args.steps, 10))
+    for i in range(2 + nfb):
+        if i == 2:
+            g0.record()
+        lb = labeler.assign(gt_boxes, gt_cls)
+        tot, _, _ = loss_fn_fused(co_g, bo_g, lb, **LOSS_KW)
+        tot.backward()
+        for t in co_g + bo_g:
+            t.grad = None
+    g1.record()
+    torch.cuda.synchronize()
+    fwd_bwd_ms = g0.elapsed_time(g1) / nfb
+    for t in cls_out + box_out:
+        t.requires_grad_(False)
+
+    tmax = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    ms_per_step = total_ms / args.steps
+    value = world * BATCH / (ms_per_step * 1e-3)
+
+    # ---- e2e: same step through the public API from pinned HOST buffers, loss read back ----
+    with torch.no_grad():
+        h_cls = [c.cpu().pin_memory() for c in cls_out]
+        h_box = [b.cpu().pin_memory() for b in box_out]
+        h_gb, h_gc = gt_boxes.cpu().pin_memory(), gt_cls.cpu().pin_memory()
+        h_out = torch.empty((3,), dtype=torch.float32).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in h_cls + h_box + [h_gb, h_gc])
+
+        def e2e_step():
+            d_cls = [t.to(dev, non_blocking=True) for t in h_cls]
+            d_box = [t.to(dev, non_blocking=True) for t in h_box]
+            lb = labeler.assign(h_gb.to(dev, non_blocking=True), h_gc.to(dev, non_blocking=True))
+            norm = global_normalizer(lb.num_positives) if world > 1 else None
+            out = loss_fn_fused(d_cls, d_box, lb, normalizer=norm, **LOSS_KW)
+            if world > 1:
+                out = reduce_losses(*out)
+            h_out.copy_(torch.stack(list(out)), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return h_out
+
+        e2e_steps = max(2, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        sync_all()
+        e2e_ms = torch.tensor([e0.elapsed_time(e1) / e2e_steps], device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        e2e_value = world * BATCH / (float(e2e_ms.item()) * 1e-3)
+        del h_cls, h_box
+
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        try:
+            extra = postprocess_extra(torch, dev, synth)
+        except Exception as exc:  # the extra block must never take the headline down
+            extra = {'error': repr(exc)}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = bytes_loss / (loss_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get('loss_kernel_dram_bytes_per_launch')
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, threads = cpu_reference_rate(16, 2)
+            cpu = {'value': rate, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                   'sample': 'D0-512 C=90 M=10 labeler+loss fwd, B=16 of the B=64 workload, best of 2 (oracle/, OpenMP)'}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'global_batch': world * BATCH, 'parallelism': f'images sharded x{world}',
+                       'l2': 'inputs (1.18 GB/step) larger than the 126 MB L2; no flush needed',
+                       'loss_out': [float(x) for x in last]},
+            'roofline': {'bound': 'hbm', 'kernel': 'odk::loss_kernel<new,fwd,fused>', 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': bytes_loss, 'kernel_ms': loss_ms},
+            'cpu_baseline': cpu,
+            'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
+                    'steps': e2e_steps},
+            'gpu_launches': 3 * args.steps,
+            'launches_per_step': {'odk::assign_kernel': 1, 'odk::assign_force_kernel': 1, 'odk::loss_kernel': 1,
+                                  'cudaMemsetAsync': 2},
+            'clocks': clocks,
+            'fwd_plus_grad': {'ms_per_step': fwd_bwd_ms, 'images_per_s': BATCH / (fwd_bwd_ms * 1e-3),
+                              'achieved_GBps': 2 * bytes_loss / (fwd_bwd_ms * 1e-3) / 1e9,
+                              'note': 'labeler + loss fwd + d total/d outputs written in the same pass + backward()'},
+            'extra': extra,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def postprocess_extra(torch, dev, synth):
+    """BASELINE.json configs[2] on one GPU (not the headline): D3 896^2 B=32 post-process."""
+    from ood_object_detection_b200.anchors import Anchors, detect_batch
+    from ood_object_detection_b200.bench import _post_process
+    size, scale = synth.MODEL_SHAPES['d3']
+    B, C, K, D = 32, 90, 5000, 100
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    feat = synth.feat_hw(size)
+    cls_out = [torch.randn((B, 9 * C, h, w), generator=g, device=dev) * 1.5 - 4.6 for h, w in feat]
+    box_out = [torch.randn((B, 36, h, w), generator=g, device=dev) * 0.2 for h, w in feat]
+    anchors = Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size)).to(dev)
+    A = anchors.boxes.shape[0]
+    out = {}
+    for soft in (False, True):
+        def step():
+            cls_k, box_k, idx, klass = _post_process(cls_out, box_out, 5, C, K)
+            return detect_batch(cls_k, box_k, anchors.boxes, idx, klass, None, None, D, soft), (cls_k, box_k, idx, klass)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        n = 10
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        tk = 0.0
+        e0.record()
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            pp = _post_process(cls_out, box_out, 5, C, K)
+            b.record()
+            detect_batch(pp[0], pp[1], anchors.boxes, pp[2], pp[3], None, None, D, soft)
+            torch.cuda.synchronize()
+            tk += a.elapsed_time(b)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        peak, _ = peaks()
+        by = B * A * 4 * C
+        out['soft_nms' if soft else 'hard_nms'] = {
+            'workload': f'D3-896 A={A} C=90 B=32 top-{K} + decode + {"soft-" if soft else ""}NMS-{D}',
+            'ms_per_step': ms, 'images_per_s': B / (ms * 1e-3), 'topk_ms': tk / n,
+            'topk_achieved_GBps': by / (tk / n * 1e-3) / 1e9, 'topk_frac_of_peak': by / (tk / n * 1e-3) / 1e9 / peak}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-extra', action='store_true', help='skip the D3 post-process extra block')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -56,7 +56,7 @@ struct TopkArgs {
 };
 
 __device__ __forceinline__ unsigned vkey_of(float x) {
-    const unsigned u = __float_as_uint(x);
+    const unsigned u = __float_as_uint(x + 0.0f);   // -0.0 -> +0.0: they compare equal in torch.topk
     return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
 }
 __device__ __forceinline__ float val_of(unsigned k) {

@@ -1,0 +1,73 @@
+"""Data-parallel use of the dense per-anchor path: images shard across ranks, nothing else moves.
+
+Every stage is independent per image (reference anchors.py:393, bench.py:44,69); the only
+cross-image coupling is the loss normaliser sum(num_positives)+1 (loss.py:261) and the final sums.
+So the sharded path needs two latency-bound collectives (the shapes the reference's own
+``effdet/distributed.py`` helpers would move, evaluator.py:38-39):
+  * all-reduce(sum) of the scalar normaliser before the loss kernel (gradients are scaled by the
+    GLOBAL 1/N inside the same pass), then all-reduce(sum) of the three loss scalars;
+  * all-gather of the padded detections [B_local, D, 6] (+ counts, + OOD scores).
+With these the result equals the single-process reference at the global batch, up to fp32
+summation order.  Works with any initialised ``torch.distributed`` backend (NCCL over NVLink on
+the B200 box, gloo in the CPU tests).
+"""
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def _active(group=None):
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def shard_range(global_batch: int, rank: int, world_size: int):
+    """Images [lo, hi) owned by ``rank`` (contiguous blocks, remainder spread over the first ranks)."""
+    base, rem = divmod(global_batch, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def global_normalizer(num_positives: torch.Tensor, group=None) -> torch.Tensor:
+    """sum over ALL ranks' images of num_positives, + 1 (loss.py:261) -> fp32 [1] on every rank."""
+    local = num_positives.float().sum().reshape(1)
+    if _active(group):
+        dist.all_reduce(local, op=dist.ReduceOp.SUM, group=group)
+    return local + 1.0
+
+
+def reduce_losses(total, cls_loss, box_loss, group=None):
+    """Per-rank partial losses (each already divided by the global normaliser) -> global values."""
+    packed = torch.stack([total.detach().reshape(()), cls_loss.detach().reshape(()), box_loss.detach().reshape(())])
+    if _active(group):
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed[0], packed[1], packed[2]
+
+
+def sharded_detection_loss(loss_module, cls_outputs, box_outputs, label_batch, group=None):
+    """Local shard's fused loss against the GLOBAL normaliser.
+
+    Returns ((total, cls, box) local partials that carry the autograd graph -- their sum over
+    ranks is the global loss, so ``total.backward()`` on every rank yields exactly the gradients
+    of the global loss w.r.t. the local outputs -- and the all-reduced (total, cls, box) for logging)."""
+    norm = global_normalizer(label_batch.num_positives, group)
+    part = loss_module.forward_fused(cls_outputs, box_outputs, label_batch, normalizer=norm)
+    return part, reduce_losses(*part, group=group)
+
+
+def gather_detections(dets: torch.Tensor, count: torch.Tensor, extras: Optional[List[torch.Tensor]] = None, group=None):
+    """all-gather of the padded per-image results in rank order (equal B_local on every rank).
+
+    dets [B_local, D, 6], count [B_local]; extras: further [B_local, ...] tensors (e.g. OOD scores).
+    Returns the same list of tensors with leading dimension B_local * world_size."""
+    tensors = [dets, count] + list(extras or [])
+    if not _active(group):
+        return tensors
+    world = dist.get_world_size(group)
+    out = []
+    for t in tensors:
+        t = t.contiguous()
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t, group=group)
+        out.append(torch.cat(parts, dim=0))
+    return out
