@@ -101,7 +101,31 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// streaming 128-bit load: read once, do not pollute L1
+// Exact unsigned division by a runtime constant with one mul.hi + shift (divisor fixed per launch).
+struct FastDiv {
+    unsigned d, mul, shr;
+};
+inline FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    f.d = d;
+    if (d <= 1) { f.mul = 0; f.shr = 0; return f; }
+    unsigned l = 0;
+    while ((1ull << l) < d) ++l;                       // ceil(log2 d)
+    f.mul = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.shr = l - 1;
+    return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned fd_div(unsigned n, const FastDiv &f) {
+    if (f.d <= 1) return n;
+    const unsigned t = __umulhi(n, f.mul);
+    return (t + ((n - t) >> 1)) >> f.shr;
+}
+#endif
+
+// Streaming 128-bit load: read once, do not pollute L1.  `volatile` on purpose: it pins the loads
+// where the source puts them, so a batch of loads issued before its consumers STAYS a batch
+// (without it the compiler sinks each load next to its first use and only one is in flight).
 __device__ __forceinline__ float4 ld_stream4(const float *p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

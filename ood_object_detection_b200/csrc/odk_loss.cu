@@ -26,7 +26,9 @@ struct LossArgs {
     const float *box[ODK_MAX_LEVELS];
     float *gcls[ODK_MAX_LEVELS];
     float *gbox[ODK_MAX_LEVELS];
-    long long item_off[ODK_MAX_LEVELS + 1];
+    unsigned item_off[ODK_MAX_LEVELS + 1];
+    FastDiv div_nq[ODK_MAX_LEVELS];
+    FastDiv div_nchunk, div_na;
     int vec[ODK_MAX_LEVELS];   // 4 if the level's planes are 16-byte aligned rows of 4, else 1
     int nq[ODK_MAX_LEVELS];    // position groups per plane
     int B, C, cchunk, nchunk, Mmax;
@@ -45,10 +47,20 @@ struct LossArgs {
 
 // softplus(x) = max(x,0) + log1p(exp(-|x|)); also returns e = exp(-|x|).
 // MUFU.EX2 + MUFU.LG2 with a 4-term series where 1+e would lose e's low bits.
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float softplus_fast(float x, float &e) {
-    e = __expf(-fabsf(x));
+    e = ex2_ftz(fabsf(x) * -1.4426950408889634f);
     const float series = e * (1.0f - e * (0.5f - e * (0.33333334f - 0.25f * e)));
-    const float lg = __logf(1.0f + e);
+    const float lg = lg2_ftz(1.0f + e) * 0.6931471805599453f;
     return fmaxf(x, 0.0f) + (e < 0.03125f ? series : lg);
 }
 __device__ __forceinline__ float sigmoid_from_e(float x, float e) {
@@ -70,16 +82,17 @@ template <> struct Vec<1> {
 };
 
 template <int VEC, int MODE, bool GRAD, bool FUSED>
-__device__ __forceinline__ void loss_item(const LossArgs &A, int l, long long local, float inv_n, float &csum,
+__device__ __forceinline__ void loss_item(const LossArgs &A, int l, unsigned local, float inv_n, float &csum,
                                           float &bsum) {
     const Geo &g = A.g;
     const int hw = g.hw[l], nq = A.nq[l];
-    const int q = (int)(local % nq);
-    long long t = local / nq;
-    const int chunk = (int)(t % A.nchunk);
-    t /= A.nchunk;
-    const int a = (int)(t % g.na);
-    const int b = (int)(t / g.na);
+    unsigned t = fd_div(local, A.div_nq[l]);
+    const int q = (int)(local - t * (unsigned)nq);
+    unsigned t2 = fd_div(t, A.div_nchunk);
+    const int chunk = (int)(t - t2 * (unsigned)A.nchunk);
+    const unsigned t3 = fd_div(t2, A.div_na);
+    const int a = (int)(t2 - t3 * (unsigned)g.na);
+    const int b = (int)t3;
     const int s0 = q * VEC;
     const int c0 = chunk * A.cchunk, c1 = min(c0 + A.cchunk, A.C);
     const float alpha = A.p.alpha, sm = A.p.label_smoothing, gamma = A.p.gamma;
@@ -105,10 +118,8 @@ __device__ __forceinline__ void loss_item(const LossArgs &A, int l, long long lo
 #pragma unroll
     for (int j = 0; j < VEC; ++j) { acc[j] = 0.f; accx[j] = 0.f; }
     const float gneg = (1.0f - alpha) * inv_n;
-#pragma unroll 4
-    for (int c = c0; c < c1; ++c) {
-        Vec<VEC> x, gr;
-        x.load_stream(px);
+    auto one_plane = [&](const Vec<VEC> &x, float *gp) {
+        Vec<VEC> gr;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             float e;
@@ -132,8 +143,28 @@ __device__ __forceinline__ void loss_item(const LossArgs &A, int l, long long lo
                 }
             }
         }
-        if (GRAD) { gr.store(pg); pg += hw; }
+        if (GRAD) gr.store(gp);
+    };
+    int c = c0;
+    for (; c + 4 <= c1; c += 4) {   // 4 independent 128-bit loads in flight per thread
+        Vec<VEC> x0, x1, x2, x3;
+        x0.load_stream(px);
+        x1.load_stream(px + hw);
+        x2.load_stream(px + 2 * (size_t)hw);
+        x3.load_stream(px + 3 * (size_t)hw);
+        one_plane(x0, pg);
+        one_plane(x1, pg + (GRAD ? hw : 0));
+        one_plane(x2, pg + (GRAD ? 2 * (size_t)hw : 0));
+        one_plane(x3, pg + (GRAD ? 3 * (size_t)hw : 0));
+        px += 4 * (size_t)hw;
+        if (GRAD) pg += 4 * (size_t)hw;
+    }
+    for (; c < c1; ++c) {
+        Vec<VEC> x0;
+        x0.load_stream(px);
+        one_plane(x0, pg);
         px += hw;
+        if (GRAD) pg += hw;
     }
 
     // ---- combine, patch the positive class, apply the ignore mask (loss.py:285) ----
@@ -212,19 +243,19 @@ __device__ __forceinline__ void loss_item(const LossArgs &A, int l, long long lo
 }
 
 template <int MODE, bool GRAD, bool FUSED>
-__global__ void __launch_bounds__(kLossThreads)
+__global__ void __launch_bounds__(kLossThreads, 3)
 loss_kernel(const __grid_constant__ LossArgs A) {
     const float nrm = __ldg(A.normalizer);
     const float inv_n = 1.0f / nrm;
     float csum = 0.f, bsum = 0.f;
-    const long long total = A.item_off[A.g.nlev];
-    const long long stride = (long long)gridDim.x * kLossThreads;
-    for (long long it = (long long)blockIdx.x * kLossThreads + threadIdx.x; it < total; it += stride) {
+    const unsigned total = A.item_off[A.g.nlev];
+    const unsigned stride = gridDim.x * kLossThreads;
+    for (unsigned it = blockIdx.x * kLossThreads + threadIdx.x; it < total; it += stride) {
         int l = 0;
 #pragma unroll
         for (int i = 1; i < ODK_MAX_LEVELS; ++i)
             if (i < A.g.nlev && it >= A.item_off[i]) l = i;
-        const long long local = it - A.item_off[l];
+        const unsigned local = it - A.item_off[l];
         if (A.vec[l] == 4) loss_item<4, MODE, GRAD, FUSED>(A, l, local, inv_n, csum, bsum);
         else loss_item<1, MODE, GRAD, FUSED>(A, l, local, inv_n, csum, bsum);
     }
@@ -330,6 +361,8 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
     a.cchunk = C < 16 ? C : 16;
     a.nchunk = (C + a.cchunk - 1) / a.cchunk;
     long long off = 0;
+    a.div_nchunk = make_fastdiv((unsigned)a.nchunk);
+    a.div_na = make_fastdiv((unsigned)na);
     for (int l = 0; l < num_levels; ++l) {
         a.cls[l] = (const float *)cls_levels[l];
         a.box[l] = (const float *)box_levels[l];
@@ -340,10 +373,12 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
         uintptr_t al = (uintptr_t)a.cls[l] | (uintptr_t)a.box[l] | (uintptr_t)a.gcls[l] | (uintptr_t)a.gbox[l];
         a.vec[l] = (a.g.hw[l] % 4 == 0 && (al & 15) == 0) ? 4 : 1;
         a.nq[l] = (a.g.hw[l] + a.vec[l] - 1) / a.vec[l];
-        a.item_off[l] = off;
+        a.div_nq[l] = make_fastdiv((unsigned)a.nq[l]);
+        a.item_off[l] = (unsigned)off;
         off += (long long)B * na * a.nchunk * a.nq[l];
+        if (off > 0x7fffffffll) return set_error(ODK_EUNSUPPORTED, "odk_loss: more than 2^31 work items");
     }
-    for (int l = num_levels; l <= ODK_MAX_LEVELS; ++l) a.item_off[l] = off;
+    for (int l = num_levels; l <= ODK_MAX_LEVELS; ++l) a.item_off[l] = (unsigned)off;
     a.match = match; a.anchors = (const float4 *)anchors; a.gt_boxes = (const float4 *)gt_boxes; a.gt_labels = gt_labels;
     a.cls_t = cls_targets; a.box_t = box_targets; a.normalizer = normalizer; a.p = *params; a.out = out;
     a.partials = (double *)workspace;
