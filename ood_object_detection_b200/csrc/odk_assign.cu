@@ -49,12 +49,12 @@ assign_kernel(const Geo g, const float4 *__restrict__ anchors, const float4 *__r
     }
     if (tid == 0) s_pos = 0;
 
+    // this warp's own bounding box (lanes past the end hold +/-inf and never widen it)
+    const float wy0 = warp_min(live ? a.x : INFINITY), wx0 = warp_min(live ? a.y : INFINITY);
+    const float wy1 = warp_max(live ? a.z : -INFINITY), wx1 = warp_max(live ? a.w : -INFINITY);
     // bounding box of this CTA's anchors
     {
-        float y0 = live ? a.x : INFINITY, x0 = live ? a.y : INFINITY;
-        float y1 = live ? a.z : -INFINITY, x1 = live ? a.w : -INFINITY;
-        y0 = warp_min(y0); x0 = warp_min(x0); y1 = warp_max(y1); x1 = warp_max(x1);
-        if (lane == 0) { s_red[0][warp] = y0; s_red[1][warp] = x0; s_red[2][warp] = y1; s_red[3][warp] = x1; }
+        if (lane == 0) { s_red[0][warp] = wy0; s_red[1][warp] = wx0; s_red[2][warp] = wy1; s_red[3][warp] = wx1; }
         __syncthreads();
         if (tid < 4) {
             float v = s_red[tid][0];
@@ -105,16 +105,34 @@ assign_kernel(const Geo g, const float4 *__restrict__ anchors, const float4 *__r
         __syncthreads();
 
         // ---- every anchor against the staged gts, ascending gt order ----
-        if (live) {
-            for (int j = 0; j < n; ++j) {
-                const float4 q = s_box[j];
-                const float v = iou_ref(q.x, q.y, q.z, q.w, s_area[j], a.x, a.y, a.z, a.w, aarea);
-                if (v > best_iou) { best_iou = v; best_g = s_idx[j]; }
-                if (v > 0.0f) {
-                    const unsigned long long key =
-                        ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
-                    if (key > *(volatile unsigned long long *)&s_best[j]) atomicMax(&s_best[j], key);
+        // A warp's 32 anchors are neighbours in one feature-map row, so most staged gts miss the
+        // whole warp: reject those with one warp-uniform test on the warp's bounding box.
+        for (int j = 0; j < n; ++j) {
+            const float4 q = s_box[j];
+            if (cull && !((q.z > wy0) && (q.x < wy1) && (q.w > wx0) && (q.y < wx1))) continue;   // warp-uniform
+            float v = 0.0f;
+            if (live) {
+                // same arithmetic as iou_ref, with the (exact) early-outs for an empty intersection
+                const float h = __fsub_rn(fminf(q.z, a.z), fmaxf(q.x, a.x));
+                const float w = __fsub_rn(fminf(q.w, a.w), fmaxf(q.y, a.y));
+                if (h > 0.0f && w > 0.0f) {
+                    const float inter = __fmul_rn(h, w);
+                    if (inter != 0.0f) v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(s_area[j], aarea), inter));
                 }
+                if (v > best_iou) { best_iou = v; best_g = s_idx[j]; }
+            }
+            // per-gt arg-max over anchors: reduce inside the warp, one shared atomic per warp at most
+            unsigned long long key = 0ull;
+            if (v > 0.0f)
+                key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+            const unsigned long long cur = *(volatile unsigned long long *)&s_best[j];
+            if (__any_sync(0xffffffffu, key > cur)) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = other > key ? other : key;
+                }
+                if (lane == 0) atomicMax(&s_best[j], key);
             }
         }
         __syncthreads();

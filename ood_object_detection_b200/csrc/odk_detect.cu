@@ -132,7 +132,17 @@ __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_kee
             if (!m) continue;
             const int i = w * 32 + lane;
             bool kill = false;
-            if ((m >> lane) & 1u) kill = (i == top) || (i > top && iou_nms(p, ap, S.box[i]) > thr_f);
+            if ((m >> lane) & 1u) {
+                kill = i == top;
+                if (i > top) {
+                    // boxes of other classes sit in other offset bands: when the x or y extents do
+                    // not overlap the intersection is 0 and the IoU cannot exceed a threshold >= 0,
+                    // so the division is skipped (identical result, ~7x fewer instructions)
+                    const float4 q = S.box[i];
+                    const bool touch = (fminf(p.z, q.z) > fmaxf(p.x, q.x)) && (fminf(p.w, q.w) > fmaxf(p.y, q.y));
+                    if (touch || thr_f < 0.0f) kill = iou_nms(p, ap, q) > thr_f;
+                }
+            }
             const unsigned k = __ballot_sync(0xffffffffu, kill);
             if (lane == 0 && k) S.alive[w] = m & ~k;
         }
@@ -197,13 +207,18 @@ __device__ int soft_nms_rounds(const DetSmem &S, int n, bool gaussian, float sig
             const int i = w * 32 + lane;
             bool kill = false;
             if ((m >> lane) & 1u) {
-                const float iou = iou_soft(p, ap, S.box[i]);
-                float decay;
-                if (gaussian) decay = expf(__fdiv_rn(-__fmul_rn(iou, iou), sigma));   // soft_nms.py:96
-                else decay = iou > iou_thr ? __fsub_rn(1.0f, iou) : 1.0f;             // :98-100
-                const float sc = __fmul_rn(S.score[i], decay);
-                S.score[i] = sc;
-                kill = !(sc > score_thr) || i == top;                                 // :103-104
+                const float4 q = S.box[i];
+                float sc = S.score[i];
+                // disjoint extents -> iou 0 -> decay exactly 1: the score is unchanged, skip the math
+                if ((fminf(p.z, q.z) > fmaxf(p.x, q.x)) && (fminf(p.w, q.w) > fmaxf(p.y, q.y))) {
+                    const float iou = iou_soft(p, ap, q);
+                    float decay;
+                    if (gaussian) decay = expf(__fdiv_rn(-__fmul_rn(iou, iou), sigma));   // soft_nms.py:96
+                    else decay = iou > iou_thr ? __fsub_rn(1.0f, iou) : 1.0f;             // :98-100
+                    sc = __fmul_rn(sc, decay);
+                    S.score[i] = sc;
+                }
+                kill = !(sc > score_thr) || i == top;                                     // :103-104
             }
             const unsigned k = __ballot_sync(0xffffffffu, kill);
             if (lane == 0 && k) S.alive[w] = m & ~k;

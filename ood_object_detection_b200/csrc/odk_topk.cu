@@ -89,53 +89,29 @@ __device__ __forceinline__ Task decode_task(const TopkArgs &A, int b, int t) {
     return k;
 }
 
-// Visit every element of a task with the warp; f(value, position_in_plane, active_lane_mask) is
-// called per element (the mask is only meaningful in SAMPLE mode).
-// SAMPLE: only pseudo-randomly chosen warp iterations (1 / 2^kSampleShift of them).
-template <bool SAMPLE, class F>
-__device__ __forceinline__ void visit_task(const Task &k, int t, int lane, F f) {
+// Visit every element of a task segment with the warp: f4(v0..v3 of one lane's float4, first
+// position) / f1(value, position).  Four independent 128-bit loads are in flight per lane.
+template <class F4, class F1>
+__device__ __forceinline__ void visit_task(const Task &k, int lane, F4 f4, F1 f1) {
     if (k.vec == 4) {
-        if (!SAMPLE) {
-            int u = k.u0 + lane;
-            for (; u + 96 < k.u1; u += 128) {   // 4 independent 128-bit loads in flight per lane
-                const float4 v0 = ld_stream4(k.base + (size_t)u * 4);
-                const float4 v1 = ld_stream4(k.base + (size_t)(u + 32) * 4);
-                const float4 v2 = ld_stream4(k.base + (size_t)(u + 64) * 4);
-                const float4 v3 = ld_stream4(k.base + (size_t)(u + 96) * 4);
-                f(v0.x, u * 4, 0u); f(v0.y, u * 4 + 1, 0u); f(v0.z, u * 4 + 2, 0u); f(v0.w, u * 4 + 3, 0u);
-                f(v1.x, u * 4 + 128, 0u); f(v1.y, u * 4 + 129, 0u); f(v1.z, u * 4 + 130, 0u); f(v1.w, u * 4 + 131, 0u);
-                f(v2.x, u * 4 + 256, 0u); f(v2.y, u * 4 + 257, 0u); f(v2.z, u * 4 + 258, 0u); f(v2.w, u * 4 + 259, 0u);
-                f(v3.x, u * 4 + 384, 0u); f(v3.y, u * 4 + 385, 0u); f(v3.z, u * 4 + 386, 0u); f(v3.w, u * 4 + 387, 0u);
-            }
-            for (; u < k.u1; u += 32) {
-                const float4 v = ld_stream4(k.base + (size_t)u * 4);
-                f(v.x, u * 4, 0u); f(v.y, u * 4 + 1, 0u); f(v.z, u * 4 + 2, 0u); f(v.w, u * 4 + 3, 0u);
-            }
-        } else {
-            for (int u = k.u0; u < k.u1; u += 32) {
-                const unsigned h = ((unsigned)t * 2654435761u) ^ ((unsigned)(u >> 5) * 2246822519u);
-                if (((h >> 13) & ((1u << kSampleShift) - 1u)) != 0u) continue;   // warp-uniform
-                const unsigned mask = __ballot_sync(0xffffffffu, u + lane < k.u1);
-                if (u + lane < k.u1) {
-                    const float4 v = ld_stream4(k.base + (size_t)(u + lane) * 4);
-                    const int s = (u + lane) * 4;
-                    f(v.x, s, mask); f(v.y, s + 1, mask); f(v.z, s + 2, mask); f(v.w, s + 3, mask);
-                }
-            }
+        int u = k.u0 + lane;
+        for (; u + 96 < k.u1; u += 128) {
+            const float4 v0 = ld_stream4(k.base + (size_t)u * 4);
+            const float4 v1 = ld_stream4(k.base + (size_t)(u + 32) * 4);
+            const float4 v2 = ld_stream4(k.base + (size_t)(u + 64) * 4);
+            const float4 v3 = ld_stream4(k.base + (size_t)(u + 96) * 4);
+            f4(v0, u * 4); f4(v1, u * 4 + 128); f4(v2, u * 4 + 256); f4(v3, u * 4 + 384);
         }
+        for (; u < k.u1; u += 32) f4(ld_stream4(k.base + (size_t)u * 4), u * 4);
     } else {
-        for (int u = k.u0; u < k.u1; u += 32) {
-            if (SAMPLE) {
-                const unsigned h = ((unsigned)t * 2654435761u) ^ ((unsigned)(u >> 5) * 2246822519u);
-                if (((h >> 13) & ((1u << kSampleShift) - 1u)) != 0u) continue;
-            }
-            const unsigned mask = __ballot_sync(0xffffffffu, u + lane < k.u1);
-            if (u + lane < k.u1) f(ld_stream1(k.base + u + lane), u + lane, mask);
-        }
+        for (int u = k.u0 + lane; u < k.u1; u += 32) f1(ld_stream1(k.base + u), u);
     }
 }
 
 // ---- P0: sample histogram ----------------------------------------------------------------
+// Each task segment has at most kSegVec/32 = 32 warp-wide units (512 bytes); unit j = hash(task) mod
+// 2^kSampleShift is sampled if the segment has one.  Every unit of the image is therefore taken with
+// probability 2^-kSampleShift, spread over all channel planes and positions.
 __global__ void __launch_bounds__(kTopkThreads) topk_sample_kernel(const __grid_constant__ TopkArgs A) {
     __shared__ unsigned s_hist[kHistBins];
     const int b = blockIdx.y;
@@ -145,13 +121,30 @@ __global__ void __launch_bounds__(kTopkThreads) topk_sample_kernel(const __grid_
     const int W = gridDim.x * (kTopkThreads / 32);
     const int ntasks = A.task_off[A.g.nlev];
     for (int t = blockIdx.x * (kTopkThreads / 32) + (threadIdx.x >> 5); t < ntasks; t += W) {
+        unsigned h = (unsigned)t * 2654435761u;
+        h ^= h >> 15;
+        const int j = (int)((h * 2246822519u) >> (32 - kSampleShift));
         const Task k = decode_task(A, b, t);
-        visit_task<true>(k, t, lane, [&](float x, int, unsigned mask) {
+        const int u = k.u0 + j * 32;
+        if (u >= k.u1) continue;   // warp-uniform
+        const bool on = u + lane < k.u1;
+        const unsigned mask = __ballot_sync(0xffffffffu, on);
+        if (!on) continue;
+        float v[4];
+        int nv = 1;
+        if (k.vec == 4) {
+            const float4 q = ld_stream4(k.base + (size_t)(u + lane) * 4);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+            nv = 4;
+        } else {
+            v[0] = ld_stream1(k.base + u + lane);
+        }
+        for (int i = 0; i < nv; ++i) {
             // aggregate equal bins across the warp first: logits crowd into a few exponent bins
-            const unsigned bin = vkey_of(x) >> 20;
+            const unsigned bin = vkey_of(v[i]) >> 20;
             const unsigned peers = __match_any_sync(mask, bin);
             if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
-        });
+        }
     }
     __syncthreads();
     unsigned *gh = A.hist + (size_t)b * kHistBins;
@@ -196,10 +189,21 @@ __device__ unsigned pick_threshold(const unsigned *__restrict__ gh, int K, long 
 }
 
 // ---- P1: single streaming pass, keep elements at or above the threshold bin ---------------
+constexpr int kStage = 1024;   // per-CTA staging slots for hits (~200 expected)
+
+__device__ __forceinline__ float thr_float(unsigned thr_key) {
+    // x >= thr_float  <=>  vkey_of(x) >= thr_key for every non-NaN x (-0.0 counts as +0.0)
+    return thr_key == 0u ? -INFINITY : val_of(thr_key);
+}
+
 __global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const __grid_constant__ TopkArgs A) {
     __shared__ unsigned s_scan[kTopkThreads];
+    __shared__ unsigned long long s_stage[kStage];
+    __shared__ unsigned s_nstage, s_base;
     const int b = blockIdx.y;
+    if (threadIdx.x == 0) s_nstage = 0u;
     const unsigned thr = pick_threshold(A.hist + (size_t)b * kHistBins, A.K, A.N, s_scan);
+    const float thr_f = thr_float(thr);
     const int lane = threadIdx.x & 31;
     const int W = gridDim.x * (kTopkThreads / 32);
     const int ntasks = A.task_off[A.g.nlev];
@@ -208,37 +212,112 @@ __global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const __grid
     const unsigned stride = (unsigned)A.planes;
     for (int t = blockIdx.x * (kTopkThreads / 32) + (threadIdx.x >> 5); t < ntasks; t += W) {
         const Task k = decode_task(A, b, t);
-        visit_task<false>(k, t, lane, [&](float x, int s, unsigned) {
-            const unsigned vk = vkey_of(x);
-            if (vk >= thr) {
+        auto hit = [&](float x, int s) {
+            if (x >= thr_f) {
                 const unsigned flat = k.fbase + (unsigned)s * stride;
-                const unsigned pos = atomicAdd(cnt, 1u);
-                if (pos < (unsigned)kCap) cand[pos] = ((unsigned long long)vk << 32) | (unsigned long long)(~flat);
+                const unsigned long long key = ((unsigned long long)vkey_of(x) << 32) | (unsigned long long)(~flat);
+                const unsigned slot = atomicAdd(&s_nstage, 1u);
+                if (slot < (unsigned)kStage) {
+                    s_stage[slot] = key;
+                } else {   // staging full (threshold far too low): straight to the global list
+                    const unsigned pos = atomicAdd(cnt, 1u);
+                    if (pos < (unsigned)kCap) cand[pos] = key;
+                }
             }
-        });
+        };
+        visit_task(k, lane,
+                   [&](float4 v, int s) {
+                       // one compare per float4 on the common path; hits are ~1 in 2000 elements
+                       if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= thr_f) {
+                           hit(v.x, s); hit(v.y, s + 1); hit(v.z, s + 2); hit(v.w, s + 3);
+                       }
+                   },
+                   hit);
     }
+    __syncthreads();
+    const unsigned n = min(s_nstage, (unsigned)kStage);
+    if (threadIdx.x == 0) s_base = n ? atomicAdd(cnt, n) : 0u;
+    __syncthreads();
+    const unsigned base = s_base;
+    for (unsigned i = threadIdx.x; i < n; i += kTopkThreads)
+        if (base + i < (unsigned)kCap) cand[base + i] = s_stage[i];
 }
 
 // ---- P2: sort candidates, emit top K + gathers ----------------------------------------------
-__device__ void bitonic_sort_desc(unsigned long long *s, int P) {
+// Block-wide bitonic sort (descending) of P = E * 1024 64-bit keys held E per thread in registers.
+// Element e = t * E + r lives in register r of thread t, so compare-exchange distance j is
+//   j <  E        : inside the thread (no communication),
+//   E <= j < 32 E : a lane exchange inside the warp (shuffles),
+//   j >= 32 E     : between warps, through shared memory in a transposed (conflict-free) layout.
+// Only 15 of the 91 stages of an 8192-key sort need a block barrier this way.
+// In: s[r * 1024 + t] (any assignment of keys to slots).  Out: rank q is at s[(q % E) * 1024 + q / E].
+__device__ __forceinline__ unsigned long long u64max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+__device__ __forceinline__ unsigned long long u64min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+
+template <int E>
+__device__ void block_sort_desc(unsigned long long *s) {
+    const int t = threadIdx.x;
+    constexpr int P = E * kSelThreads;
+    unsigned long long v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) v[r] = s[r * kSelThreads + t];
+    __syncthreads();
+#pragma unroll 1
     for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
-                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                const int hi = lo | j;
-                const unsigned long long x = s[lo], y = s[hi];
-                const bool desc = (lo & k) == 0;
-                if ((x < y) == desc) { s[lo] = y; s[hi] = x; }
+#pragma unroll 1
+        for (int j = k >> 1; j >= E; j >>= 1) {
+            const int m = j / E;   // partner thread distance
+            if (m >= 32) {
+#pragma unroll
+                for (int r = 0; r < E; ++r) s[r * kSelThreads + t] = v[r];
+                __syncthreads();
+                const int pt = t ^ m;
+                const bool keep_max = ((t & m) == 0) == (((t * E) & k) == 0);
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const unsigned long long o = s[r * kSelThreads + pt];
+                    v[r] = keep_max ? u64max(v[r], o) : u64min(v[r], o);
+                }
+                __syncthreads();
+            } else {
+                const bool keep_max = ((t & m) == 0) == (((t * E) & k) == 0);
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], m);
+                    v[r] = keep_max ? u64max(v[r], o) : u64min(v[r], o);
+                }
             }
-            __syncthreads();
+        }
+        // in-thread stages: j = min(k/2, E/2) ... 1
+#pragma unroll
+        for (int j = E >> 1; j > 0; j >>= 1) {
+            if (j < k) {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    if ((r & j) == 0) {
+                        const bool desc = (((t * E + r) & k) == 0);
+                        const unsigned long long x = v[r], y = v[r | j];
+                        if ((x < y) == desc) { v[r] = y; v[r | j] = x; }
+                    }
+                }
+            }
         }
     }
+#pragma unroll
+    for (int r = 0; r < E; ++r) s[r * kSelThreads + t] = v[r];
+    __syncthreads();
 }
 
+template <int E>
+__device__ __forceinline__ unsigned long long sorted_at(const unsigned long long *s, int q) {
+    return s[(q % E) * kSelThreads + q / E];
+}
+
+template <int E>
 __device__ void emit_topk(const TopkArgs &A, int b, const unsigned long long *s) {
     const Geo &g = A.g;
     for (int q = threadIdx.x; q < A.K; q += blockDim.x) {
-        const unsigned long long key = s[q];
+        const unsigned long long key = sorted_at<E>(s, q);
         const unsigned flat = ~(unsigned)(key & 0xFFFFFFFFull);
         const int anchor = (int)(flat / (unsigned)A.C);
         const int c = (int)(flat - (unsigned)anchor * (unsigned)A.C);
@@ -257,13 +336,12 @@ __device__ void emit_topk(const TopkArgs &A, int b, const unsigned long long *s)
 }
 
 __device__ void sort_and_emit(const TopkArgs &A, int b, int n, unsigned long long *s) {
-    int P = 2;
-    while (P < n) P <<= 1;
     const unsigned long long *cand = A.cand + (size_t)b * kCap;
+    const int P = n <= 8 * kSelThreads ? 8 * kSelThreads : 16 * kSelThreads;
     for (int i = threadIdx.x; i < P; i += blockDim.x) s[i] = i < n ? __ldcg(cand + i) : 0ull;
     __syncthreads();
-    bitonic_sort_desc(s, P);
-    emit_topk(A, b, s);
+    if (P == 8 * kSelThreads) { block_sort_desc<8>(s); emit_topk<8>(A, b, s); }
+    else { block_sort_desc<16>(s); emit_topk<16>(A, b, s); }
 }
 
 __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const __grid_constant__ TopkArgs A) {
@@ -307,12 +385,13 @@ topk_exact_kernel(const __grid_constant__ TopkArgs A) {
         const int pshift = shift + bits;
         for (int t = wid; t < ntasks; t += W) {
             const Task k = decode_task(A, b, t);
-            visit_task<false>(k, t, lane, [&](float x, int s, unsigned) {
+            auto one = [&](float x, int s) {
                 const unsigned flat = k.fbase + (unsigned)s * stride;
                 const unsigned long long key = ((unsigned long long)vkey_of(x) << 32) | (unsigned long long)(~flat);
                 const bool in = pshift >= 64 ? true : ((key >> pshift) == (prefix >> pshift));
                 if (in) atomicAdd(&s_hist[(unsigned)(key >> shift) & ((1u << bits) - 1u)], 1u);
-            });
+            };
+            visit_task(k, lane, [&](float4 v, int s) { one(v.x, s); one(v.y, s + 1); one(v.z, s + 2); one(v.w, s + 3); }, one);
         }
         cluster.sync();
         if (rank == 0) {
@@ -348,14 +427,15 @@ topk_exact_kernel(const __grid_constant__ TopkArgs A) {
     unsigned long long *cand = A.cand + (size_t)b * kCap;
     for (int t = wid; t < ntasks; t += W) {
         const Task k = decode_task(A, b, t);
-        visit_task<false>(k, t, lane, [&](float x, int s, unsigned) {
+        auto one = [&](float x, int s) {
             const unsigned flat = k.fbase + (unsigned)s * stride;
             const unsigned long long key = ((unsigned long long)vkey_of(x) << 32) | (unsigned long long)(~flat);
             if (key >= lower) {
                 const unsigned pos = atomicAdd(A.cnt + b, 1u);
                 if (pos < (unsigned)kCap) cand[pos] = key;
             }
-        });
+        };
+        visit_task(k, lane, [&](float4 v, int s) { one(v.x, s); one(v.y, s + 1); one(v.z, s + 2); one(v.w, s + 3); }, one);
     }
     __threadfence();
     cluster.sync();
@@ -442,8 +522,13 @@ int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B
         cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * 8);
         cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * 8);
     }
+    static int occ = 0;
+    if (!occ) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topk_collect_kernel, kTopkThreads, 0);
+        if (occ < 1) occ = 1;
+    }
     const int warps_per_cta = kTopkThreads / 32;
-    int per_image = (sms * 8 + B - 1) / B;                       // ~8 resident CTAs per SM chip-wide
+    int per_image = (sms * occ) / B;                             // all CTAs co-resident: exactly one wave
     const int max_useful = (toff + warps_per_cta - 1) / warps_per_cta;
     if (per_image > max_useful) per_image = max_useful;
     if (per_image < 1) per_image = 1;
