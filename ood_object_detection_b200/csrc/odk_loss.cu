@@ -1,22 +1,35 @@
 // Fused detection loss (K2): focal/BCE classification loss + Huber box loss over all pyramid
 // levels, forward and (optionally) the gradient of the total in the same pass.  HBM-bound: the
-// [B, na*C, H, W] logits are streamed exactly once with 128-bit loads in their native NCHW
-// layout; the one-hot target tensor the reference materialises (loss.py:182-186) never exists.
+// [B, na*C, H, W] logits are streamed exactly once in their native NCHW layout; the one-hot
+// target tensor the reference materialises (loss.py:182-186) never exists.
 // See include/odk.h (odk_loss).
 //
-// Work decomposition: one item = (level, image b, anchor shape a, class chunk, 4 consecutive
-// (y,x) positions).  Consecutive threads take consecutive position groups of one channel
-// plane, so every warp load is 512 contiguous bytes.  The inner loop treats every element as
-// a negative (target 0); the single positive class of a position (if any) is patched after
-// the loop.  A persistent grid (a multiple of the SM count) walks the items; per-CTA partial
-// sums are combined by the last CTA in a fixed order, so results are deterministic.
+// Work decomposition: one item = (level, image b, anchor shape a, chunk of <=48 classes, 4
+// consecutive (y,x) positions) = up to 48 rows of 16 bytes per thread.  Consecutive threads take
+// consecutive position groups of one channel plane, so every warp access is 512 contiguous
+// bytes.  The inner loop treats every element as a negative (target 0); the single positive class
+// of a position (if any) is patched after the loop.  A persistent grid (a multiple of the SM
+// count) walks the items; per-CTA partial sums are combined by the last CTA in a fixed order, so
+// results are deterministic.
+//
+// Two kernels share all the arithmetic:
+//   loss_kernel_ring : levels whose planes are 16-byte aligned rows (H*W % 4 == 0).  Each thread
+//                      keeps a private ring of cp.async (LDGSTS) 16-byte copies in shared memory,
+//                      kRingDepth row-groups (4 rows = 64 B) ahead of the math, so ~150 KB per SM
+//                      is always in flight without spending registers on it.
+//   loss_kernel      : everything else (odd-sized levels such as D3's 7x7), plain register loads.
 #include <string.h>
+
 #include "odk_common.cuh"
 
 namespace odk {
 
 constexpr int kLossThreads = 256;
 constexpr int kMaxPartials = 148 * 16;
+constexpr int kMaxChunk = 48;                  // classes per work item
+constexpr int kRingSlots = 4;                  // row-groups of smem per thread
+constexpr int kRingDepth = kRingSlots - 1;     // row-groups in flight ahead of the math
+constexpr int kRingBytes = kRingSlots * 4 * kLossThreads * 16;
 
 enum LossMode { kNew = 0, kNewSmooth = 1, kLegacy = 2 };
 
@@ -26,7 +39,7 @@ struct LossArgs {
     const float *box[ODK_MAX_LEVELS];
     float *gcls[ODK_MAX_LEVELS];
     float *gbox[ODK_MAX_LEVELS];
-    unsigned item_off[ODK_MAX_LEVELS + 1];
+    unsigned item_off[ODK_MAX_LEVELS + 1];   // items of the levels THIS launch covers
     FastDiv div_nq[ODK_MAX_LEVELS];
     FastDiv div_nchunk, div_na;
     int vec[ODK_MAX_LEVELS];   // 4 if the level's planes are 16-byte aligned rows of 4, else 1
@@ -40,13 +53,17 @@ struct LossArgs {
     const float *box_t;
     const float *normalizer;
     odk_loss_params p;
-    double *partials;     // [gridDim.x][2]
+    double *partials;     // [part_base + gridDim.x][2]
+    int part_base;        // first partial slot of this launch
+    int part_total;       // slots the finishing launch sums (0: this launch does not finish)
     unsigned *counter;
     float *out;
 };
 
-// softplus(x) = max(x,0) + log1p(exp(-|x|)); also returns e = exp(-|x|).
-// MUFU.EX2 + MUFU.LG2 with a 4-term series where 1+e would lose e's low bits.
+// ---- element math ----------------------------------------------------------------------------
+// softplus(x) = max(x,0) + log1p(exp(-|x|)); also returns e = exp(-|x|).  One MUFU.EX2 and one
+// MUFU.LG2 (flush-to-zero forms: no denormal fix-up code), with a 4-term series where 1+e would
+// lose e's low bits.
 __device__ __forceinline__ float ex2_ftz(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -63,6 +80,31 @@ __device__ __forceinline__ float softplus_fast(float x, float &e) {
     const float lg = lg2_ftz(1.0f + e) * 0.6931471805599453f;
     return fmaxf(x, 0.0f) + (e < 0.03125f ? series : lg);
 }
+// Blackwell packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2: two fp32 results per issue slot).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float &a, float &b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// softplus of two values at once; same arithmetic as softplus_fast with the polynomial, 1+e and the
+// final sums done as packed pairs.  Returns the packed softplus, e0/e1 = exp(-|x|).
+__device__ __forceinline__ f32x2 softplus_fast2(float x0, float x1, float &e0, float &e1) {
+    e0 = ex2_ftz(fabsf(x0) * -1.4426950408889634f);
+    e1 = ex2_ftz(fabsf(x1) * -1.4426950408889634f);
+    const f32x2 E = pk2(e0, e1), ONE = pk2(1.0f, 1.0f);
+    float u0, u1, s0, s1;
+    upk2(add2(E, ONE), u0, u1);
+    f32x2 T = fma2(E, pk2(-0.25f, -0.25f), pk2(0.33333334f, 0.33333334f));
+    T = fma2(E, T, pk2(-0.5f, -0.5f));
+    T = fma2(E, T, ONE);
+    upk2(mul2(E, T), s0, s1);
+    const float l0 = lg2_ftz(u0) * 0.6931471805599453f, l1 = lg2_ftz(u1) * 0.6931471805599453f;
+    const float p0 = e0 < 0.03125f ? s0 : l0, p1 = e1 < 0.03125f ? s1 : l1;
+    return add2(pk2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)), pk2(p0, p1));
+}
+
 __device__ __forceinline__ float sigmoid_from_e(float x, float e) {
     return __fdividef(x >= 0.0f ? 1.0f : e, 1.0f + e);
 }
@@ -81,98 +123,123 @@ template <> struct Vec<1> {
     __device__ __forceinline__ void store(float *p) const { st_stream1(p, v[0]); }
 };
 
-template <int VEC, int MODE, bool GRAD, bool FUSED>
-__device__ __forceinline__ void loss_item(const LossArgs &A, int l, unsigned local, float inv_n, float &csum,
-                                          float &bsum) {
-    const Geo &g = A.g;
-    const int hw = g.hw[l], nq = A.nq[l];
-    unsigned t = fd_div(local, A.div_nq[l]);
-    const int q = (int)(local - t * (unsigned)nq);
-    unsigned t2 = fd_div(t, A.div_nchunk);
-    const int chunk = (int)(t - t2 * (unsigned)A.nchunk);
-    const unsigned t3 = fd_div(t2, A.div_na);
-    const int a = (int)(t2 - t3 * (unsigned)g.na);
-    const int b = (int)t3;
-    const int s0 = q * VEC;
-    const int c0 = chunk * A.cchunk, c1 = min(c0 + A.cchunk, A.C);
-    const float alpha = A.p.alpha, sm = A.p.label_smoothing, gamma = A.p.gamma;
+// ---- one work item ------------------------------------------------------------------------------
+struct Item {
+    int l, b, a, chunk, s0, c0, c1, hw;
+    size_t plane0;   // element offset of (b, a, class c0, position s0) in the level's logits
+};
 
-    // ---- class target of each of my positions: >=0 class, -1 background, -2 ignore ----
-    int tc[VEC], mt[VEC];
+template <int VEC>
+__device__ __forceinline__ Item decode_item(const LossArgs &A, int l, unsigned local) {
+    const Geo &g = A.g;
+    Item it;
+    it.l = l;
+    it.hw = g.hw[l];
+    const unsigned nq = (unsigned)A.nq[l];
+    const unsigned t = fd_div(local, A.div_nq[l]);
+    const unsigned q = local - t * nq;
+    const unsigned t2 = fd_div(t, A.div_nchunk);
+    it.chunk = (int)(t - t2 * (unsigned)A.nchunk);
+    const unsigned t3 = fd_div(t2, A.div_na);
+    it.a = (int)(t2 - t3 * (unsigned)g.na);
+    it.b = (int)t3;
+    it.s0 = (int)q * VEC;
+    it.c0 = it.chunk * A.cchunk;
+    it.c1 = min(it.c0 + A.cchunk, A.C);
+    it.plane0 = ((size_t)(it.b * g.na + it.a) * A.C + it.c0) * it.hw + it.s0;
+    return it;
+}
+
+__device__ __forceinline__ int level_of_item(const LossArgs &A, unsigned it) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < ODK_MAX_LEVELS; ++i)
+        if (i < A.g.nlev && it >= A.item_off[i]) l = i;
+    return l;
+}
+
+// class target of each of my positions: >=0 class, -1 background, -2 ignore (+ matched gt row)
+template <int VEC, bool FUSED>
+__device__ __forceinline__ void item_targets(const LossArgs &A, const Item &it, int (&tc)[VEC], int (&mt)[VEC]) {
+    const Geo &g = A.g;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         if (FUSED) {
-            mt[j] = __ldg(A.match + (size_t)b * g.Apad + g.off[l] + a * hw + s0 + j);
-            tc[j] = mt[j] >= 0 ? __ldg(A.gt_labels + (size_t)b * A.Mmax + mt[j]) - 1 : -1;
+            mt[j] = __ldg(A.match + (size_t)it.b * g.Apad + g.off[it.l] + it.a * it.hw + it.s0 + j);
+            tc[j] = mt[j] >= 0 ? __ldg(A.gt_labels + (size_t)it.b * A.Mmax + mt[j]) - 1 : -1;
         } else {
             mt[j] = -1;
-            tc[j] = (int)__ldg(A.cls_t + (size_t)A.B * g.off[l] + ((size_t)b * hw + s0 + j) * g.na + a);
+            tc[j] = (int)__ldg(A.cls_t + (size_t)A.B * g.off[it.l] + ((size_t)it.b * it.hw + it.s0 + j) * g.na + it.a);
         }
     }
+}
 
-    // ---- stream my class chunk as negatives ----
-    const size_t plane0 = ((size_t)(b * g.na + a) * A.C + c0) * hw + s0;
-    const float *px = A.cls[l] + plane0;
-    float *pg = GRAD ? A.gcls[l] + plane0 : nullptr;
-    float acc[VEC], accx[VEC];
+// one row (one class) of VEC positions, all treated as negatives
+template <int VEC, int MODE, bool GRAD>
+__device__ __forceinline__ void row_compute(const LossArgs &A, const Vec<VEC> &x, float *gp, float gneg, float (&acc)[VEC],
+                                            float (&accx)[VEC]) {
+    Vec<VEC> gr;
+    const float gamma = A.p.gamma, sm = A.p.label_smoothing;
+    if (VEC == 4 && MODE != kLegacy) {
+        float e[4];
+        const f32x2 s01 = softplus_fast2(x.v[0], x.v[1], e[0], e[1]);
+        const f32x2 s23 = softplus_fast2(x.v[2], x.v[3], e[2], e[3]);
+        upk2(add2(pk2(acc[0], acc[1]), s01), acc[0], acc[1]);
+        upk2(add2(pk2(acc[2], acc[3]), s23), acc[2], acc[3]);
+        if (MODE == kNewSmooth) {
+            upk2(add2(pk2(accx[0], accx[1]), pk2(x.v[0], x.v[1])), accx[0], accx[1]);
+            upk2(add2(pk2(accx[2], accx[3]), pk2(x.v[2], x.v[3])), accx[2], accx[3]);
+        }
+        if (GRAD) {
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) { acc[j] = 0.f; accx[j] = 0.f; }
-    const float gneg = (1.0f - alpha) * inv_n;
-    auto one_plane = [&](const Vec<VEC> &x, float *gp) {
-        Vec<VEC> gr;
+            for (int j = 0; j < 4; ++j) {
+                const float sg = sigmoid_from_e(x.v[j], e[j]);
+                gr.v[j] = gneg * (MODE == kNewSmooth ? sg - 0.5f * sm : sg);
+            }
+            gr.store(gp);
+        }
+        return;
+    }
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
+    for (int j = 0; j < VEC; ++j) {
+        if (MODE == kLegacy) {
+            // t = 0: modulator = exp(-gamma*softplus(-x)), bce = softplus(x)   (loss.py:40-47)
+            const float xv = x.v[j];
+            const float sp = fmaxf(xv, 0.f) + log1pf(expf(-fabsf(xv)));
+            const float mod = expf(-gamma * (sp - xv));
+            acc[j] += mod * sp;
+            if (GRAD) {
+                const float sg = 1.0f / (1.0f + expf(-xv));
+                gr.v[j] = gneg * mod * (sg + sp * gamma * (1.0f - sg));
+            }
+        } else {
             float e;
-            if (MODE == kLegacy) {
-                // t = 0: modulator = exp(-gamma*softplus(-x)), bce = softplus(x)   (loss.py:40-47)
-                const float xv = x.v[j];
-                const float sp = fmaxf(xv, 0.f) + log1pf(expf(-fabsf(xv)));
-                const float mod = expf(-gamma * (sp - xv));
-                acc[j] += mod * sp;
-                if (GRAD) {
-                    const float sg = 1.0f / (1.0f + expf(-xv));
-                    gr.v[j] = gneg * mod * (sg + sp * gamma * (1.0f - sg));
-                }
-            } else {
-                const float sp = softplus_fast(x.v[j], e);
-                acc[j] += sp;
-                if (MODE == kNewSmooth) accx[j] += x.v[j];
-                if (GRAD) {
-                    const float sg = sigmoid_from_e(x.v[j], e);
-                    gr.v[j] = gneg * (MODE == kNewSmooth ? sg - 0.5f * sm : sg);
-                }
+            const float sp = softplus_fast(x.v[j], e);
+            acc[j] += sp;
+            if (MODE == kNewSmooth) accx[j] += x.v[j];
+            if (GRAD) {
+                const float sg = sigmoid_from_e(x.v[j], e);
+                gr.v[j] = gneg * (MODE == kNewSmooth ? sg - 0.5f * sm : sg);
             }
         }
-        if (GRAD) gr.store(gp);
-    };
-    int c = c0;
-    for (; c + 4 <= c1; c += 4) {   // 4 independent 128-bit loads in flight per thread
-        Vec<VEC> x0, x1, x2, x3;
-        x0.load_stream(px);
-        x1.load_stream(px + hw);
-        x2.load_stream(px + 2 * (size_t)hw);
-        x3.load_stream(px + 3 * (size_t)hw);
-        one_plane(x0, pg);
-        one_plane(x1, pg + (GRAD ? hw : 0));
-        one_plane(x2, pg + (GRAD ? 2 * (size_t)hw : 0));
-        one_plane(x3, pg + (GRAD ? 3 * (size_t)hw : 0));
-        px += 4 * (size_t)hw;
-        if (GRAD) pg += 4 * (size_t)hw;
     }
-    for (; c < c1; ++c) {
-        Vec<VEC> x0;
-        x0.load_stream(px);
-        one_plane(x0, pg);
-        px += hw;
-        if (GRAD) pg += hw;
-    }
+    if (GRAD) gr.store(gp);
+}
 
-    // ---- combine, patch the positive class, apply the ignore mask (loss.py:285) ----
+// combine the row sums, patch the positive class, apply the ignore mask (loss.py:285), and do the
+// Huber box loss once per (b, a, positions) in the first class chunk
+template <int VEC, int MODE, bool GRAD, bool FUSED>
+__device__ __forceinline__ void item_finish(const LossArgs &A, const Item &it, const int (&tc)[VEC], const int (&mt)[VEC],
+                                            const float (&acc)[VEC], const float (&accx)[VEC], float inv_n, float &csum,
+                                            float &bsum) {
+    const Geo &g = A.g;
+    const int l = it.l, hw = it.hw, c0 = it.c0, c1 = it.c1;
+    const float alpha = A.p.alpha, sm = A.p.label_smoothing, gamma = A.p.gamma;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         float val = (1.0f - alpha) * (MODE == kNewSmooth ? acc[j] - 0.5f * sm * accx[j] : acc[j]);
         if (tc[j] >= c0 && tc[j] < c1) {
-            const size_t o = ((size_t)(b * g.na + a) * A.C + tc[j]) * hw + s0 + j;
+            const size_t o = ((size_t)(it.b * g.na + it.a) * A.C + tc[j]) * hw + it.s0 + j;
             const float xp = __ldg(A.cls[l] + o);
             float gpos;
             if (MODE == kLegacy) {
@@ -196,32 +263,31 @@ __device__ __forceinline__ void loss_item(const LossArgs &A, int l, unsigned loc
         if (tc[j] == -2) {
             val = 0.f;
             if (GRAD) {
-                float *pz = A.gcls[l] + plane0 + j;
+                float *pz = A.gcls[l] + it.plane0 + j;
                 for (int c = c0; c < c1; ++c, pz += hw) *pz = 0.f;
             }
         }
         csum += val;
     }
 
-    // ---- Huber box loss: once per (b, a, positions), by the first class chunk ----
-    if (chunk == 0) {
+    if (it.chunk == 0) {
         float tg[VEC][4];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (FUSED) {
                 if (mt[j] >= 0)
-                    t4 = encode_ref(__ldg(A.gt_boxes + (size_t)b * A.Mmax + mt[j]),
-                                    __ldg(A.anchors + g.off[l] + (s0 + j) * g.na + a));
+                    t4 = encode_ref(__ldg(A.gt_boxes + (size_t)it.b * A.Mmax + mt[j]),
+                                    __ldg(A.anchors + g.off[l] + (it.s0 + j) * g.na + it.a));
             } else {
                 t4 = __ldg(reinterpret_cast<const float4 *>(A.box_t) + (size_t)A.B * g.off[l] +
-                           ((size_t)b * hw + s0 + j) * g.na + a);
+                           ((size_t)it.b * hw + it.s0 + j) * g.na + it.a);
             }
             tg[j][0] = t4.x; tg[j][1] = t4.y; tg[j][2] = t4.z; tg[j][3] = t4.w;
         }
         const float delta = A.p.delta;
         const float gb = A.p.box_loss_weight * inv_n * 0.25f;
-        const size_t bplane = ((size_t)(b * g.na + a) * 4) * hw + s0;
+        const size_t bplane = ((size_t)(it.b * g.na + it.a) * 4) * hw + it.s0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             Vec<VEC> o, gr;
@@ -242,25 +308,45 @@ __device__ __forceinline__ void loss_item(const LossArgs &A, int l, unsigned loc
     }
 }
 
-template <int MODE, bool GRAD, bool FUSED>
-__global__ void __launch_bounds__(kLossThreads, 3)
-loss_kernel(const __grid_constant__ LossArgs A) {
-    const float nrm = __ldg(A.normalizer);
-    const float inv_n = 1.0f / nrm;
-    float csum = 0.f, bsum = 0.f;
-    const unsigned total = A.item_off[A.g.nlev];
-    const unsigned stride = gridDim.x * kLossThreads;
-    for (unsigned it = blockIdx.x * kLossThreads + threadIdx.x; it < total; it += stride) {
-        int l = 0;
+// register-load path: any level
+template <int VEC, int MODE, bool GRAD, bool FUSED>
+__device__ __forceinline__ void loss_item(const LossArgs &A, int l, unsigned local, float inv_n, float &csum, float &bsum) {
+    const Item it = decode_item<VEC>(A, l, local);
+    int tc[VEC], mt[VEC];
+    item_targets<VEC, FUSED>(A, it, tc, mt);
+    const int hw = it.hw;
+    const float *px = A.cls[l] + it.plane0;
+    float *pg = GRAD ? A.gcls[l] + it.plane0 : nullptr;
+    float acc[VEC], accx[VEC];
 #pragma unroll
-        for (int i = 1; i < ODK_MAX_LEVELS; ++i)
-            if (i < A.g.nlev && it >= A.item_off[i]) l = i;
-        const unsigned local = it - A.item_off[l];
-        if (A.vec[l] == 4) loss_item<4, MODE, GRAD, FUSED>(A, l, local, inv_n, csum, bsum);
-        else loss_item<1, MODE, GRAD, FUSED>(A, l, local, inv_n, csum, bsum);
+    for (int j = 0; j < VEC; ++j) { acc[j] = 0.f; accx[j] = 0.f; }
+    const float gneg = (1.0f - A.p.alpha) * inv_n;
+    int c = it.c0;
+    for (; c + 4 <= it.c1; c += 4) {   // 4 independent loads in flight per thread
+        Vec<VEC> x0, x1, x2, x3;
+        x0.load_stream(px);
+        x1.load_stream(px + hw);
+        x2.load_stream(px + 2 * (size_t)hw);
+        x3.load_stream(px + 3 * (size_t)hw);
+        row_compute<VEC, MODE, GRAD>(A, x0, pg, gneg, acc, accx);
+        row_compute<VEC, MODE, GRAD>(A, x1, pg + (GRAD ? hw : 0), gneg, acc, accx);
+        row_compute<VEC, MODE, GRAD>(A, x2, pg + (GRAD ? 2 * (size_t)hw : 0), gneg, acc, accx);
+        row_compute<VEC, MODE, GRAD>(A, x3, pg + (GRAD ? 3 * (size_t)hw : 0), gneg, acc, accx);
+        px += 4 * (size_t)hw;
+        if (GRAD) pg += 4 * (size_t)hw;
     }
+    for (; c < it.c1; ++c) {
+        Vec<VEC> x0;
+        x0.load_stream(px);
+        row_compute<VEC, MODE, GRAD>(A, x0, pg, gneg, acc, accx);
+        px += hw;
+        if (GRAD) pg += hw;
+    }
+    item_finish<VEC, MODE, GRAD, FUSED>(A, it, tc, mt, acc, accx, inv_n, csum, bsum);
+}
 
-    // ---- deterministic two-stage reduction ----
+// ---- deterministic two-stage reduction shared by both kernels --------------------------------
+__device__ __forceinline__ void finish_block(const LossArgs &A, float csum, float bsum, float nrm) {
     __shared__ double s_c[kLossThreads / 32], s_b[kLossThreads / 32];
     __shared__ bool s_last;
     double dc = warp_sum((double)csum), db = warp_sum((double)bsum);
@@ -270,17 +356,17 @@ loss_kernel(const __grid_constant__ LossArgs A) {
     if (threadIdx.x == 0) {
         double c = 0, bx = 0;
         for (int w = 0; w < kLossThreads / 32; ++w) { c += s_c[w]; bx += s_b[w]; }
-        A.partials[2 * blockIdx.x] = c;
-        A.partials[2 * blockIdx.x + 1] = bx;
+        A.partials[2 * (A.part_base + blockIdx.x)] = c;
+        A.partials[2 * (A.part_base + blockIdx.x) + 1] = bx;
         __threadfence();
         const unsigned done = atomicAdd(A.counter, 1u);
-        s_last = (done == gridDim.x - 1);
+        s_last = A.part_total > 0 && (done == gridDim.x - 1);
     }
     __syncthreads();
     if (s_last) {
         __threadfence();
         double c = 0, bx = 0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += kLossThreads) {
+        for (int i = threadIdx.x; i < A.part_total; i += kLossThreads) {
             c += __ldcg(A.partials + 2 * i);
             bx += __ldcg(A.partials + 2 * i + 1);
         }
@@ -302,25 +388,178 @@ loss_kernel(const __grid_constant__ LossArgs A) {
 }
 
 template <int MODE, bool GRAD, bool FUSED>
-static int launch_loss(const LossArgs &args, int *grid_out, cudaStream_t st) {
-    static int blocks_per_sm = 0, sms = 0;
-    if (!blocks_per_sm) {
+__global__ void __launch_bounds__(kLossThreads, 3)
+loss_kernel(const __grid_constant__ LossArgs A) {
+    const float nrm = __ldg(A.normalizer);
+    const float inv_n = 1.0f / nrm;
+    float csum = 0.f, bsum = 0.f;
+    const unsigned total = A.item_off[A.g.nlev];
+    const unsigned stride = gridDim.x * kLossThreads;
+    for (unsigned it = blockIdx.x * kLossThreads + threadIdx.x; it < total; it += stride) {
+        const int l = level_of_item(A, it);
+        const unsigned local = it - A.item_off[l];
+        if (A.vec[l] == 4) loss_item<4, MODE, GRAD, FUSED>(A, l, local, inv_n, csum, bsum);
+        else loss_item<1, MODE, GRAD, FUSED>(A, l, local, inv_n, csum, bsum);
+    }
+    finish_block(A, csum, bsum, nrm);
+}
+
+// ---- cp.async ring kernel (vec4 levels only) -----------------------------------------------------
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const float *gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MODE, bool GRAD, bool FUSED>
+__global__ void __launch_bounds__(kLossThreads, 3)
+loss_kernel_ring(const __grid_constant__ LossArgs A) {
+    extern __shared__ __align__(16) unsigned char s_ring[];
+    const float nrm = __ldg(A.normalizer);
+    const float inv_n = 1.0f / nrm;
+    float csum = 0.f, bsum = 0.f;
+    const unsigned total = A.item_off[A.g.nlev];
+    const unsigned stride = gridDim.x * kLossThreads;
+    const unsigned first = blockIdx.x * kLossThreads + threadIdx.x;
+    const unsigned ring0 = (unsigned)__cvta_generic_to_shared(s_ring) + threadIdx.x * 16u;
+    const float4 *ring_rd = reinterpret_cast<const float4 *>(s_ring) + threadIdx.x;
+    // slot s, row r of this thread: ring + ((s * 4 + r) * kLossThreads) * 16 bytes (conflict-free)
+
+    // load cursor: runs kRingDepth row-groups ahead of the compute cursor over the same sequence
+    unsigned it_ld = first;
+    const float *px_ld = nullptr;
+    int rows_ld = 0, hw_ld = 0;
+    if (it_ld < total) {
+        const int l = level_of_item(A, it_ld);
+        const Item t = decode_item<4>(A, l, it_ld - A.item_off[l]);
+        px_ld = A.cls[l] + t.plane0; rows_ld = t.c1 - t.c0; hw_ld = t.hw;
+    }
+    auto issue_group = [&](int slot) {
+        if (it_ld < total) {
+            const unsigned dst = ring0 + (unsigned)(slot * 4) * (kLossThreads * 16u);
+            if (rows_ld >= 4) {   // common case: no per-row predicates
+                cp_async16(dst, px_ld);
+                cp_async16(dst + kLossThreads * 16u, px_ld + hw_ld);
+                cp_async16(dst + 2 * kLossThreads * 16u, px_ld + 2 * (size_t)hw_ld);
+                cp_async16(dst + 3 * kLossThreads * 16u, px_ld + 3 * (size_t)hw_ld);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    if (r < rows_ld) cp_async16(dst + (unsigned)r * (kLossThreads * 16u), px_ld + (size_t)r * hw_ld);
+            }
+            rows_ld -= 4;
+            px_ld += 4 * (size_t)hw_ld;
+            if (rows_ld <= 0) {
+                it_ld += stride;
+                if (it_ld < total) {
+                    const int l = level_of_item(A, it_ld);
+                    const Item t = decode_item<4>(A, l, it_ld - A.item_off[l]);
+                    px_ld = A.cls[l] + t.plane0; rows_ld = t.c1 - t.c0; hw_ld = t.hw;
+                }
+            }
+        }
+        cp_async_commit();   // always commit so group counting stays uniform
+    };
+#pragma unroll
+    for (int s = 0; s < kRingDepth; ++s) issue_group(s);
+
+    int slot = 0;
+    const float gneg = (1.0f - A.p.alpha) * inv_n;
+    for (unsigned itx = first; itx < total; itx += stride) {
+        const int l = level_of_item(A, itx);
+        const Item it = decode_item<4>(A, l, itx - A.item_off[l]);
+        int tc[4], mt[4];
+        item_targets<4, FUSED>(A, it, tc, mt);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, accx[4] = {0.f, 0.f, 0.f, 0.f};
+        float *pg = GRAD ? A.gcls[l] + it.plane0 : nullptr;
+        for (int c = it.c0; c < it.c1; c += 4) {
+            issue_group((slot + kRingDepth) % kRingSlots);
+            cp_async_wait<kRingDepth>();   // the oldest group (this slot) has landed
+            const int rows = it.c1 - c;
+            const float4 *rd = ring_rd + (size_t)(slot * 4) * kLossThreads;
+            if (rows >= 4) {
+                Vec<4> x[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float4 q = rd[(size_t)r * kLossThreads];
+                    x[r].v[0] = q.x; x[r].v[1] = q.y; x[r].v[2] = q.z; x[r].v[3] = q.w;
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    row_compute<4, MODE, GRAD>(A, x[r], pg + (GRAD ? (size_t)r * it.hw : 0), gneg, acc, accx);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    if (r < rows) {
+                        const float4 q = rd[(size_t)r * kLossThreads];
+                        Vec<4> x;
+                        x.v[0] = q.x; x.v[1] = q.y; x.v[2] = q.z; x.v[3] = q.w;
+                        row_compute<4, MODE, GRAD>(A, x, pg + (GRAD ? (size_t)r * it.hw : 0), gneg, acc, accx);
+                    }
+                }
+            }
+            if (GRAD) pg += 4 * (size_t)it.hw;
+            slot = (slot + 1) % kRingSlots;
+        }
+        item_finish<4, MODE, GRAD, FUSED>(A, it, tc, mt, acc, accx, inv_n, csum, bsum);
+    }
+    cp_async_wait<0>();
+    finish_block(A, csum, bsum, nrm);
+}
+
+static int g_sms = 0;
+static int sm_count() {
+    if (!g_sms) {
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, loss_kernel<MODE, GRAD, FUSED>, kLossThreads, 0);
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-        if (sms < 1) sms = 148;
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sms < 1) g_sms = 148;
     }
-    const long long total = args.item_off[args.g.nlev];
-    long long need = (total + kLossThreads - 1) / kLossThreads;
-    long long grid = (long long)sms * blocks_per_sm;
-    if (grid > kMaxPartials) grid = kMaxPartials;
+    return g_sms;
+}
+
+static int grid_for(long long items, int blocks_per_sm) {
+    long long need = (items + kLossThreads - 1) / kLossThreads;
+    long long grid = (long long)sm_count() * blocks_per_sm;
+    if (grid > kMaxPartials / 2) grid = kMaxPartials / 2;
     if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
-    *grid_out = (int)grid;
-    loss_kernel<MODE, GRAD, FUSED><<<(unsigned)grid, kLossThreads, 0, st>>>(args);
-    return check_launch("odk_loss/loss_kernel");
+    return (int)(grid < 1 ? 1 : grid);
+}
+
+template <int MODE, bool GRAD, bool FUSED>
+static int launch_loss(LossArgs &ring, LossArgs &plain, cudaStream_t st) {
+    static int occ_ring = 0, occ_plain = 0;
+    if (!occ_ring) {
+        cudaFuncSetAttribute(loss_kernel_ring<MODE, GRAD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ring, loss_kernel_ring<MODE, GRAD, FUSED>, kLossThreads, kRingBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_plain, loss_kernel<MODE, GRAD, FUSED>, kLossThreads, 0);
+        if (occ_ring < 1) occ_ring = 1;
+        if (occ_plain < 1) occ_plain = 1;
+    }
+    const long long n_ring = ring.item_off[ring.g.nlev], n_plain = plain.item_off[plain.g.nlev];
+    // The finishing launch sums every partial slot; the other one (if any) runs first on the stream.
+    int g_plain = 0, g_ring = 0;
+    if (n_plain > 0) g_plain = grid_for(n_plain, occ_plain);
+    if (n_ring > 0) g_ring = grid_for(n_ring, occ_ring);
+    if (n_plain > 0) {
+        plain.part_base = 0;
+        plain.part_total = n_ring > 0 ? 0 : g_plain;
+        loss_kernel<MODE, GRAD, FUSED><<<g_plain, kLossThreads, 0, st>>>(plain);
+        int rc = check_launch("odk_loss/loss_kernel");
+        if (rc) return rc;
+        if (n_ring > 0) {   // the ring launch starts from a zero counter again
+            cudaError_t e = cudaMemsetAsync(plain.counter, 0, sizeof(unsigned), st);
+            if (e != cudaSuccess) return set_error((int)e, "odk_loss memset: %s", cudaGetErrorString(e));
+        }
+    }
+    if (n_ring > 0) {
+        ring.part_base = g_plain;
+        ring.part_total = g_plain + g_ring;
+        loss_kernel_ring<MODE, GRAD, FUSED><<<g_ring, kLossThreads, kRingBytes, st>>>(ring);
+        return check_launch("odk_loss/loss_kernel_ring");
+    }
+    return ODK_OK;
 }
 
 }  // namespace odk
@@ -358,9 +597,11 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
     if ((uintptr_t)workspace & 15) return set_error(ODK_EINVAL, "odk_loss: workspace must be 16-byte aligned");
 
     a.B = B; a.C = C; a.Mmax = Mmax;
-    a.cchunk = C < 16 ? C : 16;
+    // class chunks: as few as possible with <= kMaxChunk classes each, so the per-item work (index
+    // decode, target lookup, positive patch) is amortised over up to 192 elements per thread
+    a.nchunk = (C + kMaxChunk - 1) / kMaxChunk;
+    a.cchunk = (C + a.nchunk - 1) / a.nchunk;
     a.nchunk = (C + a.cchunk - 1) / a.cchunk;
-    long long off = 0;
     a.div_nchunk = make_fastdiv((unsigned)a.nchunk);
     a.div_na = make_fastdiv((unsigned)na);
     for (int l = 0; l < num_levels; ++l) {
@@ -374,26 +615,33 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
         a.vec[l] = (a.g.hw[l] % 4 == 0 && (al & 15) == 0) ? 4 : 1;
         a.nq[l] = (a.g.hw[l] + a.vec[l] - 1) / a.vec[l];
         a.div_nq[l] = make_fastdiv((unsigned)a.nq[l]);
-        a.item_off[l] = (unsigned)off;
-        off += (long long)B * na * a.nchunk * a.nq[l];
-        if (off > 0x7fffffffll) return set_error(ODK_EUNSUPPORTED, "odk_loss: more than 2^31 work items");
     }
-    for (int l = num_levels; l <= ODK_MAX_LEVELS; ++l) a.item_off[l] = (unsigned)off;
     a.match = match; a.anchors = (const float4 *)anchors; a.gt_boxes = (const float4 *)gt_boxes; a.gt_labels = gt_labels;
     a.cls_t = cls_targets; a.box_t = box_targets; a.normalizer = normalizer; a.p = *params; a.out = out;
     a.partials = (double *)workspace;
     a.counter = (unsigned *)((char *)workspace + (size_t)kMaxPartials * 2 * sizeof(double));
+
+    // split the levels between the two kernels: item_off counts only the levels a launch covers
+    LossArgs ring = a, plain = a;
+    long long off_r = 0, off_p = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        const long long items = (long long)B * na * a.nchunk * a.nq[l];
+        ring.item_off[l] = (unsigned)off_r;
+        plain.item_off[l] = (unsigned)off_p;
+        if (a.vec[l] == 4) off_r += items; else off_p += items;
+        if (off_r > 0x7fffffffll || off_p > 0x7fffffffll) return set_error(ODK_EUNSUPPORTED, "odk_loss: more than 2^31 work items");
+    }
+    for (int l = num_levels; l <= ODK_MAX_LEVELS; ++l) { ring.item_off[l] = (unsigned)off_r; plain.item_off[l] = (unsigned)off_p; }
 
     cudaStream_t st = (cudaStream_t)stream;
     // the counter must be zero on entry; the kernel re-zeroes it, but a fresh workspace is arbitrary
     cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned), st);
     if (e != cudaSuccess) return set_error((int)e, "odk_loss memset: %s", cudaGetErrorString(e));
     const int mode = params->legacy_focal ? kLegacy : (params->label_smoothing > 0.0f ? kNewSmooth : kNew);
-    int grid = 0;
-#define ODK_LOSS_CASE(M)                                                                          \
-    if (mode == M) {                                                                              \
-        if (grad) return fused ? launch_loss<M, true, true>(a, &grid, st) : launch_loss<M, true, false>(a, &grid, st); \
-        return fused ? launch_loss<M, false, true>(a, &grid, st) : launch_loss<M, false, false>(a, &grid, st);         \
+#define ODK_LOSS_CASE(M)                                                                                       \
+    if (mode == M) {                                                                                           \
+        if (grad) return fused ? launch_loss<M, true, true>(ring, plain, st) : launch_loss<M, true, false>(ring, plain, st);   \
+        return fused ? launch_loss<M, false, true>(ring, plain, st) : launch_loss<M, false, false>(ring, plain, st);           \
     }
     ODK_LOSS_CASE(kNew)
     ODK_LOSS_CASE(kNewSmooth)
