@@ -304,15 +304,14 @@ def run_ours(args):
             'config': {'workload': WORKLOAD, 'global_batch': world * BATCH, 'parallelism': f'images sharded x{world}',
                        'l2': 'inputs (1.18 GB/step) larger than the 126 MB L2; no flush needed',
                        'loss_out': [float(x) for x in last]},
-            'roofline': {'bound': 'hbm', 'kernel': 'odk::loss_kernel<new,fwd,fused>', 'achieved': achieved, 'peak': peak,
+            'roofline': {'bound': 'hbm', 'kernel': 'odk::loss_kernel_ring<new,fwd,fused>', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': bytes_loss, 'kernel_ms': loss_ms},
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
                     'steps': e2e_steps},
-            'gpu_launches': 3 * args.steps,
-            'launches_per_step': {'odk::assign_kernel': 1, 'odk::assign_force_kernel': 1, 'odk::loss_kernel': 1,
-                                  'cudaMemsetAsync': 2},
+            'gpu_launches': 2 * args.steps,
+            'launches_per_step': {'odk::assign_kernel': 1, 'odk::loss_kernel_ring': 1, 'cudaMemsetAsync': 2},
             'clocks': clocks,
             'fwd_plus_grad': {'ms_per_step': fwd_bwd_ms, 'images_per_s': BATCH / (fwd_bwd_ms * 1e-3),
                               'achieved_GBps': 2 * bytes_loss / (fwd_bwd_ms * 1e-3) / 1e9,
