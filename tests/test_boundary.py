@@ -1,0 +1,141 @@
+"""Host-side checks that need no GPU: the C-ABI library loads and exports every symbol that
+include/odk.h declares, the python shims expose the reference's API surface, argument
+errors are reported through the ABI, and the drop-in `effdet` namespace resolves to our modules."""
+import ctypes
+import importlib
+import inspect
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'odk.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(odk_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ood_object_detection_b200 import _lib
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 17
+    for name in syms:
+        assert hasattr(handle, name), f'libodk.so does not export {name}'
+    # and the python binding table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == syms
+    assert _lib.lib().odk_version() == 1
+    assert _lib.lib().odk_planar_stride(49104) == 49104 and _lib.lib().odk_planar_stride(150381) == 150384
+
+
+def test_abi_argument_errors_without_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on the CPU box."""
+    from ood_object_detection_b200 import _lib
+    lib = _lib.lib()
+    hw = _lib.int_array([16, 4])
+    rc = lib.odk_assign(None, None, None, None, 2, 4, hw, 2, 9, 0.5, 1, None, None, None, 0, None)
+    assert rc == -1 and b'null pointer' in lib.odk_last_error()
+    rc = lib.odk_assign(None, None, None, None, 2, 4, hw, 9, 9, 0.5, 1, None, None, None, 0, None)
+    assert rc == -1 and b'num_levels' in lib.odk_last_error()
+    assert lib.odk_topk_workspace_bytes(4, 5000) > 4 * 16384 * 8
+    assert lib.odk_assign_workspace_bytes(4, 100) >= 4 * 100 * 8
+    with pytest.raises(RuntimeError):
+        _lib.check(rc)
+
+
+def test_shims_refuse_cpu_tensors():
+    from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
+    from ood_object_detection_b200.bench import _post_process
+    from ood_object_detection_b200 import soft_nms as S
+    anc = Anchors(3, 7, 3, [(1.0, 1.0), (1.4, 0.7), (0.7, 1.4)], 4.0, (128, 128))
+    lab = AnchorLabeler(anc, 20)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        lab.batch_label_anchors([torch.zeros(1, 4)], [torch.ones(1, dtype=torch.long)])
+    with pytest.raises(RuntimeError, match='CUDA'):
+        _post_process([torch.zeros(1, 9, 16, 16)], [torch.zeros(1, 36, 16, 16)], 1, 1, 10)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        S.soft_nms(torch.zeros(3, 4), torch.zeros(3))
+
+
+REFERENCE_API = {
+    'anchors': ['Anchors', 'AnchorLabeler', 'decode_box_outputs', 'clip_boxes_xyxy', 'generate_detections',
+                'get_feat_sizes', 'MIN_CLASS_SCORE'],
+    'loss': ['loss_fn', 'DetectionLoss', 'SupportLoss', 'smooth_l1_loss', 'l2_loss', 'cosine_loss', 'huber_loss',
+             'new_focal_loss', 'focal_loss_legacy', 'one_hot', 'class_loss_fn', 'box_only_loss', '_box_loss'],
+    'bench': ['_post_process', '_batch_detection', 'DetBenchPredict', 'DetBenchTrain', 'unwrap_bench'],
+    'soft_nms': ['soft_nms', 'batched_soft_nms', 'pairwise_iou'],
+    'object_detection': ['ArgMaxMatcher', 'FasterRcnnBoxCoder', 'BoxList', 'Match', 'IouSimilarity', 'TargetAssigner'],
+}
+
+
+def test_reference_api_surface():
+    for mod, names in REFERENCE_API.items():
+        m = importlib.import_module(f'ood_object_detection_b200.{mod}')
+        for n in names:
+            assert hasattr(m, n), f'{mod}.{n} missing'
+    from ood_object_detection_b200 import anchors, bench, loss, soft_nms
+    # signatures the reference scripts rely on (pretrain.py:241-246, infer.py:683-695)
+    assert list(inspect.signature(bench._post_process).parameters) == [
+        'cls_outputs', 'box_outputs', 'num_levels', 'num_classes', 'max_detection_points']
+    assert list(inspect.signature(anchors.generate_detections).parameters) == [
+        'cls_outputs', 'box_outputs', 'anchor_boxes', 'indices', 'classes', 'img_scale', 'img_size',
+        'max_det_per_image', 'soft_nms']
+    assert list(inspect.signature(loss.loss_fn).parameters)[:12] == [
+        'cls_outputs', 'box_outputs', 'cls_targets', 'box_targets', 'num_positives', 'num_classes', 'alpha', 'gamma',
+        'delta', 'box_loss_weight', 'label_smoothing', 'legacy_focal']
+    assert list(inspect.signature(anchors.AnchorLabeler.batch_label_anchors).parameters) == [
+        'self', 'gt_boxes', 'gt_classes', 'filter_valid', 'task_cls']
+    assert list(inspect.signature(soft_nms.soft_nms).parameters) == [
+        'boxes', 'scores', 'method_gaussian', 'sigma', 'iou_threshold', 'score_threshold']
+    a = anchors.Anchors(3, 7, 3, [(1.0, 1.0), (1.4, 0.7), (0.7, 1.4)], 4.0, (512, 512))
+    assert a.boxes.shape == (49104, 4) and a.get_anchors_per_location() == 9 and len(a.feat_sizes) == 8
+    lab = anchors.AnchorLabeler(a, 90)
+    for attr in ('target_assigner', 'anchors', 'match_threshold', 'num_classes', 'indices_cache'):
+        assert hasattr(lab, attr)
+    assert hasattr(lab.target_assigner, '_similarity_calc')   # used by the reference at anchors.py:401
+
+
+def test_dropin_namespace_resolves_to_kernels():
+    """`effdet.anchors` etc. resolve to our modules when the drop-in directory is first on sys.path."""
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import effdet.anchors as A, effdet.loss as L, effdet.bench as B, effdet.soft_nms as S\n"
+        "from effdet.object_detection import ArgMaxMatcher, FasterRcnnBoxCoder, BoxList, IouSimilarity, TargetAssigner\n"
+        "from effdet.anchors import Anchors, AnchorLabeler, generate_detections\n"
+        "from effdet.bench import _post_process, _batch_detection, DetBenchTrain, DetBenchPredict\n"
+        "from effdet.loss import DetectionLoss, SupportLoss, smooth_l1_loss, l2_loss, cosine_loss\n"
+        "import ood_object_detection_b200.anchors as OA\n"
+        "assert A.Anchors is OA.Anchors and B._post_process.__module__.startswith('ood_object_detection_b200')\n"
+        "print('ok')\n") % (ROOT, os.path.join(ROOT, 'ood_object_detection_b200', 'dropin'))
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == 'ok', out.stderr[-2000:]
+
+
+def test_matcher_and_coder_tensor_paths():
+    """The non-hot-path tensor implementations agree with the oracle on CPU tensors."""
+    import numpy as np
+    import synth
+    from oracle import oracle as orc
+    from ood_object_detection_b200.object_detection import ArgMaxMatcher, BoxList, FasterRcnnBoxCoder, Match
+    anc = orc.anchor_boxes(3, 7, 3, synth.ASPECTS, 4.0, (128, 128))
+    gb, gc = synth.gt_boxes(3, 1, 128, 7, 20)
+    sim = torch.from_numpy(orc.iou_matrix(gb[0], anc))
+    m = ArgMaxMatcher(0.5, 0.5, True, True).match(sim)
+    _, _, _, om, _ = orc.batch_label_anchors(anc, [gb[0]], [gc[0]])
+    np.testing.assert_array_equal(m.match_results.numpy(), om[0])
+    assert isinstance(m, Match) and m.num_matched_columns() == int((om[0] >= 0).sum())
+    assert ArgMaxMatcher(0.5, 0.5, True, True).match(sim[:0]).match_results.eq(-1).all()
+    pos = np.nonzero(om[0] >= 0)[0]
+    enc = FasterRcnnBoxCoder().encode(BoxList(torch.from_numpy(gb[0][om[0][pos]])), BoxList(torch.from_numpy(anc[pos])))
+    _, ob, _, _, _ = orc.batch_label_anchors(anc, [gb[0]], [gc[0]])
+    np.testing.assert_allclose(enc.numpy(), ob[0][pos], rtol=1e-5, atol=1e-7)
+    dec = FasterRcnnBoxCoder().decode(enc, BoxList(torch.from_numpy(anc[pos]))).boxes()
+    np.testing.assert_allclose(dec.numpy(), gb[0][om[0][pos]], rtol=1e-4, atol=1e-3)
+    with pytest.raises(ValueError):
+        ArgMaxMatcher(0.4, 0.5)
