@@ -509,6 +509,15 @@ ORC_API void orc_ood(const float *rows, int64_t n, int64_t C, float T, float *en
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the baseline leg asks for all host cores explicitly */
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

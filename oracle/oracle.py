@@ -44,6 +44,17 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def use_all_cores():
+    """OpenMP threads = cores this process may run on (launchers such as torchrun export
+    OMP_NUM_THREADS=1, which would turn the CPU baseline into a single-thread run)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(ctypes.c_int(n))
+    return num_threads()
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
