@@ -148,7 +148,7 @@ def run_ours(args):
     from ood_object_detection_b200 import _lib
     from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
     from ood_object_detection_b200.loss import loss_fn_fused
-    from ood_object_detection_b200.distributed import global_normalizer, reduce_losses
+    from ood_object_detection_b200.distributed import forward_losses_one_collective, global_normalizer, reduce_losses
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -174,19 +174,18 @@ def run_ours(args):
     A = anchors.boxes.shape[0]
     bytes_loss = BATCH * A * (4 * NUM_CLASSES + 16)          # A*(4C+16) bytes per image, forward
 
+    unit = torch.ones((1,), dtype=torch.float32, device=dev)
+
     def step(record=None):
         lb = labeler.assign(gt_boxes, gt_cls)
-        if world > 1:
-            norm = global_normalizer(lb.num_positives)
-        else:
-            norm = None
         if record is not None:
             record[0].record()
-        out = loss_fn_fused(cls_out, box_out, lb, normalizer=norm, **LOSS_KW)
+        # N > 1 (forward): partial sums against a unit normaliser, ONE all-reduce of 3 floats, divide after
+        out = loss_fn_fused(cls_out, box_out, lb, normalizer=unit if world > 1 else None, **LOSS_KW)
         if record is not None:
             record[1].record()
         if world > 1:
-            out = reduce_losses(*out)
+            out = forward_losses_one_collective(out[1], out[2], lb.num_positives, LOSS_KW['box_loss_weight'])
         return out
 
     def sync_all():
@@ -261,10 +260,9 @@ def run_ours(args):
             d_cls = [t.to(dev, non_blocking=True) for t in h_cls]
             d_box = [t.to(dev, non_blocking=True) for t in h_box]
             lb = labeler.assign(h_gb.to(dev, non_blocking=True), h_gc.to(dev, non_blocking=True))
-            norm = global_normalizer(lb.num_positives) if world > 1 else None
-            out = loss_fn_fused(d_cls, d_box, lb, normalizer=norm, **LOSS_KW)
+            out = loss_fn_fused(d_cls, d_box, lb, normalizer=unit if world > 1 else None, **LOSS_KW)
             if world > 1:
-                out = reduce_losses(*out)
+                out = forward_losses_one_collective(out[1], out[2], lb.num_positives, LOSS_KW['box_loss_weight'])
             h_out.copy_(torch.stack(list(out)), non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return h_out

@@ -44,6 +44,20 @@ def reduce_losses(total, cls_loss, box_loss, group=None):
     return packed[0], packed[1], packed[2]
 
 
+def forward_losses_one_collective(cls_unnorm, box_unnorm, num_positives, box_loss_weight, group=None):
+    """Forward-only variant with ONE collective: every rank computes its partial sums
+    against a unit normaliser, a single all-reduce carries [sum_cls, sum_box, sum_num_positives], and
+    the division by the global (num_positives + 1) happens afterwards.  Returns (total, cls, box).
+    (With gradients use ``sharded_detection_loss``: the backward scale needs the global N up front.)"""
+    packed = torch.stack([cls_unnorm.detach().reshape(()).float(), box_unnorm.detach().reshape(()).float(),
+                          num_positives.float().sum().reshape(())])
+    if _active(group):
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    n = packed[2] + 1.0
+    cls_loss, box_loss = packed[0] / n, packed[1] / n
+    return cls_loss + box_loss_weight * box_loss, cls_loss, box_loss
+
+
 def sharded_detection_loss(loss_module, cls_outputs, box_outputs, label_batch, group=None):
     """Local shard's fused loss against the GLOBAL normaliser.
 

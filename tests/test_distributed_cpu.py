@@ -44,6 +44,10 @@ def _worker(rank, world, port, out_dir):
     part = orc.loss_fn([c[lo:hi] for c in co], [b[lo:hi] for b in bo], orc.split_levels(cls_t, fhw),
                        orc.split_levels(box_t, fhw), fake_npos, C, 0.25, 1.5, 0.1, 50.0)
     tot, cl, bl = D.reduce_losses(*[torch.tensor(v, dtype=torch.float64) for v in part])
+    # forward-only form: unit normaliser locally, one collective, divide by the global N afterwards
+    unit = orc.loss_fn([c[lo:hi] for c in co], [b[lo:hi] for b in bo], orc.split_levels(cls_t, fhw),
+                       orc.split_levels(box_t, fhw), np.zeros(1, np.float32), C, 0.25, 1.5, 0.1, 50.0)
+    one = D.forward_losses_one_collective(torch.tensor(unit[1]), torch.tensor(unit[2]), torch.from_numpy(npos), 50.0)
     # ---- detections: each rank post-processes its images, all-gather in rank order ----
     o_cls, o_box, o_idx, o_klass = orc.post_process([c[lo:hi] for c in co], [b[lo:hi] for b in bo], 5, C, 300)
     Dmax = 20
@@ -56,6 +60,7 @@ def _worker(rank, world, port, out_dir):
     g_dets, g_count = D.gather_detections(dets, count)
     if rank == 0:
         np.savez(os.path.join(out_dir, 'sharded.npz'), loss=np.array([tot.item(), cl.item(), bl.item()]),
+                 one=np.array([float(v) for v in one]),
                  dets=g_dets.numpy(), count=g_count.numpy(), norm=norm.numpy())
     dist.barrier()
     dist.destroy_process_group()
@@ -77,6 +82,7 @@ def test_sharded_path_matches_single_process(tmp_path):
     ref = orc.loss_fn(co, bo, orc.split_levels(cls_t, fhw), orc.split_levels(box_t, fhw), npos, C, 0.25, 1.5, 0.1, 50.0)
     np.testing.assert_allclose(got['norm'], npos.sum() + 1.0)
     np.testing.assert_allclose(got['loss'], ref, rtol=1e-6)   # same element values, different summation split
+    np.testing.assert_allclose(got['one'], ref, rtol=1e-5)    # one-collective forward form (fp32 wire format)
     o_cls, o_box, o_idx, o_klass = orc.post_process(co, bo, 5, C, 300)
     assert got['dets'].shape == (B, 20, 6)
     for i in range(B):
