@@ -65,6 +65,19 @@ int odk_assign(const float *anchors, const float *gt_boxes, const int32_t *gt_la
                int Mmax, const int32_t *level_hw, int num_levels, int na, float match_thr, int filter_valid,
                int32_t *match, float *num_pos, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Same result as odk_assign for anchors that are REGULAR GRIDS per (level, shape) -- the pyramid
+ * of anchors.py:264-299 -- in time proportional to the anchors each gt box can touch instead of
+ * B*M*A (a CTA per gt enumerates only the cells of the planes that can matter).
+ *   plane_desc  DEVICE [num_levels*na][12] fp32, plane k = level*na + shape:
+ *               cy0, cx0 (centre of cell (0,0)), sy, sx (cell pitch), hy, hx (half sizes), area,
+ *               W, H, off_l, shape, level
+ * match_thr must be > 0.  Workspace: odk_assign_grid_workspace_bytes(B, A). */
+size_t odk_assign_grid_workspace_bytes(int B, int64_t A);
+int odk_assign_grid(const float *anchors, const float *plane_desc, int num_planes, const float *gt_boxes,
+                    const int32_t *gt_labels, const int32_t *gt_count, int B, int Mmax, const int32_t *level_hw,
+                    int num_levels, int na, float match_thr, int filter_valid, int32_t *match, float *num_pos,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
 /* Pairwise IoU matrix out[n,m] of yxyx boxes: IouSimilarity.compare
  * (region_similarity_calculator.py:59-101), same fp32 operation order. */
 int odk_iou_matrix(const float *boxes1, int n, const float *boxes2, int m, float *out, void *stream);

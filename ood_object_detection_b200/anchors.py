@@ -56,6 +56,7 @@ class Anchors(nn.Module):
         self.feat_sizes = get_feat_sizes(image_size, max_level)
         self.config = self._generate_configs()
         self.register_buffer('boxes', self._generate_boxes())
+        self.register_buffer('plane_desc', self._generate_plane_desc())
 
     @classmethod
     def from_config(cls, config, img_size=None, min_level=0):
@@ -99,6 +100,24 @@ class Anchors(nn.Module):
 
     def get_anchors_per_location(self):
         return self.num_scales * len(self.aspect_ratios)
+
+    def _generate_plane_desc(self):
+        """[levels*na, 12] fp32 description of every (level, shape) anchor grid for odk_assign_grid:
+        cy0, cx0, sy, sx, hy, hx, area, W, H, off_l, shape, level -- read off the anchor table itself."""
+        boxes = self.boxes.double().numpy()
+        na = self.get_anchors_per_location()
+        rows, off = [], 0
+        for li, level in enumerate(range(self.min_level, self.max_level + 1)):
+            h, w = self.feat_sizes[level]
+            for a in range(na):
+                b00 = boxes[off + a]
+                cy0, cx0 = (b00[0] + b00[2]) / 2, (b00[1] + b00[3]) / 2
+                sy = (boxes[off + w * na + a][0] + boxes[off + w * na + a][2]) / 2 - cy0 if h > 1 else 1.0
+                sx = (boxes[off + na + a][1] + boxes[off + na + a][3]) / 2 - cx0 if w > 1 else 1.0
+                hy, hx = (b00[2] - b00[0]) / 2, (b00[3] - b00[1]) / 2
+                rows.append([cy0, cx0, sy, sx, hy, hx, 4 * hy * hx, w, h, off, a, li])
+            off += h * w * na
+        return torch.tensor(rows, dtype=torch.float32)
 
     # ---- libodk geometry -------------------------------------------------------------------
     def level_hw(self):
@@ -150,6 +169,9 @@ class AnchorLabeler(object):
         self.match_threshold = match_threshold
         self.num_classes = num_classes
         self.indices_cache = {}
+        # gt-centric kernel (odk_assign_grid) for the regular pyramid grids; the dense kernel
+        # (odk_assign) is kept for arbitrary anchor sets and non-positive thresholds
+        self.use_grid_kernel = True
 
     # ---- helpers ---------------------------------------------------------------------------
     def _device(self):
@@ -204,15 +226,25 @@ class AnchorLabeler(object):
         apad = lib.odk_planar_stride(A)
         match = torch.empty((B, apad), dtype=torch.int32, device=dev)
         num_pos = torch.empty((B,), dtype=torch.float32, device=dev)
-        ws_bytes = lib.odk_assign_workspace_bytes(B, M)
-        ws = torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=dev)
         hw = self.anchors.level_hw()
+        na = self.anchors.get_anchors_per_location()
+        thr = float(np.float32(self.match_threshold))
+        desc = getattr(self.anchors, 'plane_desc', None)
         with torch.cuda.device(dev):
-            _lib.check(lib.odk_assign(_lib.ptr(anc), _lib.ptr(boxes), _lib.ptr(labels), _lib.ptr(count), B, M,
-                                      _lib.int_array(hw), len(hw), self.anchors.get_anchors_per_location(),
-                                      float(np.float32(self.match_threshold)), int(bool(filter_valid)),
-                                      _lib.ptr(match), _lib.ptr(num_pos), _lib.ptr(ws), ws.numel() * 8,
-                                      _lib.stream_ptr(dev)))
+            if self.use_grid_kernel and desc is not None and thr > 0.0:
+                ws_bytes = lib.odk_assign_grid_workspace_bytes(B, A)
+                ws = torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=dev)
+                _lib.check(lib.odk_assign_grid(_lib.ptr(anc), _lib.ptr(desc), desc.shape[0], _lib.ptr(boxes),
+                                               _lib.ptr(labels), _lib.ptr(count), B, M, _lib.int_array(hw), len(hw), na,
+                                               thr, int(bool(filter_valid)), _lib.ptr(match), _lib.ptr(num_pos),
+                                               _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr(dev)))
+            else:
+                ws_bytes = lib.odk_assign_workspace_bytes(B, M)
+                ws = torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=dev)
+                _lib.check(lib.odk_assign(_lib.ptr(anc), _lib.ptr(boxes), _lib.ptr(labels), _lib.ptr(count), B, M,
+                                          _lib.int_array(hw), len(hw), na, thr, int(bool(filter_valid)),
+                                          _lib.ptr(match), _lib.ptr(num_pos), _lib.ptr(ws), ws.numel() * 8,
+                                          _lib.stream_ptr(dev)))
         return LabelBatch(self, boxes, labels, match, num_pos)
 
     def _materialize(self, lb: LabelBatch):

@@ -312,6 +312,158 @@ targets_kernel(const Geo g, int B, const float4 *__restrict__ anchors, const flo
     box_targets[o] = t;
 }
 
+// ---- gt-centric assignment over regular anchor grids ----------------------------------------------
+// The pyramid's anchors are regular grids: plane k = (level, shape) has centres (cy0 + y*sy, cx0 + x*sx)
+// and one half-size.  A gt box can only have a positive IoU with the cells whose anchor overlaps it, and
+// IoU <= min(area)/max(area), so instead of testing every (gt, anchor) pair a CTA per gt enumerates
+//   pass 0: the planes whose area bound can reach the match threshold (these hold every match), and
+//   pass 1: only if its best IoU is still below the threshold, the planes whose bound exceeds that best
+//           (the forced match needs the true arg-max).
+// The enumeration is a superset of the pairs that matter and every IoU is still computed from the fp32
+// anchor table in the reference's operation order, so results are bit-identical to the dense kernel.
+// One 64-bit atomicMax array keys[B, Apad] resolves everything: an IoU>=thr pair writes
+// (iou_bits<<32 | ~gt) (highest IoU, then lowest gt row: torch.max's first index), a forced match writes
+// (0xFFFFFFFF<<32 | ~gt) (beats any IoU; lowest gt row wins, argmax_matcher.py:141-143).  The first
+// writer of an anchor (old key 0) counts it into num_positives.
+constexpr int kGtcThreads = 256;
+constexpr int kMaxPlanes = ODK_MAX_LEVELS * 16;
+constexpr int kDescFloats = 12;   // cy0, cx0, sy, sx, hy, hx, area, W, H, off, a, level
+
+__global__ void __launch_bounds__(kGtcThreads)
+assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *__restrict__ desc, int nplanes,
+                 const float4 *__restrict__ gt_boxes, const int32_t *__restrict__ gt_labels,
+                 const int32_t *__restrict__ gt_count, int Mmax, float thr, int filter_valid,
+                 unsigned long long *keys, int32_t *pos_count) {
+    __shared__ int s_off[kMaxPlanes + 1], s_x0[kMaxPlanes], s_nx[kMaxPlanes], s_y0[kMaxPlanes];
+    __shared__ unsigned char s_done[kMaxPlanes];
+    __shared__ unsigned long long s_red[kGtcThreads / 32];
+    __shared__ unsigned long long s_best;
+    const int b = blockIdx.y, i = blockIdx.x;
+    int M = Mmax;
+    if (gt_count) M = min(max(__ldg(gt_count + b), 0), Mmax);
+    if (i >= M) return;
+    if (filter_valid && __ldg(gt_labels + (size_t)b * Mmax + i) < 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float4 q = __ldg(gt_boxes + (size_t)b * Mmax + i);
+    const float qa = area_ref(q.x, q.y, q.z, q.w);
+    if (tid == 0) s_best = 0ull;
+    for (int k = tid; k < nplanes; k += kGtcThreads) s_done[k] = 0;
+    __syncthreads();
+    unsigned long long *krow = keys + (size_t)b * g.Apad;
+
+    for (int pass = 0; pass < 2; ++pass) {
+        // ---- which planes, which cells ----
+        const float best_so_far = __uint_as_float((unsigned)(s_best >> 32));
+        for (int k = tid; k < nplanes; k += kGtcThreads) {
+            const float *d = desc + (size_t)k * kDescFloats;
+            int nx = 0, ny = 0, x0 = 0, y0 = 0;
+            if (!s_done[k] && qa > 0.0f) {
+                const float pa = d[6];
+                const float bound = fminf(pa, qa) / fmaxf(pa, qa) * 1.00001f;   // >= any IoU in this plane
+                const bool want = pass == 0 ? (bound >= thr) : (bound > best_so_far);
+                if (want) {
+                    const int W = (int)d[7], H = (int)d[8];
+                    // centres strictly inside (g0 - h, g1 + h) can overlap; widen by one cell for rounding
+                    const float ylo = (q.x - d[4] - d[0]) / d[2], yhi = (q.z + d[4] - d[0]) / d[2];
+                    const float xlo = (q.y - d[5] - d[1]) / d[3], xhi = (q.w + d[5] - d[1]) / d[3];
+                    const int ya = max((int)floorf(ylo) - 1, 0), yb = min((int)ceilf(yhi) + 1, H - 1);
+                    const int xa = max((int)floorf(xlo) - 1, 0), xb = min((int)ceilf(xhi) + 1, W - 1);
+                    if (yb >= ya && xb >= xa) { ny = yb - ya + 1; nx = xb - xa + 1; y0 = ya; x0 = xa; }
+                    s_done[k] = 1;
+                }
+            }
+            s_x0[k] = x0; s_y0[k] = y0; s_nx[k] = nx;
+            s_off[k + 1] = nx * ny;   // turned into a prefix sum below
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_off[0] = 0;
+            for (int k = 0; k < nplanes; ++k) s_off[k + 1] += s_off[k];
+        }
+        __syncthreads();
+        const int total = s_off[nplanes];
+        if (total == 0) continue;   // uniform (pass 0 may select nothing: pass 1 still has to look)
+
+        // ---- enumerate the cells ----
+        unsigned long long best = 0ull;
+        for (int c = tid; c < total; c += kGtcThreads) {
+            int lo = 0, hi = nplanes - 1;   // last plane with s_off[k] <= c
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_off[mid] <= c) lo = mid; else hi = mid - 1;
+            }
+            const int k = lo;
+            const float *d = desc + (size_t)k * kDescFloats;
+            const int loc = c - s_off[k];
+            const int nx = s_nx[k];
+            const int yy = s_y0[k] + loc / nx, xx = s_x0[k] + loc % nx;
+            const int W = (int)d[7], off = (int)d[9], sh = (int)d[10], lev = (int)d[11];
+            const int cell = yy * W + xx;
+            const int r = off + cell * g.na + sh;
+            const float4 a = __ldg(anchors + r);
+            const float h = __fsub_rn(fminf(q.z, a.z), fmaxf(q.x, a.x));
+            const float w = __fsub_rn(fminf(q.w, a.w), fmaxf(q.y, a.y));
+            if (h > 0.0f && w > 0.0f) {
+                const float inter = __fmul_rn(h, w);
+                if (inter != 0.0f) {
+                    const float v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(qa, area_ref(a.x, a.y, a.z, a.w)), inter));
+                    if (v > 0.0f) {
+                        const unsigned long long kr =
+                            ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+                        best = kr > best ? kr : best;
+                        if (!(thr > v)) {   // a candidate match for this anchor (argmax_matcher.py:126-137)
+                            const int p = off + sh * g.hw[lev] + cell;
+                            const unsigned long long kg =
+                                ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+                            if (atomicMax(krow + p, kg) == 0ull) atomicAdd(pos_count + (size_t)b * kCtrStride, 1);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (lane == 0) s_red[warp] = best;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long v = s_best;
+            for (int w = 0; w < kGtcThreads / 32; ++w) v = s_red[w] > v ? s_red[w] : v;
+            s_best = v;
+        }
+        __syncthreads();
+    }
+    // ---- forced match: the arg-max anchor (anchor 0 when the gt overlaps nothing) ----
+    if (tid == 0) {
+        const unsigned long long kb = s_best;
+        const int r = kb ? (int)(0xFFFFFFFFu - (unsigned)(kb & 0xFFFFFFFFull)) : 0;
+        int l;
+        const int p = ref_to_planar(g, r, l);
+        const unsigned long long kf = (0xFFFFFFFFull << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+        if (atomicMax(krow + p, kf) == 0ull) atomicAdd(pos_count + (size_t)b * kCtrStride, 1);
+    }
+}
+
+// keys -> match (gt row or -1) and num_positives; four anchors per thread
+__global__ void __launch_bounds__(256)
+keys_to_match_kernel(const Geo g, int B, const unsigned long long *__restrict__ keys, const int32_t *__restrict__ pos_count,
+                     int32_t *__restrict__ match, float *__restrict__ num_pos) {
+    const size_t n4 = (size_t)B * g.Apad / 4;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (size_t)B) num_pos[t] = (float)__ldg(pos_count + t * kCtrStride);
+    if (t >= n4) return;
+    const ulonglong2 k01 = __ldcg(reinterpret_cast<const ulonglong2 *>(keys) + 2 * t);
+    const ulonglong2 k23 = __ldcg(reinterpret_cast<const ulonglong2 *>(keys) + 2 * t + 1);
+    int4 m;
+    m.x = k01.x ? (int)(0xFFFFFFFFu - (unsigned)(k01.x & 0xFFFFFFFFull)) : -1;
+    m.y = k01.y ? (int)(0xFFFFFFFFu - (unsigned)(k01.y & 0xFFFFFFFFull)) : -1;
+    m.z = k23.x ? (int)(0xFFFFFFFFu - (unsigned)(k23.x & 0xFFFFFFFFull)) : -1;
+    m.w = k23.y ? (int)(0xFFFFFFFFu - (unsigned)(k23.y & 0xFFFFFFFFull)) : -1;
+    reinterpret_cast<int4 *>(match)[t] = m;
+}
+
 __global__ void iou_matrix_kernel(const float4 *__restrict__ b1, int n, const float4 *__restrict__ b2, int m,
                                   float *__restrict__ out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -396,6 +548,52 @@ int odk_assign(const float *anchors, const float *gt_boxes, const int32_t *gt_la
             g, (const float4 *)anchors, (const float4 *)gt_boxes, gt_labels, gt_count, Mmax, match_thr, filter_valid,
             match_thr > 0.0f ? 1 : 0, match, best, pos, done, num_pos);
     return check_launch("odk_assign/assign_kernel");
+}
+
+
+size_t odk_assign_grid_workspace_bytes(int B, int64_t A) {
+    if (B < 0 || A < 0) return 0;
+    return (size_t)B * (size_t)odk_planar_stride(A) * sizeof(unsigned long long) + (size_t)B * odk::kCtrStride * sizeof(int32_t) + 16;
+}
+
+int odk_assign_grid(const float *anchors, const float *plane_desc, int num_planes, const float *gt_boxes,
+                    const int32_t *gt_labels, const int32_t *gt_count, int B, int Mmax, const int32_t *level_hw,
+                    int num_levels, int na, float match_thr, int filter_valid, int32_t *match, float *num_pos,
+                    void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace odk;
+    Geo g;
+    int rc = make_geo(&g, level_hw, num_levels, na);
+    if (rc) return rc;
+    if (B < 0 || Mmax < 0) return set_error(ODK_EINVAL, "odk_assign_grid: negative size");
+    if (B == 0) return ODK_OK;
+    if (!anchors || !plane_desc || !match || !num_pos || (Mmax > 0 && (!gt_boxes || !gt_labels)))
+        return set_error(ODK_EINVAL, "odk_assign_grid: null pointer");
+    if (num_planes != num_levels * na || num_planes > kMaxPlanes)
+        return set_error(ODK_EINVAL, "odk_assign_grid: need one descriptor per (level, shape), at most %d", kMaxPlanes);
+    if (!(match_thr > 0.0f)) return set_error(ODK_EUNSUPPORTED, "odk_assign_grid: match_thr must be > 0 (use odk_assign)");
+    if (B > 65535) return set_error(ODK_EUNSUPPORTED, "odk_assign_grid: batch > 65535");
+    if (workspace_bytes < odk_assign_grid_workspace_bytes(B, g.A) || !workspace)
+        return set_error(ODK_EWORKSPACE, "odk_assign_grid: workspace too small (%zu < %zu)", workspace_bytes,
+                         odk_assign_grid_workspace_bytes(B, g.A));
+    if (((uintptr_t)anchors | (uintptr_t)gt_boxes | (uintptr_t)workspace | (uintptr_t)match) & 15)
+        return set_error(ODK_EINVAL, "odk_assign_grid: anchors / gt_boxes / match / workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *keys = (unsigned long long *)workspace;
+    int32_t *pos = (int32_t *)((char *)workspace + (size_t)B * g.Apad * sizeof(unsigned long long));
+    cudaError_t e = cudaMemsetAsync(workspace, 0, odk_assign_grid_workspace_bytes(B, g.A) - 16, st);
+    if (e != cudaSuccess) return set_error((int)e, "odk_assign_grid memset: %s", cudaGetErrorString(e));
+    if (Mmax > 0) {
+        dim3 grid(Mmax, B);
+        assign_gt_kernel<<<grid, kGtcThreads, 0, st>>>(g, (const float4 *)anchors, plane_desc, num_planes,
+                                                       (const float4 *)gt_boxes, gt_labels, gt_count, Mmax, match_thr,
+                                                       filter_valid, keys, pos);
+        rc = check_launch("odk_assign_grid/assign_gt_kernel");
+        if (rc) return rc;
+    }
+    const size_t n4 = (size_t)B * g.Apad / 4;
+    const size_t threads = n4 > (size_t)B ? n4 : (size_t)B;
+    keys_to_match_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g, B, keys, pos, match, num_pos);
+    return check_launch("odk_assign_grid/keys_to_match_kernel");
 }
 
 int odk_targets(const float *anchors, const float *gt_boxes, const int32_t *gt_labels, int B, int Mmax,

@@ -16,10 +16,21 @@ def dev():
     return torch.device('cuda:0')
 
 
+USE_GRID = [True]   # flipped by the `kernel` fixture: every labeler test runs on both assignment kernels
+
+
+@pytest.fixture(autouse=True, params=['grid', 'dense'])
+def kernel(request):
+    USE_GRID[0] = request.param == 'grid'
+    yield request.param
+
+
 def make_labeler(size, scale=4.0, num_classes=90, thr=0.5):
     from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
     anc = Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size)).to(dev())
-    return anc, AnchorLabeler(anc, num_classes, match_threshold=thr)
+    lab = AnchorLabeler(anc, num_classes, match_threshold=thr)
+    lab.use_grid_kernel = USE_GRID[0]
+    return anc, lab
 
 
 def flat_targets(cls_t, box_t):
