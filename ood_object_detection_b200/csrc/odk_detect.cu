@@ -98,15 +98,27 @@ __device__ __forceinline__ void init_alive(unsigned *alive, int n, int cap) {
 // Greedy NMS over candidates already in descending score order.  Returns the number kept
 // (<= max_keep); kept[q] = candidate rank.  thr_f is the largest float <= the double threshold,
 // so `iou > thr_f` equals torchvision's `(double)iou > thr`.
-__device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_keep, int *kept) {
+// Lazy window: only the first `window` candidates are "activated" at first; a later chunk is
+// activated (each of its candidates tested against everything kept so far) only when the window
+// runs out of alive candidates.  When the first max_keep survivors come from the first chunk --
+// the common case -- the other candidates are never touched.  Same result as testing everything.
+__device__ __forceinline__ bool nms_hit(float4 p, float ap, float4 q, float thr_f) {
+    // boxes of other classes sit in other offset bands: when the x or y extents do not overlap the
+    // intersection is 0 and the IoU cannot exceed a threshold >= 0, so the division is skipped
+    const bool touch = (fminf(p.z, q.z) > fmaxf(p.x, q.x)) && (fminf(p.w, q.w) > fmaxf(p.y, q.y));
+    return (touch || thr_f < 0.0f) && iou_nms(p, ap, q) > thr_f;
+}
+
+__device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_keep, int *kept, int window) {
     __shared__ int s_first[kDetWarps];
     __shared__ int s_top;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwords = (n + 31) / 32;
+    int limit = min(n, window);   // activated prefix (a multiple of 32 or n)
     int count = 0;
     int from = 0;   // every word below `from` is known dead
     while (count < max_keep) {
-        // first alive candidate
+        const int nwords = (limit + 31) / 32;
+        // first alive candidate of the activated prefix
         int mine = 0x7fffffff;
         for (int w = from + threadIdx.x; w < nwords; w += kDetThreads) {
             const unsigned m = S.alive[w];
@@ -121,7 +133,28 @@ __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_kee
         }
         __syncthreads();
         const int top = s_top;
-        if (top == 0x7fffffff) break;
+        if (top == 0x7fffffff) {
+            if (limit >= n) break;
+            // activate the next chunk: a candidate stays alive iff nothing kept so far suppresses it
+            const int new_limit = min(n, limit + window);
+            for (int w = limit / 32 + warp; w < (new_limit + 31) / 32; w += kDetWarps) {
+                const int i = w * 32 + lane;
+                bool dead = i >= new_limit;
+                if (!dead) {
+                    const float4 q = S.box[i];
+                    for (int c = 0; c < count && !dead; ++c) {
+                        const float4 p = S.box[kept[c]];
+                        dead = nms_hit(p, __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y)), q, thr_f);
+                    }
+                }
+                const unsigned k = __ballot_sync(0xffffffffu, !dead);
+                if (lane == 0) S.alive[w] = k;
+            }
+            from = limit / 32;
+            limit = new_limit;
+            __syncthreads();
+            continue;
+        }
         if (threadIdx.x == 0) kept[count] = top;
         ++count;
         from = top >> 5;
@@ -132,17 +165,7 @@ __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_kee
             if (!m) continue;
             const int i = w * 32 + lane;
             bool kill = false;
-            if ((m >> lane) & 1u) {
-                kill = i == top;
-                if (i > top) {
-                    // boxes of other classes sit in other offset bands: when the x or y extents do
-                    // not overlap the intersection is 0 and the IoU cannot exceed a threshold >= 0,
-                    // so the division is skipped (identical result, ~7x fewer instructions)
-                    const float4 q = S.box[i];
-                    const bool touch = (fminf(p.z, q.z) > fmaxf(p.x, q.x)) && (fminf(p.w, q.w) > fmaxf(p.y, q.y));
-                    if (touch || thr_f < 0.0f) kill = iou_nms(p, ap, q) > thr_f;
-                }
-            }
+            if ((m >> lane) & 1u) kill = i == top || (i > top && nms_hit(p, ap, S.box[i], thr_f));
             const unsigned k = __ballot_sync(0xffffffffu, kill);
             if (lane == 0 && k) S.alive[w] = m & ~k;
         }
@@ -151,17 +174,31 @@ __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_kee
     return count;
 }
 
-// Soft-NMS rounds (soft_nms.py:88-110).  Returns rounds run; kept[q] = candidate rank, kept_score
-// [q] = its score when picked.  `emit` is called by thread 0 for every pick.
+// Soft-NMS rounds (soft_nms.py:88-110).  Returns rounds run; `emit(q, rank, score)` is called by
+// thread 0 for every pick, `picked[q]` receives the rank.  Lazy window (only valid when the input
+// scores are non-increasing, i.e. `window < n` must not be used otherwise): the arg-max over the
+// activated prefix is the global arg-max as long as it is >= the ORIGINAL score of the first
+// un-activated candidate (scores only ever decay).  Otherwise the next chunk is activated by
+// replaying, in order, the decays of all picks so far on each of its candidates -- the same fp32
+// operations in the same order as if it had been active from the start.
+__device__ __forceinline__ float soft_decay(float4 p, float ap, float4 q, bool gaussian, float sigma, float iou_thr) {
+    // disjoint extents -> iou 0 -> decay exactly 1
+    if (!((fminf(p.z, q.z) > fmaxf(p.x, q.x)) && (fminf(p.w, q.w) > fmaxf(p.y, q.y)))) return 1.0f;
+    const float iou = iou_soft(p, ap, q);
+    if (gaussian) return expf(__fdiv_rn(-__fmul_rn(iou, iou), sigma));   // soft_nms.py:96
+    return iou > iou_thr ? __fsub_rn(1.0f, iou) : 1.0f;                   // :98-100
+}
+
 template <class Emit>
 __device__ int soft_nms_rounds(const DetSmem &S, int n, bool gaussian, float sigma, float iou_thr, float score_thr,
-                               int max_rounds, Emit emit) {
+                               int max_rounds, int *picked, int window, Emit emit) {
     __shared__ unsigned long long s_best[kDetWarps];
     __shared__ unsigned long long s_pick;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwords = (n + 31) / 32;
+    int limit = min(n, window);
     int count = 0;
     while (count < max_rounds) {
+        const int nwords = (limit + 31) / 32;
         // block arg-max on (score key, ~rank): highest score, first index on ties
         unsigned long long best = 0ull;
         for (int w = warp; w < nwords; w += kDetWarps) {
@@ -194,9 +231,37 @@ __device__ int soft_nms_rounds(const DetSmem &S, int n, bool gaussian, float sig
         }
         __syncthreads();
         const unsigned long long pick = s_pick;
+        if (limit < n) {
+            // un-activated candidates still carry their original scores; the first one bounds them all
+            const unsigned ub = __float_as_uint(S.score[limit]);
+            const unsigned bk = ub ^ ((unsigned)((int)ub >> 31) | 0x80000000u);
+            if (pick == 0ull || (unsigned)(pick >> 32) < bk) {
+                const int new_limit = min(n, limit + window);
+                for (int w = limit / 32 + warp; w < (new_limit + 31) / 32; w += kDetWarps) {
+                    const int i = w * 32 + lane;
+                    bool ok = i < new_limit;
+                    if (ok) {
+                        const float4 q = S.box[i];
+                        float sc = S.score[i];
+                        for (int c = 0; c < count && ok; ++c) {
+                            const float4 p = S.box[picked[c]];
+                            const float d = soft_decay(p, __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y)), q, gaussian, sigma, iou_thr);
+                            if (d != 1.0f) sc = __fmul_rn(sc, d);
+                            ok = sc > score_thr;
+                        }
+                        S.score[i] = sc;
+                    }
+                    const unsigned k = __ballot_sync(0xffffffffu, ok);
+                    if (lane == 0) S.alive[w] = k;
+                }
+                limit = new_limit;
+                __syncthreads();
+                continue;
+            }
+        }
         if (pick == 0ull) break;
         const int top = (int)(0xFFFFFFFFu - (unsigned)(pick & 0xFFFFFFFFull));
-        if (threadIdx.x == 0) emit(count, top, S.score[top]);
+        if (threadIdx.x == 0) { emit(count, top, S.score[top]); picked[count] = top; }
         ++count;
         const float4 p = S.box[top];
         const float ap = __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y));
@@ -207,17 +272,9 @@ __device__ int soft_nms_rounds(const DetSmem &S, int n, bool gaussian, float sig
             const int i = w * 32 + lane;
             bool kill = false;
             if ((m >> lane) & 1u) {
-                const float4 q = S.box[i];
                 float sc = S.score[i];
-                // disjoint extents -> iou 0 -> decay exactly 1: the score is unchanged, skip the math
-                if ((fminf(p.z, q.z) > fmaxf(p.x, q.x)) && (fminf(p.w, q.w) > fmaxf(p.y, q.y))) {
-                    const float iou = iou_soft(p, ap, q);
-                    float decay;
-                    if (gaussian) decay = expf(__fdiv_rn(-__fmul_rn(iou, iou), sigma));   // soft_nms.py:96
-                    else decay = iou > iou_thr ? __fsub_rn(1.0f, iou) : 1.0f;             // :98-100
-                    sc = __fmul_rn(sc, decay);
-                    S.score[i] = sc;
-                }
+                const float d = soft_decay(p, ap, S.box[i], gaussian, sigma, iou_thr);
+                if (d != 1.0f) { sc = __fmul_rn(sc, d); S.score[i] = sc; }
                 kill = !(sc > score_thr) || i == top;                                     // :103-104
             }
             const unsigned k = __ballot_sync(0xffffffffu, kill);
@@ -294,12 +351,12 @@ __global__ void __launch_bounds__(kDetThreads) detect_kernel(const __grid_consta
     int kept_n = 0;
     if (n > 0) {
         // 2. torchvision::nms orders by descending score (stable); top-k output already is
-        if (!A.p.soft_nms) {
+        {
             int bad = 0;
             for (int i = tid; i + 1 < n; i += kDetThreads) bad |= (s_key[i] >> 32) < (s_key[i + 1] >> 32);
             if (bad) s_unsorted = 1;
             __syncthreads();
-            if (s_unsorted) {
+            if (s_unsorted && !A.p.soft_nms) {
                 int P = 2;
                 while (P < n) P <<= 1;
                 for (int i = n + tid; i < P; i += kDetThreads) s_key[i] = 0ull;
@@ -345,10 +402,12 @@ __global__ void __launch_bounds__(kDetThreads) detect_kernel(const __grid_consta
         __syncthreads();
         // 5. suppression, first D survivors
         if (A.p.soft_nms)
-            kept_n = soft_nms_rounds(S, n, true, A.p.soft_sigma, A.p.soft_iou, A.p.soft_score_thr, D,
-                                     [&](int q, int i, float sc) { s_kept[q] = i; s_keptscore[q] = sc; });
+            // the window needs non-increasing scores: true for top-k output (checked below for API inputs)
+            kept_n = soft_nms_rounds(S, n, true, A.p.soft_sigma, A.p.soft_iou, A.p.soft_score_thr, D, s_kept,
+                                     s_unsorted ? n : kDetThreads,
+                                     [&](int q, int i, float sc) { s_keptscore[q] = sc; });
         else
-            kept_n = hard_nms_rounds(S, n, A.nms_thr_f, D, s_kept);
+            kept_n = hard_nms_rounds(S, n, A.nms_thr_f, D, s_kept, kDetThreads);
         __syncthreads();
     }
     // 6. rows: boxes (re-decoded, unoffset) * img_scale, score, class + 1 (anchors.py:153-166)
@@ -383,7 +442,8 @@ soft_nms_kernel(const float4 *__restrict__ boxes, const float *__restrict__ scor
     for (int i = threadIdx.x; i < n; i += kDetThreads) { S.box[i] = __ldg(boxes + i); S.score[i] = __ldg(scores + i); }
     init_alive(S.alive, n, cap);
     __syncthreads();
-    const int c = soft_nms_rounds(S, n, gaussian != 0, sigma, iou_thr, score_thr, max_rounds,
+    __shared__ int s_picked[kDetMaxN];   // 32 KB: ranks in pick order (needed to replay decays)
+    const int c = soft_nms_rounds(S, n, gaussian != 0, sigma, iou_thr, score_thr, max_rounds, s_picked, n,
                                   [&](int q, int i, float sc) { idx_out[q] = i; score_out[q] = sc; });
     if (threadIdx.x == 0) *count = c;
 }
@@ -423,7 +483,7 @@ nms_kernel(const float4 *__restrict__ boxes, const float *__restrict__ scores, i
     }
     init_alive(S.alive, n, cap);
     __syncthreads();
-    const int c = hard_nms_rounds(S, n, thr_f, n, s_kept);
+    const int c = hard_nms_rounds(S, n, thr_f, n, s_kept, n);
     __syncthreads();
     for (int q = threadIdx.x; q < c; q += kDetThreads) keep[q] = S.src[s_kept[q]];
     if (threadIdx.x == 0) *count = c;

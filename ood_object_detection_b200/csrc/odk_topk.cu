@@ -30,6 +30,7 @@ constexpr int kTopkThreads = 256;
 constexpr int kSelThreads = 1024;
 constexpr int kCap = 16384;            // candidate capacity per image (128 KB of 64-bit keys)
 constexpr int kHistBins = 4096;        // top 12 bits of the value key
+constexpr int kSlots = 8192;           // per-image sample slots (lane maxima)
 constexpr int kSampleShift = 6;        // sample 1 / 64 of the 512-byte units
 constexpr int kSegVec = 1024;          // vec4 units per task segment
 constexpr int kClusterSize = 8;
@@ -45,7 +46,9 @@ struct TopkArgs {
     int task_off[ODK_MAX_LEVELS + 1];
     int B, C, K, planes;          // planes = na * C channel planes per level
     long long N;                  // elements per image = A * C
-    unsigned *hist;               // [B][kHistBins]
+    unsigned *slots;              // [B][kSlots] value keys: maxima of the sampled units of one lane
+    unsigned *thr;                // [B] threshold key of the collect pass
+    int nslots;                   // slots actually used per image
     unsigned *cnt;                // [B]
     unsigned *flag;               // [B]
     unsigned long long *cand;     // [B][kCap]
@@ -108,84 +111,120 @@ __device__ __forceinline__ void visit_task(const Task &k, int lane, F4 f4, F1 f1
     }
 }
 
-// ---- P0: sample histogram ----------------------------------------------------------------
+// ---- P0: sample ------------------------------------------------------------------------------
 // Each task segment has at most kSegVec/32 = 32 warp-wide units (512 bytes); unit j = hash(task) mod
-// 2^kSampleShift is sampled if the segment has one.  Every unit of the image is therefore taken with
-// probability 2^-kSampleShift, spread over all channel planes and positions.
+// 2^kSampleShift is sampled if the segment has one, so every unit of the image is taken with
+// probability 2^-kSampleShift, spread over all channel planes and positions.  A lane only keeps the
+// MAXIMUM of what it sampled (no histogram, no atomics in the loop) and merges it into its slot at
+// the end; the r-th largest slot maximum estimates the r-th largest sample because the few largest
+// samples almost surely sit in different slots (collisions only make the threshold more cautious).
 __global__ void __launch_bounds__(kTopkThreads) topk_sample_kernel(const __grid_constant__ TopkArgs A) {
-    __shared__ unsigned s_hist[kHistBins];
     const int b = blockIdx.y;
-    for (int i = threadIdx.x; i < kHistBins; i += kTopkThreads) s_hist[i] = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int W = gridDim.x * (kTopkThreads / 32);
     const int ntasks = A.task_off[A.g.nlev];
-    for (int t = blockIdx.x * (kTopkThreads / 32) + (threadIdx.x >> 5); t < ntasks; t += W) {
-        unsigned h = (unsigned)t * 2654435761u;
-        h ^= h >> 15;
-        const int j = (int)((h * 2246822519u) >> (32 - kSampleShift));
-        const Task k = decode_task(A, b, t);
-        const int u = k.u0 + j * 32;
-        if (u >= k.u1) continue;   // warp-uniform
-        const bool on = u + lane < k.u1;
-        const unsigned mask = __ballot_sync(0xffffffffu, on);
-        if (!on) continue;
-        float v[4];
-        int nv = 1;
-        if (k.vec == 4) {
-            const float4 q = ld_stream4(k.base + (size_t)(u + lane) * 4);
-            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-            nv = 4;
-        } else {
-            v[0] = ld_stream1(k.base + u + lane);
+    float m = -INFINITY;
+    bool any = false;
+    for (int t0 = blockIdx.x * (kTopkThreads / 32) + (threadIdx.x >> 5); t0 < ntasks; t0 += 4 * W) {
+        // four tasks per round: their (predicated) loads are issued back to back
+        float4 v[4];
+        bool on[4], vec[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int t = t0 + i * W;
+            on[i] = false; vec[i] = true;
+            v[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (t < ntasks) {
+                unsigned h = (unsigned)t * 2654435761u;
+                h ^= h >> 15;
+                const int j = (int)((h * 2246822519u) >> (32 - kSampleShift));
+                const Task k = decode_task(A, b, t);
+                const int u = k.u0 + j * 32 + lane;
+                if (u < k.u1) {
+                    on[i] = true;
+                    if (k.vec == 4) v[i] = ld_stream4(k.base + (size_t)u * 4);
+                    else { vec[i] = false; v[i].x = ld_stream1(k.base + u); }
+                }
+            }
         }
-        for (int i = 0; i < nv; ++i) {
-            // aggregate equal bins across the warp first: logits crowd into a few exponent bins
-            const unsigned bin = vkey_of(v[i]) >> 20;
-            const unsigned peers = __match_any_sync(mask, bin);
-            if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
-        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (on[i]) { m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w))); any = true; }
     }
-    __syncthreads();
-    unsigned *gh = A.hist + (size_t)b * kHistBins;
-    for (int i = threadIdx.x; i < kHistBins; i += kTopkThreads)
-        if (s_hist[i]) atomicAdd(gh + i, s_hist[i]);
+    if (any) atomicMax(A.slots + (size_t)b * kSlots + (blockIdx.x * kTopkThreads + threadIdx.x) % kSlots, vkey_of(m));
 }
 
-// Threshold bin from the sample histogram: the highest bin t whose suffix count reaches the
-// sample rank m that puts (m - 5*sqrt(m)) * 2^kSampleShift >= K.  Runs in every collect CTA.
-__device__ unsigned pick_threshold(const unsigned *__restrict__ gh, int K, long long N, unsigned *s_scan /*[256]*/) {
-    if (N <= kCap) return 0u;   // everything fits: keep all elements
-    const float kr = (float)K / (float)(1 << kSampleShift);
-    const float rt = 0.5f * (5.0f + sqrtf(25.0f + 4.0f * kr));
-    const unsigned m_target = (unsigned)ceilf(rt * rt) + 1u;
-    // each thread owns 16 consecutive bins, highest bins first
-    const int tid = threadIdx.x;
+// Threshold per image from the slot maxima (one CTA per image).  With L slots of n samples each, a
+// threshold exceeded by r slots is exceeded by about -ln(1 - r/L)/n of all elements; r is the smallest
+// rank whose 5-sigma lower bound on that fraction still covers K of the N elements.  The collect pass
+// keeps everything at or above the 12-bit bin of the r-th largest slot maximum.
+__global__ void __launch_bounds__(kTopkThreads) topk_threshold_kernel(const __grid_constant__ TopkArgs A) {
+    __shared__ unsigned s_hist[kHistBins];
+    __shared__ unsigned s_scan[kTopkThreads];
+    __shared__ unsigned s_thr;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < kHistBins; i += kTopkThreads) s_hist[i] = 0;
+    if (tid == 0) s_thr = 0u;   // default: keep everything (the select kernel then flags the image)
+    __syncthreads();
+    const unsigned *sl = A.slots + (size_t)b * kSlots;
+    unsigned used = 0;
+    for (int i = tid; i < A.nslots; i += kTopkThreads) {
+        const unsigned k = __ldcg(sl + i);
+        if (k) { atomicAdd(&s_hist[k >> 20], 1u); ++used; }
+    }
+    __syncthreads();   // histogram complete
+    // number of used slots
+    s_scan[tid] = used;
+    __syncthreads();
+    for (int o = kTopkThreads / 2; o > 0; o >>= 1) {
+        if (tid < o) s_scan[tid] += s_scan[tid + o];
+        __syncthreads();
+    }
+    const float L = (float)s_scan[0];
+    __syncthreads();
+    const float n_per = fmaxf((float)A.N / (float)(1 << kSampleShift) / fmaxf(L, 1.0f), 1.0f);
+    const float need = (float)A.K / (float)A.N;
+    unsigned r_target = 0;
+    if (tid == 0 && L >= 16.0f) {
+        // the bound grows with r: binary search for the smallest rank that covers K
+        auto covers = [&](unsigned r) {
+            return -logf(1.0f - (float)r / L) / n_per * (1.0f - 5.0f * rsqrtf((float)r)) >= need;
+        };
+        unsigned lo = 26, hi = (unsigned)(L * 0.75f);   // r > 25 keeps the 5-sigma factor positive
+        if (hi > lo && covers(hi)) {
+            while (lo < hi) {
+                const unsigned mid = (lo + hi) >> 1;
+                if (covers(mid)) hi = mid; else lo = mid + 1;
+            }
+            r_target = lo;
+        }
+    }
+    // suffix scan of the histogram from the top bin: each thread owns 16 consecutive bins
     const int hi = kHistBins - 1 - tid * 16;
     unsigned mine = 0;
-    for (int i = 0; i < 16; ++i) mine += __ldcg(gh + hi - i);
+    for (int i = 0; i < 16; ++i) mine += s_hist[hi - i];
     s_scan[tid] = mine;
     __syncthreads();
-    // inclusive scan over threads (thread 0 holds the top bins)
     for (int o = 1; o < kTopkThreads; o <<= 1) {
-        unsigned v = tid >= o ? s_scan[tid - o] : 0u;
+        const unsigned v = tid >= o ? s_scan[tid - o] : 0u;
         __syncthreads();
         s_scan[tid] += v;
         __syncthreads();
     }
-    __shared__ unsigned s_thr;
-    if (tid == 0) s_thr = 0u;   // sample too small to reach the rank: keep everything (flag decides)
+    __shared__ unsigned s_r;
+    if (tid == 0) s_r = r_target;
     __syncthreads();
+    const unsigned r = s_r;
     const unsigned before = s_scan[tid] - mine;
-    if (before < m_target && s_scan[tid] >= m_target) {
+    if (r > 0 && before < r && s_scan[tid] >= r) {
         unsigned run = before;
         for (int i = 0; i < 16; ++i) {
-            run += __ldcg(gh + hi - i);
-            if (run >= m_target) { s_thr = (unsigned)(hi - i) << 20; break; }
+            run += s_hist[hi - i];
+            if (run >= r) { s_thr = (unsigned)(hi - i) << 20; break; }
         }
     }
     __syncthreads();
-    return s_thr;
+    if (tid == 0) A.thr[b] = (A.N <= kCap) ? 0u : s_thr;
 }
 
 // ---- P1: single streaming pass, keep elements at or above the threshold bin ---------------
@@ -197,12 +236,12 @@ __device__ __forceinline__ float thr_float(unsigned thr_key) {
 }
 
 __global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const __grid_constant__ TopkArgs A) {
-    __shared__ unsigned s_scan[kTopkThreads];
     __shared__ unsigned long long s_stage[kStage];
     __shared__ unsigned s_nstage, s_base;
     const int b = blockIdx.y;
     if (threadIdx.x == 0) s_nstage = 0u;
-    const unsigned thr = pick_threshold(A.hist + (size_t)b * kHistBins, A.K, A.N, s_scan);
+    __syncthreads();
+    const unsigned thr = __ldcg(A.thr + b);
     const float thr_f = thr_float(thr);
     const int lane = threadIdx.x & 31;
     const int W = gridDim.x * (kTopkThreads / 32);
@@ -335,13 +374,85 @@ __device__ void emit_topk(const TopkArgs &A, int b, const unsigned long long *s)
     }
 }
 
-__device__ void sort_and_emit(const TopkArgs &A, int b, int n, unsigned long long *s) {
+// Cut n <= kCap candidates down to just over K before sorting: a 1024-bin histogram on the value-key
+// bits below the collect threshold finds the finest edge T with count(key >= T) >= K; everything
+// below T cannot be in the top K.  Survivors are compacted (order is irrelevant: they are sorted next)
+// so the sort always runs on 8192 slots.  Returns the new count.
+constexpr int kRefineBins = 1024;
+constexpr int kRefineShift = 14;   // sub-bin = 2^14 key units: 64 sub-bins per 12-bit threshold bin
+
+__device__ int refine_candidates(const TopkArgs &A, int b, int n, unsigned long long *s) {
+    __shared__ unsigned s_rh[kRefineBins];
+    __shared__ unsigned s_edge, s_cnt;
+    const int tid = threadIdx.x;
+    const unsigned base = __ldcg(A.thr + b);   // every candidate key is >= base
     const unsigned long long *cand = A.cand + (size_t)b * kCap;
-    const int P = n <= 8 * kSelThreads ? 8 * kSelThreads : 16 * kSelThreads;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) s[i] = i < n ? __ldcg(cand + i) : 0ull;
+    for (int i = tid; i < kRefineBins; i += blockDim.x) s_rh[i] = 0;
+    if (tid == 0) { s_edge = 0u; s_cnt = 0u; }
     __syncthreads();
-    if (P == 8 * kSelThreads) { block_sort_desc<8>(s); emit_topk<8>(A, b, s); }
-    else { block_sort_desc<16>(s); emit_topk<16>(A, b, s); }
+    unsigned long long mine[kCap / kSelThreads];
+#pragma unroll
+    for (int k = 0; k < kCap / kSelThreads; ++k) {
+        const int i = tid + k * kSelThreads;
+        mine[k] = i < n ? __ldcg(cand + i) : 0ull;
+        if (i < n) {
+            const unsigned d = ((unsigned)(mine[k] >> 32) - base) >> kRefineShift;
+            atomicAdd(&s_rh[min(d, (unsigned)kRefineBins - 1u)], 1u);
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {   // one warp: suffix sums from the top sub-bin, first edge reaching K
+        unsigned run = 0;
+        for (int c = kRefineBins / 32 - 1; c >= 0; --c) {
+            const int bin = c * 32 + (31 - tid);   // lane 0 holds the highest bin of the chunk
+            const unsigned v = s_rh[bin];
+            unsigned inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (tid >= o) inc += t;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, run + inc >= (unsigned)A.K);
+            if (hit) {
+                const int ln = __ffs(hit) - 1;
+                if (tid == ln) s_edge = (unsigned)bin;
+                break;
+            }
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    __syncthreads();
+    const unsigned edge = s_edge;   // keep sub-bins >= edge (edge 0: keep everything)
+#pragma unroll
+    for (int k = 0; k < kCap / kSelThreads; ++k) {
+        const int i = tid + k * kSelThreads;
+        if (i < n) {
+            const unsigned d = min(((unsigned)(mine[k] >> 32) - base) >> kRefineShift, (unsigned)kRefineBins - 1u);
+            if (d >= edge) {
+                const unsigned slot = atomicAdd(&s_cnt, 1u);
+                if (slot < 8u * kSelThreads) s[slot] = mine[k];
+            }
+        }
+    }
+    __syncthreads();
+    return (int)s_cnt;
+}
+
+__device__ void sort_and_emit(const TopkArgs &A, int b, int n, unsigned long long *s) {
+    int m = refine_candidates(A, b, n, s);
+    if (m <= 8 * kSelThreads) {
+        for (int i = m + threadIdx.x; i < 8 * kSelThreads; i += blockDim.x) s[i] = 0ull;
+        __syncthreads();
+        block_sort_desc<8>(s);
+        emit_topk<8>(A, b, s);
+    } else {   // more than 8192 keys tie inside one sub-bin: sort everything
+        const unsigned long long *cand = A.cand + (size_t)b * kCap;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 16 * kSelThreads; i += blockDim.x) s[i] = i < n ? __ldcg(cand + i) : 0ull;
+        __syncthreads();
+        block_sort_desc<16>(s);
+        emit_topk<16>(A, b, s);
+    }
 }
 
 __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const __grid_constant__ TopkArgs A) {
@@ -441,6 +552,8 @@ topk_exact_kernel(const __grid_constant__ TopkArgs A) {
     cluster.sync();
     if (rank == 0) {
         const unsigned n = *(volatile unsigned *)(A.cnt + b);
+        if (threadIdx.x == 0) A.thr[b] = (unsigned)(lower >> 32);   // every collected key is >= this
+        __syncthreads();
         sort_and_emit(A, b, (int)min(n, (unsigned)kCap), s_keys);
     }
     cluster.sync();   // keep peers' shared memory alive until rank 0 is done with DSMEM
@@ -448,7 +561,7 @@ topk_exact_kernel(const __grid_constant__ TopkArgs A) {
 
 static size_t topk_ws_layout(int B, size_t *o_hist, size_t *o_cnt, size_t *o_flag, size_t *o_cand) {
     size_t off = 0;
-    *o_hist = off; off += (size_t)B * kHistBins * sizeof(unsigned);
+    *o_hist = off; off += (size_t)B * (kSlots + 4) * sizeof(unsigned);   // slot maxima + threshold (padded)
     *o_cnt = off; off += (((size_t)B * sizeof(unsigned)) + 15) & ~(size_t)15;
     *o_flag = off; off += (((size_t)B * sizeof(unsigned)) + 15) & ~(size_t)15;
     const size_t zero_bytes = off;
@@ -505,7 +618,7 @@ int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B
     size_t o_hist, o_cnt, o_flag, o_cand;
     topk_ws_layout(B, &o_hist, &o_cnt, &o_flag, &o_cand);
     char *ws = (char *)workspace;
-    a.hist = (unsigned *)(ws + o_hist); a.cnt = (unsigned *)(ws + o_cnt); a.flag = (unsigned *)(ws + o_flag);
+    a.slots = (unsigned *)(ws + o_hist); a.thr = a.slots + (size_t)B * kSlots; a.cnt = (unsigned *)(ws + o_cnt); a.flag = (unsigned *)(ws + o_flag);
     a.cand = (unsigned long long *)(ws + o_cand);
     a.out_val = cls_topk; a.out_box = box_topk; a.out_idx = (long long *)indices; a.out_cls = (long long *)classes;
 
@@ -533,11 +646,15 @@ int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B
     if (per_image > max_useful) per_image = max_useful;
     if (per_image < 1) per_image = 1;
     dim3 grid(per_image, B);
+    a.nslots = per_image * kTopkThreads < kSlots ? per_image * kTopkThreads : kSlots;
     if (a.N > kCap) {
         topk_sample_kernel<<<grid, kTopkThreads, 0, st>>>(a);
         rc = check_launch("odk_topk/sample");
         if (rc) return rc;
     }
+    topk_threshold_kernel<<<B, kTopkThreads, 0, st>>>(a);
+    rc = check_launch("odk_topk/threshold");
+    if (rc) return rc;
     topk_collect_kernel<<<grid, kTopkThreads, 0, st>>>(a);
     rc = check_launch("odk_topk/collect");
     if (rc) return rc;
