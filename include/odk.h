@@ -123,6 +123,9 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
 /* In-place `buf[i] *= *scale` over n floats; returns immediately on device when *scale == 1.
  * Used by the autograd shim when the upstream gradient of the loss is not 1. */
 int odk_scale_inplace(float *buf, int64_t n, const float *scale, void *stream);
+/* Same for up to ODK_SCALE_MAX separate buffers in ONE launch (bufs / sizes: HOST arrays). */
+#define ODK_SCALE_MAX 16
+int odk_scale_inplace_multi(void *const *bufs, const int64_t *sizes, int count, const float *scale, void *stream);
 
 /* ---- post-process: top-k -------------------------------------------------------------------
  * Replaces _post_process (bench.py:12-56): concat/permute of the levels, torch.topk over

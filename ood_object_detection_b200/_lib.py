@@ -42,6 +42,7 @@ SIGNATURES = {
     'odk_loss': (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P,
                          ctypes.POINTER(LossParams), _P, _P, _P, _P, c_size_t, _P]),
     'odk_scale_inplace': (c_int, [_P, c_int64, _P, _P]),
+    'odk_scale_inplace_multi': (c_int, [_P, _P, c_int, _P, _P]),
     'odk_topk_workspace_bytes': (c_size_t, [c_int, c_int]),
     'odk_topk': (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     'odk_detect': (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int64, _P, _P, ctypes.POINTER(DetectParams), _P, _P, _P,

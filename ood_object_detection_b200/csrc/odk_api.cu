@@ -55,6 +55,31 @@ __global__ void scale_inplace_kernel(float *__restrict__ buf, int64_t n, const f
     }
 }
 
+struct ScaleMulti {
+    float *ptr[ODK_SCALE_MAX];
+    long long n[ODK_SCALE_MAX];
+    int count;
+};
+
+__global__ void scale_multi_kernel(const ScaleMulti m, const float *__restrict__ scale) {
+    const float s = __ldg(scale);
+    if (s == 1.0f) return;  // loss.backward(): nothing to do, no memory traffic
+    float *buf = m.ptr[blockIdx.y];
+    const long long n = m.n[blockIdx.y];
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    const bool al = ((uintptr_t)buf & 15) == 0;
+    for (; i < n; i += stride) {
+        if (al && i + 3 < n) {
+            float4 v = *reinterpret_cast<float4 *>(buf + i);
+            v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+            *reinterpret_cast<float4 *>(buf + i) = v;
+        } else {
+            for (int k = 0; k < 4 && i + k < n; ++k) buf[i + k] *= s;
+        }
+    }
+}
+
 }  // namespace odk
 
 extern "C" {
@@ -71,6 +96,23 @@ int odk_scale_inplace(float *buf, int64_t n, const float *scale, void *stream) {
     if (blocks < 1) blocks = 1;
     odk::scale_inplace_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(buf, n, scale);
     return odk::check_launch("odk_scale_inplace");
+}
+
+int odk_scale_inplace_multi(void *const *bufs, const int64_t *sizes, int count, const float *scale, void *stream) {
+    using namespace odk;
+    if (count < 0 || count > ODK_SCALE_MAX || !scale || (count > 0 && (!bufs || !sizes)))
+        return set_error(ODK_EINVAL, "odk_scale_inplace_multi: bad arguments (at most %d buffers)", ODK_SCALE_MAX);
+    if (count == 0) return ODK_OK;
+    ScaleMulti m;
+    for (int i = 0; i < count; ++i) {
+        if (!bufs[i] || sizes[i] < 0) return set_error(ODK_EINVAL, "odk_scale_inplace_multi: bad buffer %d", i);
+        m.ptr[i] = (float *)bufs[i];
+        m.n[i] = sizes[i];
+    }
+    m.count = count;
+    dim3 grid(148 * 4, count);
+    scale_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m, scale);
+    return check_launch("odk_scale_inplace_multi");
 }
 
 }  // extern "C"

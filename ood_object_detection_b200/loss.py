@@ -69,16 +69,9 @@ class _DetectionLossFn(torch.autograd.Function):
         gcls = gbox = None
         gcls_p = gbox_p = None
         if need_grad:
-            def flat_views(ts):
-                sizes = [(t.numel() + 3) // 4 * 4 for t in ts]
-                buf = torch.empty((sum(sizes),), dtype=torch.float32, device=dev)
-                views, off = [], 0
-                for t, s in zip(ts, sizes):
-                    views.append(buf[off:off + t.numel()].view(t.shape))
-                    off += s
-                return buf, views
-            gcls_buf, gcls = flat_views(cls_out)
-            gbox_buf, gbox = flat_views(box_out)
+            # one owning tensor per level: autograd can adopt them as .grad without a copy
+            gcls = [torch.empty_like(t) for t in cls_out]
+            gbox = [torch.empty_like(t) for t in box_out]
             gcls_p, gbox_p = _lib.ptr_array(gcls), _lib.ptr_array(gbox)
         params = _lib.LossParams(meta['alpha'], meta['gamma'], meta['delta'], meta['box_loss_weight'],
                                  meta['label_smoothing'], int(bool(meta['legacy_focal'])))
@@ -96,7 +89,7 @@ class _DetectionLossFn(torch.autograd.Function):
                                     _lib.ptr(cls_t), _lib.ptr(box_t), _lib.ptr(meta['normalizer']), params,
                                     _lib.ptr(out), gcls_p, gbox_p, _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr(dev)))
         if need_grad:
-            ctx.gcls_buf, ctx.gbox_buf, ctx.gcls, ctx.gbox = gcls_buf, gbox_buf, gcls, gbox
+            ctx.gcls, ctx.gbox = gcls, gbox
         ctx.box_loss_weight = meta['box_loss_weight']
         ctx.levels = n
         ctx.in_dtypes = [t.dtype for t in outputs]
@@ -106,7 +99,7 @@ class _DetectionLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_total, g_cls, g_box):
         lib = _lib.lib()
-        dev = ctx.gcls_buf.device
+        dev = ctx.gcls[0].device
         zero = torch.zeros((), dtype=torch.float32, device=dev)
         g_total = zero if g_total is None else g_total.float()
         # stored: d total / d logits (= d cls_loss / d logits) and d total / d box (= w * d box_loss / d box)
@@ -114,13 +107,18 @@ class _DetectionLossFn(torch.autograd.Function):
         w = ctx.box_loss_weight
         s_box = (g_total + (zero if g_box is None or w == 0 else g_box.float() / w)).reshape(1).contiguous()
         with torch.cuda.device(dev):
-            _lib.check(lib.odk_scale_inplace(_lib.ptr(ctx.gcls_buf), ctx.gcls_buf.numel(), _lib.ptr(s_cls),
-                                             _lib.stream_ptr(dev)))
-            _lib.check(lib.odk_scale_inplace(_lib.ptr(ctx.gbox_buf), ctx.gbox_buf.numel(), _lib.ptr(s_box),
-                                             _lib.stream_ptr(dev)))
-        grads = [g.to(dt) if dt != torch.float32 else g for g, dt in zip(ctx.gcls + ctx.gbox, ctx.in_dtypes)]
-        grads = [g if need else None for g, need in zip(grads, ctx.needs_input_grad[1:])]
-        return (None, *grads)
+            for bufs, sc in ((ctx.gcls, s_cls), (ctx.gbox, s_box)):
+                for lo in range(0, len(bufs), 16):
+                    part = bufs[lo:lo + 16]
+                    sizes = (_lib.c_int64 * len(part))(*[t.numel() for t in part])
+                    _lib.check(lib.odk_scale_inplace_multi(_lib.ptr_array(part), sizes, len(part), _lib.ptr(sc),
+                                                           _lib.stream_ptr(dev)))
+        # hand the buffers over (no reference kept here) so autograd can adopt them as .grad without a copy
+        bufs = ctx.gcls + ctx.gbox
+        ctx.gcls = ctx.gbox = None
+        grads = [g.to(dt) if dt != torch.float32 else g for g, dt in zip(bufs, ctx.in_dtypes)]
+        del bufs
+        return (None, *[g if need else None for g, need in zip(grads, ctx.needs_input_grad[1:])])
 
 
 def _normalizer(num_positives):
