@@ -176,19 +176,35 @@ def run_ours(args):
 
     unit = torch.ones((1,), dtype=torch.float32, device=dev)
 
-    def step(record=None):
+    def compute():
+        """Our kernels for one batch: labeler -> fused loss (N > 1: partial sums against a unit normaliser)."""
         lb = labeler.assign(gt_boxes, gt_cls)
-        if record is not None:
-            record[0].record()
-        # N > 1 (forward): partial sums against a unit normaliser, ONE all-reduce of 3 floats, divide after
         out = loss_fn_fused(cls_out, box_out, lb, normalizer=unit if world > 1 else None, **LOSS_KW)
-        if record is not None:
-            record[1].record()
+        return out, lb.num_positives
+
+    def finish(out, npos):
         if world > 1:
-            out = forward_losses_one_collective(out[1], out[2], lb.num_positives, LOSS_KW['box_loss_weight'])
+            # ONE all-reduce of 3 floats, divide by the global (num_positives + 1) afterwards.  It runs on
+            # NCCL's stream and is collected one step later, so it overlaps the next step's kernels (the
+            # loss values are only logged, nothing waits on them).
+            pending.append(forward_losses_one_collective(out[1], out[2], npos, LOSS_KW['box_loss_weight'], async_op=True))
+            if len(pending) > 1:
+                return pending.pop(0).result()
+        return out
+
+    def step():
+        return finish(*compute())
+
+    pending = []
+
+    def drain():
+        out = None
+        while pending:
+            out = pending.pop(0).result()
         return out
 
     def sync_all():
+        drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -199,19 +215,19 @@ def run_ours(args):
         for _ in range(max(args.warmup, 3)):
             step()
         sync_all()
-        # The step is a fixed launch sequence (2 memsets, 2 of our kernels, 3 tiny torch kernels): on one GPU
+        # The compute part of a step is a fixed launch sequence (memsets, our kernels, tiny torch kernels):
         # it is captured once into a CUDA graph and replayed, so the timed region measures the GPU, not the
-        # python launch path.  With NCCL in the step (N > 1) it is launched eagerly.
+        # python launch path.  The NCCL all-reduce (N > 1) stays outside the graph.
         graph, graph_out, mode = None, None, 'eager'
-        if world == 1 and not args.no_graph:
+        if not args.no_graph:
             try:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
-                    step()
+                    compute()
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph, stream=side):
-                        graph_out = step()
+                        graph_out = compute()
                 torch.cuda.current_stream().wait_stream(side)
                 for _ in range(3):
                     graph.replay()
@@ -227,10 +243,14 @@ def run_ours(args):
         if graph is not None:
             for i in range(args.steps):
                 graph.replay()
-            last = graph_out
+                last = finish(*graph_out)
+            if world > 1:
+                last = drain() or last
         else:
             for i in range(args.steps):
                 last = step()
+            if world > 1:
+                last = drain() or last
         t_end.record()
         sync_all()
         total_ms = t_start.elapsed_time(t_end)

@@ -44,18 +44,34 @@ def reduce_losses(total, cls_loss, box_loss, group=None):
     return packed[0], packed[1], packed[2]
 
 
-def forward_losses_one_collective(cls_unnorm, box_unnorm, num_positives, box_loss_weight, group=None):
+class PendingLosses:
+    """Result of ``forward_losses_one_collective(..., async_op=True)``: the all-reduce runs on NCCL's own
+    stream while the caller keeps enqueueing the next step; ``result()`` waits and normalises."""
+
+    def __init__(self, packed, work, box_loss_weight):
+        self.packed, self.work, self.w = packed, work, box_loss_weight
+
+    def result(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        n = self.packed[2] + 1.0
+        cls_loss, box_loss = self.packed[0] / n, self.packed[1] / n
+        return cls_loss + self.w * box_loss, cls_loss, box_loss
+
+
+def forward_losses_one_collective(cls_unnorm, box_unnorm, num_positives, box_loss_weight, group=None, async_op=False):
     """Forward-only variant with ONE collective: every rank computes its partial sums
     against a unit normaliser, a single all-reduce carries [sum_cls, sum_box, sum_num_positives], and
     the division by the global (num_positives + 1) happens afterwards.  Returns (total, cls, box).
     (With gradients use ``sharded_detection_loss``: the backward scale needs the global N up front.)"""
     packed = torch.stack([cls_unnorm.detach().reshape(()).float(), box_unnorm.detach().reshape(()).float(),
                           num_positives.float().sum().reshape(())])
+    work = None
     if _active(group):
-        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-    n = packed[2] + 1.0
-    cls_loss, box_loss = packed[0] / n, packed[1] / n
-    return cls_loss + box_loss_weight * box_loss, cls_loss, box_loss
+        work = dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    pending = PendingLosses(packed, work if async_op else None, box_loss_weight)
+    return pending if async_op else pending.result()
 
 
 def sharded_detection_loss(loss_module, cls_outputs, box_outputs, label_batch, group=None):

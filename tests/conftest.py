@@ -14,6 +14,11 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    # the native pieces are build artefacts (git-ignored): build them if this checkout has none yet
+    need = [os.path.join(ROOT, 'ood_object_detection_b200', 'libodk.so'), os.path.join(ROOT, 'oracle', 'liboracle.so')]
+    if not all(os.path.exists(p) for p in need):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope='session')
