@@ -1,0 +1,57 @@
+"""SURVEY 8f rows 2-3 on the GPU: device-side collate labelling and the evaluator hand-off."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def test_label_batch_targets_matches_collate_semantics():
+    """DetectionFastCollate calls label_anchors(filter_valid=False) on -1 padded [100,4]/[100] gt."""
+    from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
+    from ood_object_detection_b200.pipeline import label_batch_targets
+    size, B, C = 256, 3, 30
+    anc = Anchors(3, 7, 3, synth.ASPECTS, 4.0, (size, size)).to(DEV)
+    lab = AnchorLabeler(anc, C)
+    gb, gc = synth.gt_boxes(21, B, size, 7, C)
+    bbox = -np.ones((B, 100, 4), np.float32)
+    cls = -np.ones((B, 100), np.float32)          # the loader's float class tensor
+    bbox[:, :7], cls[:, :7] = gb, gc
+    target = label_batch_targets(lab, {'bbox': torch.from_numpy(bbox).to(DEV), 'cls': torch.from_numpy(cls).to(DEV)})
+    oc, ob, onp, _, _ = orc.batch_label_anchors(anc.boxes.cpu().numpy(), list(bbox), list(cls), filter_valid=False)
+    fhw = synth.feat_hw(size)
+    for l, (ct, bt) in enumerate(zip(orc.split_levels(oc, fhw), orc.split_levels(ob, fhw))):
+        assert target[f'label_cls_{l}'].dtype == torch.int64
+        np.testing.assert_array_equal(target[f'label_cls_{l}'].cpu().numpy(), ct)
+        np.testing.assert_allclose(target[f'label_bbox_{l}'].cpu().numpy(), bt, rtol=1e-5, atol=1e-7)
+    np.testing.assert_array_equal(target['label_num_positives'].cpu().numpy(), onp)
+    assert (oc == -2).any()    # the padded rows really produce ignore targets, as in the reference
+    # and DetBenchTrain(create_labeler=False)-style consumption: loss on these targets
+    from ood_object_detection_b200.loss import loss_fn
+    co, bo = synth.head_outputs(22, B, size, C, tie_free=False)
+    out = loss_fn([torch.from_numpy(x).to(DEV) for x in co], [torch.from_numpy(x).to(DEV) for x in bo],
+                  [target[f'label_cls_{l}'] for l in range(5)], [target[f'label_bbox_{l}'] for l in range(5)],
+                  target['label_num_positives'], C, 0.25, 1.5, 0.1, 50.0)
+    ref = orc.loss_fn(co, bo, orc.split_levels(oc, fhw), orc.split_levels(ob, fhw), onp, C, 0.25, 1.5, 0.1, 50.0)
+    np.testing.assert_allclose([float(v) for v in out], ref, rtol=1e-5)
+
+
+def test_detections_for_evaluator():
+    from ood_object_detection_b200.pipeline import detections_for_evaluator
+    rs = np.random.RandomState(3)
+    dets = np.zeros((4, 10, 6), np.float32)
+    count = np.array([10, 3, 0, 7], np.int32)
+    for i, n in enumerate(count):
+        dets[i, :n] = rs.uniform(0, 100, (n, 6))
+    out = detections_for_evaluator(torch.from_numpy(dets).to(DEV), torch.from_numpy(count).to(DEV))
+    for i, n in enumerate(count):
+        assert out[i]['bbox'].shape == (n, 4)
+        np.testing.assert_array_equal(out[i]['bbox'], dets[i, :n][:, [1, 0, 3, 2]])   # pretrain.py:248
+        np.testing.assert_array_equal(out[i]['scores'], dets[i, :n, 4])
+        np.testing.assert_array_equal(out[i]['cls'], dets[i, :n, 5])
+    raw = detections_for_evaluator(torch.from_numpy(dets).to(DEV), torch.from_numpy(count).to(DEV), yxyx=False)
+    np.testing.assert_array_equal(raw[0]['bbox'], dets[0, :10, :4])
