@@ -118,6 +118,8 @@ __device__ __forceinline__ void visit_task(const Task &k, int lane, F4 f4, F1 f1
 // MAXIMUM of what it sampled (no histogram, no atomics in the loop) and merges it into its slot at
 // the end; the r-th largest slot maximum estimates the r-th largest sample because the few largest
 // samples almost surely sit in different slots (collisions only make the threshold more cautious).
+__device__ void compute_threshold(const TopkArgs &A, int b);
+
 __global__ void __launch_bounds__(kTopkThreads) topk_sample_kernel(const __grid_constant__ TopkArgs A) {
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(kTopkThreads) topk_sample_kernel(const __grid_
                 unsigned h = (unsigned)t * 2654435761u;
                 h ^= h >> 15;
                 const int j = (int)((h * 2246822519u) >> (32 - kSampleShift));
+                if (j * 32 >= kSegVec) continue;   // no segment has that unit: skip the decode (half the tasks)
                 const Task k = decode_task(A, b, t);
                 const int u = k.u0 + j * 32 + lane;
                 if (u < k.u1) {
@@ -152,17 +155,28 @@ __global__ void __launch_bounds__(kTopkThreads) topk_sample_kernel(const __grid_
             if (on[i]) { m = fmaxf(m, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w))); any = true; }
     }
     if (any) atomicMax(A.slots + (size_t)b * kSlots + (blockIdx.x * kTopkThreads + threadIdx.x) % kSlots, vkey_of(m));
+    // the last CTA of the image turns the slot maxima into the collect threshold (no extra launch)
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(A.flag + b, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (threadIdx.x == 0) A.flag[b] = 0u;   // the flag array doubles as the CTA counter; select re-uses it
+        compute_threshold(A, b);
+    }
 }
 
 // Threshold per image from the slot maxima (one CTA per image).  With L slots of n samples each, a
 // threshold exceeded by r slots is exceeded by about -ln(1 - r/L)/n of all elements; r is the smallest
 // rank whose 5-sigma lower bound on that fraction still covers K of the N elements.  The collect pass
 // keeps everything at or above the 12-bit bin of the r-th largest slot maximum.
-__global__ void __launch_bounds__(kTopkThreads) topk_threshold_kernel(const __grid_constant__ TopkArgs A) {
+__device__ void compute_threshold(const TopkArgs &A, int b) {
     __shared__ unsigned s_hist[kHistBins];
     __shared__ unsigned s_scan[kTopkThreads];
     __shared__ unsigned s_thr;
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     for (int i = tid; i < kHistBins; i += kTopkThreads) s_hist[i] = 0;
     if (tid == 0) s_thr = 0u;   // default: keep everything (the select kernel then flags the image)
     __syncthreads();
@@ -225,6 +239,11 @@ __global__ void __launch_bounds__(kTopkThreads) topk_threshold_kernel(const __gr
     }
     __syncthreads();
     if (tid == 0) A.thr[b] = (A.N <= kCap) ? 0u : s_thr;
+}
+
+// used only when the sample pass is skipped (N <= kCap: everything is kept)
+__global__ void __launch_bounds__(kTopkThreads) topk_threshold_kernel(const __grid_constant__ TopkArgs A) {
+    compute_threshold(A, blockIdx.x);
 }
 
 // ---- P1: single streaming pass, keep elements at or above the threshold bin ---------------
@@ -652,9 +671,11 @@ int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B
         rc = check_launch("odk_topk/sample");
         if (rc) return rc;
     }
-    topk_threshold_kernel<<<B, kTopkThreads, 0, st>>>(a);
-    rc = check_launch("odk_topk/threshold");
-    if (rc) return rc;
+    if (a.N <= kCap) {
+        topk_threshold_kernel<<<B, kTopkThreads, 0, st>>>(a);
+        rc = check_launch("odk_topk/threshold");
+        if (rc) return rc;
+    }
     topk_collect_kernel<<<grid, kTopkThreads, 0, st>>>(a);
     rc = check_launch("odk_topk/collect");
     if (rc) return rc;
