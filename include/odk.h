@@ -76,7 +76,12 @@ size_t odk_assign_grid_workspace_bytes(int B, int64_t A);
 int odk_assign_grid(const float *anchors, const float *plane_desc, int num_planes, const float *gt_boxes,
                     const int32_t *gt_labels, const int32_t *gt_count, int B, int Mmax, const int32_t *level_hw,
                     int num_levels, int na, float match_thr, int filter_valid, int32_t *match, float *num_pos,
-                    void *workspace, size_t workspace_bytes, void *stream);
+                    float *normalizer, void *workspace, size_t workspace_bytes, void *stream);
+/* `match` may be NULL: the assignment then stays in the workspace as 64-bit keys
+ * ([B, odk_planar_stride(A)] uint64 at offset 0; 0 = unmatched, else low 32 bits = ~gt_row), which
+ * odk_loss consumes directly (odk_loss_params.match_is_key64) and odk_keys_to_match converts on
+ * demand.  `normalizer` (nullable) receives sum(num_pos) + 1 (loss.py:261) as one fp32. */
+int odk_keys_to_match(const void *keys, int B, int64_t A, int32_t *match, void *stream);
 
 /* Pairwise IoU matrix out[n,m] of yxyx boxes: IouSimilarity.compare
  * (region_similarity_calculator.py:59-101), same fp32 operation order. */
@@ -111,6 +116,7 @@ typedef struct odk_loss_params {
     float box_loss_weight;
     float label_smoothing;
     int32_t legacy_focal;
+    int32_t match_is_key64;   /* `match` points at odk_assign_grid's 64-bit keys instead of int32 rows */
 } odk_loss_params;
 
 size_t odk_loss_workspace_bytes(void);

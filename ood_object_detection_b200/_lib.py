@@ -18,7 +18,7 @@ c_void_p, c_int, c_int64, c_float, c_double, c_size_t = (
 
 class LossParams(ctypes.Structure):
     _fields_ = [('alpha', c_float), ('gamma', c_float), ('delta', c_float), ('box_loss_weight', c_float),
-                ('label_smoothing', c_float), ('legacy_focal', ctypes.c_int32)]
+                ('label_smoothing', c_float), ('legacy_focal', ctypes.c_int32), ('match_is_key64', ctypes.c_int32)]
 
 
 class DetectParams(ctypes.Structure):
@@ -35,7 +35,8 @@ SIGNATURES = {
     'odk_assign_workspace_bytes': (c_size_t, [c_int, c_int]),
     'odk_assign': (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P]),
     'odk_assign_grid_workspace_bytes': (c_size_t, [c_int, c_int64]),
-    'odk_assign_grid': (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P]),
+    'odk_assign_grid': (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    'odk_keys_to_match': (c_int, [_P, c_int, c_int64, _P, _P]),
     'odk_iou_matrix': (c_int, [_P, c_int, _P, c_int, _P, _P]),
     'odk_targets': (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P]),
     'odk_loss_workspace_bytes': (c_size_t, []),

@@ -138,13 +138,27 @@ class LabelBatch:
     ``match`` ([B, Apad] int32, planar order) is all the fused loss needs; the reference-layout
     target tensors are only materialised on demand (``targets()``)."""
 
-    def __init__(self, labeler, gt_boxes, gt_labels, match, num_positives):
+    def __init__(self, labeler, gt_boxes, gt_labels, match, num_positives, keys=None, normalizer=None):
         self.labeler = labeler
         self.gt_boxes = gt_boxes
         self.gt_labels = gt_labels
-        self.match = match
+        self._match = match
+        self.keys = keys                  # [B, Apad] 64-bit assignment keys (gt-centric kernel) or None
+        self.normalizer = normalizer      # [1] sum(num_positives) + 1, produced by the kernel, or None
         self.num_positives = num_positives
         self._targets = None
+
+    @property
+    def match(self):
+        """[B, Apad] int32 gt row per anchor (planar order), converted from the keys on first use."""
+        if self._match is None:
+            lib = _lib.lib()
+            B, apad = self.keys.shape
+            self._match = torch.empty((B, apad), dtype=torch.int32, device=self.keys.device)
+            with torch.cuda.device(self.keys.device):
+                _lib.check(lib.odk_keys_to_match(_lib.ptr(self.keys), B, self.labeler.anchors.boxes.shape[0],
+                                                 _lib.ptr(self._match), _lib.stream_ptr(self.keys.device)))
+        return self._match
 
     def targets(self):
         if self._targets is None:
@@ -224,7 +238,6 @@ class AnchorLabeler(object):
         anc = self.anchors.boxes
         A = anc.shape[0]
         apad = lib.odk_planar_stride(A)
-        match = torch.empty((B, apad), dtype=torch.int32, device=dev)
         num_pos = torch.empty((B,), dtype=torch.float32, device=dev)
         hw = self.anchors.level_hw()
         na = self.anchors.get_anchors_per_location()
@@ -232,13 +245,19 @@ class AnchorLabeler(object):
         desc = getattr(self.anchors, 'plane_desc', None)
         with torch.cuda.device(dev):
             if self.use_grid_kernel and desc is not None and thr > 0.0:
+                # the assignment stays in the workspace as 64-bit keys: the fused loss reads them directly,
+                # int32 `match` is only materialised if somebody asks for it (LabelBatch.match / targets())
                 ws_bytes = lib.odk_assign_grid_workspace_bytes(B, A)
                 ws = torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=dev)
+                normalizer = torch.empty((1,), dtype=torch.float32, device=dev)
                 _lib.check(lib.odk_assign_grid(_lib.ptr(anc), _lib.ptr(desc), desc.shape[0], _lib.ptr(boxes),
                                                _lib.ptr(labels), _lib.ptr(count), B, M, _lib.int_array(hw), len(hw), na,
-                                               thr, int(bool(filter_valid)), _lib.ptr(match), _lib.ptr(num_pos),
-                                               _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr(dev)))
+                                               thr, int(bool(filter_valid)), None, _lib.ptr(num_pos),
+                                               _lib.ptr(normalizer), _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr(dev)))
+                keys = ws[:B * apad].view(B, apad)
+                return LabelBatch(self, boxes, labels, None, num_pos, keys=keys, normalizer=normalizer)
             else:
+                match = torch.empty((B, apad), dtype=torch.int32, device=dev)
                 ws_bytes = lib.odk_assign_workspace_bytes(B, M)
                 ws = torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=dev)
                 _lib.check(lib.odk_assign(_lib.ptr(anc), _lib.ptr(boxes), _lib.ptr(labels), _lib.ptr(count), B, M,

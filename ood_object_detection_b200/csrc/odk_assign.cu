@@ -447,12 +447,30 @@ assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *_
 }
 
 // keys -> match (gt row or -1) and num_positives; four anchors per thread
+// num_positives per image and the loss normaliser sum + 1 (loss.py:261); one CTA
 __global__ void __launch_bounds__(256)
-keys_to_match_kernel(const Geo g, int B, const unsigned long long *__restrict__ keys, const int32_t *__restrict__ pos_count,
-                     int32_t *__restrict__ match, float *__restrict__ num_pos) {
-    const size_t n4 = (size_t)B * g.Apad / 4;
+finish_counts_kernel(int B, const int32_t *__restrict__ pos_count, float *__restrict__ num_pos, float *__restrict__ normalizer) {
+    __shared__ float s_w[8];
+    float acc = 0.f;
+    for (int b = threadIdx.x; b < B; b += 256) {
+        const float v = (float)__ldg(pos_count + (size_t)b * kCtrStride);
+        num_pos[b] = v;
+        acc += v;   // integer-valued, exact in fp32 below 2^24 like the reference's fp32 sum
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0 && normalizer) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        normalizer[0] = t + 1.0f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+keys_to_match_kernel(int B, int Apad, const unsigned long long *__restrict__ keys, int32_t *__restrict__ match) {
+    const size_t n4 = (size_t)B * Apad / 4;
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < (size_t)B) num_pos[t] = (float)__ldg(pos_count + t * kCtrStride);
     if (t >= n4) return;
     const ulonglong2 k01 = __ldcg(reinterpret_cast<const ulonglong2 *>(keys) + 2 * t);
     const ulonglong2 k23 = __ldcg(reinterpret_cast<const ulonglong2 *>(keys) + 2 * t + 1);
@@ -556,17 +574,30 @@ size_t odk_assign_grid_workspace_bytes(int B, int64_t A) {
     return (size_t)B * (size_t)odk_planar_stride(A) * sizeof(unsigned long long) + (size_t)B * odk::kCtrStride * sizeof(int32_t) + 16;
 }
 
+int odk_keys_to_match(const void *keys, int B, int64_t A, int32_t *match, void *stream) {
+    using namespace odk;
+    if (B < 0 || A < 0) return set_error(ODK_EINVAL, "odk_keys_to_match: negative size");
+    if (B == 0 || A == 0) return ODK_OK;
+    if (!keys || !match || (((uintptr_t)keys | (uintptr_t)match) & 15))
+        return set_error(ODK_EINVAL, "odk_keys_to_match: keys / match must be non-null and 16-byte aligned");
+    const int Apad = (int)odk_planar_stride(A);
+    const size_t n4 = (size_t)B * Apad / 4;
+    keys_to_match_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        B, Apad, (const unsigned long long *)keys, match);
+    return check_launch("odk_keys_to_match");
+}
+
 int odk_assign_grid(const float *anchors, const float *plane_desc, int num_planes, const float *gt_boxes,
                     const int32_t *gt_labels, const int32_t *gt_count, int B, int Mmax, const int32_t *level_hw,
                     int num_levels, int na, float match_thr, int filter_valid, int32_t *match, float *num_pos,
-                    void *workspace, size_t workspace_bytes, void *stream) {
+                    float *normalizer, void *workspace, size_t workspace_bytes, void *stream) {
     using namespace odk;
     Geo g;
     int rc = make_geo(&g, level_hw, num_levels, na);
     if (rc) return rc;
     if (B < 0 || Mmax < 0) return set_error(ODK_EINVAL, "odk_assign_grid: negative size");
     if (B == 0) return ODK_OK;
-    if (!anchors || !plane_desc || !match || !num_pos || (Mmax > 0 && (!gt_boxes || !gt_labels)))
+    if (!anchors || !plane_desc || !num_pos || (Mmax > 0 && (!gt_boxes || !gt_labels)))
         return set_error(ODK_EINVAL, "odk_assign_grid: null pointer");
     if (num_planes != num_levels * na || num_planes > kMaxPlanes)
         return set_error(ODK_EINVAL, "odk_assign_grid: need one descriptor per (level, shape), at most %d", kMaxPlanes);
@@ -590,10 +621,10 @@ int odk_assign_grid(const float *anchors, const float *plane_desc, int num_plane
         rc = check_launch("odk_assign_grid/assign_gt_kernel");
         if (rc) return rc;
     }
-    const size_t n4 = (size_t)B * g.Apad / 4;
-    const size_t threads = n4 > (size_t)B ? n4 : (size_t)B;
-    keys_to_match_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g, B, keys, pos, match, num_pos);
-    return check_launch("odk_assign_grid/keys_to_match_kernel");
+    finish_counts_kernel<<<1, 256, 0, st>>>(B, pos, num_pos, normalizer);
+    rc = check_launch("odk_assign_grid/finish_counts_kernel");
+    if (rc || !match) return rc;
+    return odk_keys_to_match(keys, B, g.A, match, stream);
 }
 
 int odk_targets(const float *anchors, const float *gt_boxes, const int32_t *gt_labels, int B, int Mmax,

@@ -165,7 +165,13 @@ __device__ __forceinline__ void item_targets(const LossArgs &A, const Item &it, 
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         if (FUSED) {
-            mt[j] = __ldg(A.match + (size_t)it.b * g.Apad + g.off[it.l] + it.a * it.hw + it.s0 + j);
+            const size_t mi = (size_t)it.b * g.Apad + g.off[it.l] + it.a * it.hw + it.s0 + j;
+            if (A.p.match_is_key64) {
+                const unsigned long long k = __ldg(reinterpret_cast<const unsigned long long *>(A.match) + mi);
+                mt[j] = k ? (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull)) : -1;
+            } else {
+                mt[j] = __ldg(A.match + mi);
+            }
             tc[j] = mt[j] >= 0 ? __ldg(A.gt_labels + (size_t)it.b * A.Mmax + mt[j]) - 1 : -1;
         } else {
             mt[j] = -1;

@@ -73,11 +73,13 @@ class _DetectionLossFn(torch.autograd.Function):
             gcls = [torch.empty_like(t) for t in cls_out]
             gbox = [torch.empty_like(t) for t in box_out]
             gcls_p, gbox_p = _lib.ptr_array(gcls), _lib.ptr_array(gbox)
-        params = _lib.LossParams(meta['alpha'], meta['gamma'], meta['delta'], meta['box_loss_weight'],
-                                 meta['label_smoothing'], int(bool(meta['legacy_focal'])))
         fused = meta.get('label_batch')
+        use_keys = fused is not None and fused.keys is not None
+        params = _lib.LossParams(meta['alpha'], meta['gamma'], meta['delta'], meta['box_loss_weight'],
+                                 meta['label_smoothing'], int(bool(meta['legacy_focal'])), int(use_keys))
         if fused is not None:
-            match, anchors, gtb, gtl = fused.match, fused.labeler.anchors.boxes, fused.gt_boxes, fused.gt_labels
+            match = fused.keys if use_keys else fused.match
+            anchors, gtb, gtl = fused.labeler.anchors.boxes, fused.gt_boxes, fused.gt_labels
             cls_t = box_t = None
             mmax = gtb.shape[1]
         else:
@@ -165,7 +167,7 @@ def loss_fn_fused(cls_outputs, box_outputs, label_batch, num_classes: int, alpha
     """Same value as ``loss_fn(.., *labeler.batch_label_anchors(..))`` without ever materialising
     the target tensors: ``label_batch`` is ``AnchorLabeler.assign(...)``."""
     if normalizer is None:
-        normalizer = _normalizer(label_batch.num_positives)
+        normalizer = label_batch.normalizer if label_batch.normalizer is not None else _normalizer(label_batch.num_positives)
     meta = dict(levels=len(cls_outputs), num_classes=int(num_classes), alpha=float(alpha), gamma=float(gamma),
                 delta=float(delta), box_loss_weight=float(box_loss_weight), label_smoothing=float(label_smoothing),
                 legacy_focal=bool(legacy_focal), label_batch=label_batch,
