@@ -335,6 +335,7 @@ assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *_
                  const int32_t *__restrict__ gt_count, int Mmax, float thr, int filter_valid,
                  unsigned long long *keys, int32_t *pos_count) {
     __shared__ int s_off[kMaxPlanes + 1], s_x0[kMaxPlanes], s_nx[kMaxPlanes], s_y0[kMaxPlanes];
+    __shared__ int s_w[kMaxPlanes], s_base[kMaxPlanes], s_sh[kMaxPlanes], s_hw[kMaxPlanes];
     __shared__ unsigned char s_done[kMaxPlanes];
     __shared__ unsigned long long s_red[kGtcThreads / 32];
     __shared__ unsigned long long s_best;
@@ -347,7 +348,11 @@ assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *_
     const float4 q = __ldg(gt_boxes + (size_t)b * Mmax + i);
     const float qa = area_ref(q.x, q.y, q.z, q.w);
     if (tid == 0) s_best = 0ull;
-    for (int k = tid; k < nplanes; k += kGtcThreads) s_done[k] = 0;
+    for (int k = tid; k < nplanes; k += kGtcThreads) {
+        const float *d = desc + (size_t)k * kDescFloats;
+        s_done[k] = 0;
+        s_w[k] = (int)d[7]; s_base[k] = (int)d[9]; s_sh[k] = (int)d[10]; s_hw[k] = g.hw[(int)d[11]];
+    }
     __syncthreads();
     unsigned long long *krow = keys + (size_t)b * g.Apad;
 
@@ -376,31 +381,50 @@ assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *_
             s_off[k + 1] = nx * ny;   // turned into a prefix sum below
         }
         __syncthreads();
-        if (tid == 0) {
-            s_off[0] = 0;
-            for (int k = 0; k < nplanes; ++k) s_off[k + 1] += s_off[k];
+        if (tid < 32) {   // inclusive scan of up to 128 plane counts by one warp (4 per lane)
+            int v[kMaxPlanes / 32], run = 0;
+#pragma unroll
+            for (int j = 0; j < kMaxPlanes / 32; ++j) {
+                const int k = tid * (kMaxPlanes / 32) + j;
+                run += k < nplanes ? s_off[k + 1] : 0;
+                v[j] = run;
+            }
+            int inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (tid >= o) inc += t;
+            }
+            const int excl = inc - run;
+#pragma unroll
+            for (int j = 0; j < kMaxPlanes / 32; ++j) {
+                const int k = tid * (kMaxPlanes / 32) + j;
+                if (k < nplanes) s_off[k + 1] = excl + v[j];
+            }
+            if (tid == 0) s_off[0] = 0;
         }
         __syncthreads();
         const int total = s_off[nplanes];
         if (total == 0) continue;   // uniform (pass 0 may select nothing: pass 1 still has to look)
 
         // ---- enumerate the cells ----
+        // a thread's cells c = tid, tid+256, ... ascend, so its plane index only moves forward; two cells
+        // are in flight per iteration (independent anchor gathers)
         unsigned long long best = 0ull;
-        for (int c = tid; c < total; c += kGtcThreads) {
-            int lo = 0, hi = nplanes - 1;   // last plane with s_off[k] <= c
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (s_off[mid] <= c) lo = mid; else hi = mid - 1;
-            }
-            const int k = lo;
-            const float *d = desc + (size_t)k * kDescFloats;
+        int kcur = 0;
+        auto locate = [&](int c, int &k, int &r, int &p, bool &ok) {
+            ok = c < total;
+            r = 0; p = 0;
+            if (!ok) return;
+            while (s_off[k + 1] <= c) ++k;
             const int loc = c - s_off[k];
             const int nx = s_nx[k];
             const int yy = s_y0[k] + loc / nx, xx = s_x0[k] + loc % nx;
-            const int W = (int)d[7], off = (int)d[9], sh = (int)d[10], lev = (int)d[11];
-            const int cell = yy * W + xx;
-            const int r = off + cell * g.na + sh;
-            const float4 a = __ldg(anchors + r);
+            const int cell = yy * s_w[k] + xx;
+            r = s_base[k] + cell * g.na + s_sh[k];
+            p = s_base[k] + s_sh[k] * s_hw[k] + cell;
+        };
+        auto visit = [&](float4 a, int r, int p) {
             const float h = __fsub_rn(fminf(q.z, a.z), fmaxf(q.x, a.x));
             const float w = __fsub_rn(fminf(q.w, a.w), fmaxf(q.y, a.y));
             if (h > 0.0f && w > 0.0f) {
@@ -412,7 +436,6 @@ assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *_
                             ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
                         best = kr > best ? kr : best;
                         if (!(thr > v)) {   // a candidate match for this anchor (argmax_matcher.py:126-137)
-                            const int p = off + sh * g.hw[lev] + cell;
                             const unsigned long long kg =
                                 ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
                             if (atomicMax(krow + p, kg) == 0ull) atomicAdd(pos_count + (size_t)b * kCtrStride, 1);
@@ -420,6 +443,18 @@ assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *_
                     }
                 }
             }
+        };
+        for (int c = tid; c < total; c += 2 * kGtcThreads) {
+            int r0, p0, r1, p1;
+            bool ok0, ok1;
+            locate(c, kcur, r0, p0, ok0);
+            int k1 = kcur;
+            locate(c + kGtcThreads, k1, r1, p1, ok1);
+            const float4 a0 = __ldg(anchors + r0);
+            const float4 a1 = __ldg(anchors + r1);   // r1 = 0 when out of range: a harmless, cached read
+            visit(a0, r0, p0);
+            if (ok1) visit(a1, r1, p1);
+            kcur = k1;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
