@@ -144,3 +144,52 @@ def test_config3_4_postprocess_properties(name, B):
     ok = out['anchor'][:4] >= 0
     np.testing.assert_allclose(out['energy'][:4][ok].cpu().numpy(), (-torch.logsumexp(rows, 2))[ok].cpu().numpy(), rtol=1e-5)
     assert torch.equal(out['max_logit'][:4][ok], rows.amax(2)[ok])
+
+
+def test_non_square_images_whole_chain():
+    """H != W (384x640) and a different anchor scale: exercises the (y, x) index maps, the plane
+    descriptors of the gt-centric kernel and every per-level stride with H_l != W_l."""
+    from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
+    from ood_object_detection_b200.bench import detect_with_ood
+    from ood_object_detection_b200.loss import loss_fn_fused
+    H, W, B, C, M = 384, 640, 3, 17, 12
+    anc = Anchors(3, 7, 3, synth.ASPECTS, 3.0, (H, W)).to(DEV)
+    anc_np = orc.anchor_boxes(3, 7, 3, synth.ASPECTS, 3.0, (H, W))
+    np.testing.assert_array_equal(anc.boxes.cpu().numpy(), anc_np)
+    fhw = [(H // s, W // s) for s in (8, 16, 32, 64, 128)]
+    rs = np.random.RandomState(9)
+    cy, cx = rs.uniform(0, H, (B, M)), rs.uniform(0, W, (B, M))
+    hh, ww = rs.uniform(6, 0.5 * H, (B, M)), rs.uniform(6, 0.5 * W, (B, M))
+    gb = np.clip(np.stack([cy - hh / 2, cx - ww / 2, cy + hh / 2, cx + ww / 2], -1), 0, [H, W, H, W]).astype(np.float32)
+    gc = rs.randint(1, C + 1, (B, M)).astype(np.int64)
+    co = [(rs.standard_normal((B, 9 * C, h, w)) * 1.5 - 4.0).astype(np.float32) for h, w in fhw]
+    bo = [(rs.standard_normal((B, 36, h, w)) * 0.2).astype(np.float32) for h, w in fhw]
+    synth.make_tie_free(co)
+    oc, ob, onp, om, _ = orc.batch_label_anchors(anc_np, list(gb), list(gc))
+    ref = orc.loss_fn(co, bo, orc.split_levels(oc, fhw), orc.split_levels(ob, fhw), onp, C, 0.25, 1.5, 0.1, 50.0, want_grad=True)
+    for use_grid in (True, False):
+        lab = AnchorLabeler(anc, C)
+        lab.use_grid_kernel = use_grid
+        lb = lab.assign(torch.from_numpy(gb).to(DEV), torch.from_numpy(gc).to(DEV))
+        cls_t, box_t = lb.targets()
+        np.testing.assert_array_equal(torch.cat([t.reshape(B, -1) for t in cls_t], 1).cpu().numpy(), oc)
+        np.testing.assert_allclose(torch.cat([t.reshape(B, -1, 4) for t in box_t], 1).cpu().numpy(), ob, rtol=1e-5, atol=1e-7)
+        np.testing.assert_array_equal(lb.num_positives.cpu().numpy(), onp)
+        cg = [torch.from_numpy(x).to(DEV).requires_grad_(True) for x in co]
+        bg = [torch.from_numpy(x).to(DEV).requires_grad_(True) for x in bo]
+        tot, cl, bl = loss_fn_fused(cg, bg, lb, num_classes=C, **KW)
+        np.testing.assert_allclose([tot.item(), cl.item(), bl.item()], ref[:3], rtol=1e-5)
+        tot.backward()
+        for l in range(5):
+            np.testing.assert_allclose(cg[l].grad.cpu().numpy(), ref[3][l], rtol=2e-5, atol=1e-9)
+            np.testing.assert_allclose(bg[l].grad.cpu().numpy(), ref[4][l], rtol=2e-5, atol=1e-9)
+    K, D = 3000, 60
+    out = detect_with_ood([torch.from_numpy(x).to(DEV) for x in co], [torch.from_numpy(x).to(DEV) for x in bo], anc.boxes,
+                          5, C, K, D, False)
+    o_cls, o_box, o_idx, o_klass = orc.post_process(co, bo, 5, C, K)
+    for i in range(B):
+        det, src = orc.generate_detections(o_cls[i], o_box[i], anc_np, o_idx[i], o_klass[i], None, None, D, False, return_src=True)
+        n = int(out['count'][i])
+        assert n == det.shape[0]
+        np.testing.assert_array_equal(out['anchor'][i, :n].cpu().numpy(), o_idx[i][src])
+        np.testing.assert_allclose(out['detections'][i, :n, 4:].cpu().numpy(), det[:, 4:], rtol=1e-5)
