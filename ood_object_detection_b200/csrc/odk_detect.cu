@@ -110,34 +110,29 @@ __device__ __forceinline__ bool nms_hit(float4 p, float ap, float4 q, float thr_
 }
 
 __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_keep, int *kept, int window) {
-    __shared__ int s_first[kDetWarps];
-    __shared__ int s_top;
+    // One block barrier per round: while a warp kills the candidates of its words it also notes its
+    // first survivor; after the barrier every warp reduces the 32 notes to the next pick by itself.
+    __shared__ int s_first[2][kDetWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int limit = min(n, window);   // activated prefix (a multiple of 32 or n)
-    int count = 0;
-    int from = 0;   // every word below `from` is known dead
-    while (count < max_keep) {
-        const int nwords = (limit + 31) / 32;
-        // first alive candidate of the activated prefix
-        int mine = 0x7fffffff;
-        for (int w = from + threadIdx.x; w < nwords; w += kDetThreads) {
+    int limit = min(n, window);   // activated prefix
+    int count = 0, parity = 0;
+    auto first_alive = [&](int from_word, int nwords) {   // this warp's first alive candidate, or INT_MAX
+        for (int w = from_word + ((warp - from_word) & (kDetWarps - 1)); w < nwords; w += kDetWarps) {
             const unsigned m = S.alive[w];
-            if (m) { mine = w * 32 + __ffs(m) - 1; break; }
+            if (m) return w * 32 + __ffs(m) - 1;
         }
-        mine = __reduce_min_sync(0xffffffffu, mine);
-        if (lane == 0) s_first[warp] = mine;
+        return 0x7fffffff;
+    };
+    if (lane == 0) s_first[0][warp] = first_alive(0, (limit + 31) / 32);
+    while (count < max_keep) {
         __syncthreads();
-        if (warp == 0) {
-            int v = __reduce_min_sync(0xffffffffu, s_first[lane]);
-            if (lane == 0) s_top = v;
-        }
-        __syncthreads();
-        const int top = s_top;
+        const int nwords = (limit + 31) / 32;
+        const int top = __reduce_min_sync(0xffffffffu, s_first[parity][lane]);
         if (top == 0x7fffffff) {
             if (limit >= n) break;
             // activate the next chunk: a candidate stays alive iff nothing kept so far suppresses it
             const int new_limit = min(n, limit + window);
-            for (int w = limit / 32 + warp; w < (new_limit + 31) / 32; w += kDetWarps) {
+            for (int w = limit / 32 + ((warp - limit / 32) & (kDetWarps - 1)); w < (new_limit + 31) / 32; w += kDetWarps) {
                 const int i = w * 32 + lane;
                 bool dead = i >= new_limit;
                 if (!dead) {
@@ -150,27 +145,34 @@ __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_kee
                 const unsigned k = __ballot_sync(0xffffffffu, !dead);
                 if (lane == 0) S.alive[w] = k;
             }
-            from = limit / 32;
+            __syncwarp();
+            const int mine = first_alive(limit / 32, (new_limit + 31) / 32);   // own words only: written by this warp
+            if (lane == 0) s_first[parity ^ 1][warp] = mine;
+            parity ^= 1;
             limit = new_limit;
-            __syncthreads();
             continue;
         }
         if (threadIdx.x == 0) kept[count] = top;
         ++count;
-        from = top >> 5;
+        const int from = top >> 5;
         const float4 p = S.box[top];
         const float ap = __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y));
-        for (int w = from + warp; w < nwords; w += kDetWarps) {
-            const unsigned m = S.alive[w];   // warp-uniform
+        int mine = 0x7fffffff;
+        for (int w = from + ((warp - from) & (kDetWarps - 1)); w < nwords; w += kDetWarps) {
+            unsigned m = S.alive[w];   // warp-uniform
             if (!m) continue;
             const int i = w * 32 + lane;
             bool kill = false;
             if ((m >> lane) & 1u) kill = i == top || (i > top && nms_hit(p, ap, S.box[i], thr_f));
             const unsigned k = __ballot_sync(0xffffffffu, kill);
-            if (lane == 0 && k) S.alive[w] = m & ~k;
+            m &= ~k;
+            if (lane == 0 && k) S.alive[w] = m;
+            if (m && mine == 0x7fffffff) mine = w * 32 + __ffs(m) - 1;
         }
-        __syncthreads();
+        if (lane == 0) s_first[parity ^ 1][warp] = mine;
+        parity ^= 1;
     }
+    __syncthreads();
     return count;
 }
 
@@ -192,52 +194,52 @@ __device__ __forceinline__ float soft_decay(float4 p, float ap, float4 q, bool g
 template <class Emit>
 __device__ int soft_nms_rounds(const DetSmem &S, int n, bool gaussian, float sigma, float iou_thr, float score_thr,
                                int max_rounds, int *picked, int window, Emit emit) {
-    __shared__ unsigned long long s_best[kDetWarps];
-    __shared__ unsigned long long s_pick;
+    // One block barrier per round: a warp that rescales its candidates also notes its best survivor
+    // (score key, ~rank); after the barrier every warp reduces the 32 notes to the next pick itself.
+    __shared__ unsigned long long s_best[2][kDetWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int limit = min(n, window);
-    int count = 0;
-    while (count < max_rounds) {
-        const int nwords = (limit + 31) / 32;
-        // block arg-max on (score key, ~rank): highest score, first index on ties
+    int count = 0, parity = 0;
+    auto score_key = [&](int i) {   // order-preserving (scores may be <= 0 in the first round); never 0
+        const unsigned u = __float_as_uint(S.score[i]);
+        const unsigned vk = u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
+        return ((unsigned long long)vk << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+    };
+    auto warp_max64 = [&](unsigned long long v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+            v = other > v ? other : v;
+        }
+        return v;
+    };
+    auto local_best = [&](int from_word, int nwords) {
         unsigned long long best = 0ull;
-        for (int w = warp; w < nwords; w += kDetWarps) {
+        for (int w = from_word + ((warp - from_word) & (kDetWarps - 1)); w < nwords; w += kDetWarps) {
             const unsigned m = S.alive[w];
-            if (!m) continue;
-            const int i = w * 32 + lane;
             if ((m >> lane) & 1u) {
-                // order-preserving score key (scores may be <= 0 in the first round); never 0
-                const unsigned u = __float_as_uint(S.score[i]);
-                const unsigned vk = u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
-                const unsigned long long key = ((unsigned long long)vk << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+                const unsigned long long key = score_key(w * 32 + lane);
                 best = key > best ? key : best;
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-            best = other > best ? other : best;
-        }
-        if (lane == 0) s_best[warp] = best;
+        return warp_max64(best);
+    };
+    {
+        const unsigned long long b0 = local_best(0, (limit + 31) / 32);
+        if (lane == 0) s_best[0][warp] = b0;
+    }
+    while (count < max_rounds) {
         __syncthreads();
-        if (warp == 0) {
-            unsigned long long v = s_best[lane];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
-                v = other > v ? other : v;
-            }
-            if (lane == 0) s_pick = v;
-        }
-        __syncthreads();
-        const unsigned long long pick = s_pick;
+        const int nwords = (limit + 31) / 32;
+        const unsigned long long pick = warp_max64(s_best[parity][lane]);
         if (limit < n) {
             // un-activated candidates still carry their original scores; the first one bounds them all
             const unsigned ub = __float_as_uint(S.score[limit]);
             const unsigned bk = ub ^ ((unsigned)((int)ub >> 31) | 0x80000000u);
             if (pick == 0ull || (unsigned)(pick >> 32) < bk) {
                 const int new_limit = min(n, limit + window);
-                for (int w = limit / 32 + warp; w < (new_limit + 31) / 32; w += kDetWarps) {
+                unsigned long long best = 0ull;
+                for (int w = limit / 32 + ((warp - limit / 32) & (kDetWarps - 1)); w < (new_limit + 31) / 32; w += kDetWarps) {
                     const int i = w * 32 + lane;
                     bool ok = i < new_limit;
                     if (ok) {
@@ -250,38 +252,59 @@ __device__ int soft_nms_rounds(const DetSmem &S, int n, bool gaussian, float sig
                             ok = sc > score_thr;
                         }
                         S.score[i] = sc;
+                        if (ok) { const unsigned long long key = score_key(i); best = key > best ? key : best; }
                     }
                     const unsigned k = __ballot_sync(0xffffffffu, ok);
                     if (lane == 0) S.alive[w] = k;
                 }
+                // merge with what this warp already had in the old prefix
+                const unsigned long long old = local_best(0, nwords);
+                best = warp_max64(best);
+                if (lane == 0) s_best[parity ^ 1][warp] = best > old ? best : old;
+                parity ^= 1;
                 limit = new_limit;
-                __syncthreads();
                 continue;
             }
         }
         if (pick == 0ull) break;
         const int top = (int)(0xFFFFFFFFu - (unsigned)(pick & 0xFFFFFFFFull));
-        if (threadIdx.x == 0) { emit(count, top, S.score[top]); picked[count] = top; }
+        {
+            // the pick's score is in its key (nobody may read score[top] now: its owner is about to decay it)
+            const unsigned vk = (unsigned)(pick >> 32);
+            const float top_score = __uint_as_float((vk & 0x80000000u) ? (vk ^ 0x80000000u) : ~vk);
+            if (threadIdx.x == 0) { emit(count, top, top_score); picked[count] = top; }
+        }
         ++count;
         const float4 p = S.box[top];
         const float ap = __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y));
-        __syncthreads();   // everyone has read score[top] / s_pick before scores change
+        unsigned long long best = 0ull;
         for (int w = warp; w < nwords; w += kDetWarps) {
-            const unsigned m = S.alive[w];
+            unsigned m = S.alive[w];
             if (!m) continue;
             const int i = w * 32 + lane;
             bool kill = false;
+            float sc = 0.f;
             if ((m >> lane) & 1u) {
-                float sc = S.score[i];
+                sc = S.score[i];
                 const float d = soft_decay(p, ap, S.box[i], gaussian, sigma, iou_thr);
                 if (d != 1.0f) { sc = __fmul_rn(sc, d); S.score[i] = sc; }
                 kill = !(sc > score_thr) || i == top;                                     // :103-104
             }
             const unsigned k = __ballot_sync(0xffffffffu, kill);
-            if (lane == 0 && k) S.alive[w] = m & ~k;
+            m &= ~k;
+            if (lane == 0 && k) S.alive[w] = m;
+            if ((m >> lane) & 1u) {
+                const unsigned u = __float_as_uint(sc);
+                const unsigned vk = u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
+                const unsigned long long key = ((unsigned long long)vk << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+                best = key > best ? key : best;
+            }
         }
-        __syncthreads();
+        best = warp_max64(best);
+        if (lane == 0) s_best[parity ^ 1][warp] = best;
+        parity ^= 1;
     }
+    __syncthreads();
     return count;
 }
 
