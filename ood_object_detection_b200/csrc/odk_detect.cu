@@ -24,6 +24,7 @@ namespace odk {
 constexpr int kDetThreads = 1024;
 constexpr int kDetMaxN = 8192;
 constexpr int kDetWarps = kDetThreads / 32;
+constexpr int kDetFirstWindow = 256;   // first activated chunk of the lazy window (doubles up to kDetThreads)
 
 struct DetSmem {
     float4 *box;          // [cap] class-offset xyxy boxes in processing order
@@ -109,7 +110,7 @@ __device__ __forceinline__ bool nms_hit(float4 p, float ap, float4 q, float thr_
     return (touch || thr_f < 0.0f) && iou_nms(p, ap, q) > thr_f;
 }
 
-__device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_keep, int *kept, int window) {
+__device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_keep, int *kept, int window, int window_max) {
     // One block barrier per round: while a warp kills the candidates of its words it also notes its
     // first survivor; after the barrier every warp reduces the 32 notes to the next pick by itself.
     __shared__ int s_first[2][kDetWarps];
@@ -131,6 +132,7 @@ __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_kee
         if (top == 0x7fffffff) {
             if (limit >= n) break;
             // activate the next chunk: a candidate stays alive iff nothing kept so far suppresses it
+            window = min(2 * window, window_max);   // chunks grow: 1 word per warp at most
             const int new_limit = min(n, limit + window);
             for (int w = limit / 32 + ((warp - limit / 32) & (kDetWarps - 1)); w < (new_limit + 31) / 32; w += kDetWarps) {
                 const int i = w * 32 + lane;
@@ -193,7 +195,7 @@ __device__ __forceinline__ float soft_decay(float4 p, float ap, float4 q, bool g
 
 template <class Emit>
 __device__ int soft_nms_rounds(const DetSmem &S, int n, bool gaussian, float sigma, float iou_thr, float score_thr,
-                               int max_rounds, int *picked, int window, Emit emit) {
+                               int max_rounds, int *picked, int window, int window_max, Emit emit) {
     // One block barrier per round: a warp that rescales its candidates also notes its best survivor
     // (score key, ~rank); after the barrier every warp reduces the 32 notes to the next pick itself.
     __shared__ unsigned long long s_best[2][kDetWarps];
@@ -237,6 +239,7 @@ __device__ int soft_nms_rounds(const DetSmem &S, int n, bool gaussian, float sig
             const unsigned ub = __float_as_uint(S.score[limit]);
             const unsigned bk = ub ^ ((unsigned)((int)ub >> 31) | 0x80000000u);
             if (pick == 0ull || (unsigned)(pick >> 32) < bk) {
+                window = min(2 * window, window_max);
                 const int new_limit = min(n, limit + window);
                 unsigned long long best = 0ull;
                 for (int w = limit / 32 + ((warp - limit / 32) & (kDetWarps - 1)); w < (new_limit + 31) / 32; w += kDetWarps) {
@@ -427,10 +430,10 @@ __global__ void __launch_bounds__(kDetThreads) detect_kernel(const __grid_consta
         if (A.p.soft_nms)
             // the window needs non-increasing scores: true for top-k output (checked below for API inputs)
             kept_n = soft_nms_rounds(S, n, true, A.p.soft_sigma, A.p.soft_iou, A.p.soft_score_thr, D, s_kept,
-                                     s_unsorted ? n : kDetThreads,
+                                     s_unsorted ? n : kDetFirstWindow, s_unsorted ? n : kDetThreads,
                                      [&](int q, int i, float sc) { s_keptscore[q] = sc; });
         else
-            kept_n = hard_nms_rounds(S, n, A.nms_thr_f, D, s_kept, kDetThreads);
+            kept_n = hard_nms_rounds(S, n, A.nms_thr_f, D, s_kept, kDetFirstWindow, kDetThreads);
         __syncthreads();
     }
     // 6. rows: boxes (re-decoded, unoffset) * img_scale, score, class + 1 (anchors.py:153-166)
@@ -466,7 +469,7 @@ soft_nms_kernel(const float4 *__restrict__ boxes, const float *__restrict__ scor
     init_alive(S.alive, n, cap);
     __syncthreads();
     __shared__ int s_picked[kDetMaxN];   // 32 KB: ranks in pick order (needed to replay decays)
-    const int c = soft_nms_rounds(S, n, gaussian != 0, sigma, iou_thr, score_thr, max_rounds, s_picked, n,
+    const int c = soft_nms_rounds(S, n, gaussian != 0, sigma, iou_thr, score_thr, max_rounds, s_picked, n, n,
                                   [&](int q, int i, float sc) { idx_out[q] = i; score_out[q] = sc; });
     if (threadIdx.x == 0) *count = c;
 }
@@ -506,7 +509,7 @@ nms_kernel(const float4 *__restrict__ boxes, const float *__restrict__ scores, i
     }
     init_alive(S.alive, n, cap);
     __syncthreads();
-    const int c = hard_nms_rounds(S, n, thr_f, n, s_kept, n);
+    const int c = hard_nms_rounds(S, n, thr_f, n, s_kept, n, n);
     __syncthreads();
     for (int q = threadIdx.x; q < c; q += kDetThreads) keep[q] = S.src[s_kept[q]];
     if (threadIdx.x == 0) *count = c;
