@@ -61,24 +61,34 @@ struct LossArgs {
 };
 
 // ---- element math ----------------------------------------------------------------------------
-// softplus(x) = max(x,0) + log1p(exp(-|x|)); also returns e = exp(-|x|).  One MUFU.EX2 and one
-// MUFU.LG2 (flush-to-zero forms: no denormal fix-up code), with a 4-term series where 1+e would
-// lose e's low bits.
+// softplus(x) = max(x,0) + log1p(e), e = exp(-|x|) in (0,1].  One MUFU.EX2 (flush-to-zero form: no
+// denormal fix-up code); log1p(e) = e*(1 + e*Q(e)) with Q a degree-7 polynomial fitted at Chebyshev
+// nodes of [0,1] (profiles/probes/log1p_poly.py: max relative error 3.1e-7 in fp32 Horner form, mean
+// signed error 6e-10).  A MUFU.LG2 here would make the XU pipe (4 lanes/clk/SMSP) the kernel's limit
+// and is biased near 1 (profiles/probes/lg2_probe.cu).
 __device__ __forceinline__ float ex2_ftz(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float lg2_ftz(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
+#define ODK_Q0 -0.4999998211860657f
+#define ODK_Q1 0.3333110213279724f
+#define ODK_Q2 -0.2494998425245285f
+#define ODK_Q3 0.19561563432216644f
+#define ODK_Q4 -0.14697664976119995f
+#define ODK_Q5 0.0910765677690506f
+#define ODK_Q6 -0.03774333372712135f
+#define ODK_Q7 0.007363723125308752f
+__device__ __forceinline__ float log1p_unit(float e) {
+    float t = fmaf(e, ODK_Q7, ODK_Q6);
+    t = fmaf(e, t, ODK_Q5); t = fmaf(e, t, ODK_Q4); t = fmaf(e, t, ODK_Q3);
+    t = fmaf(e, t, ODK_Q2); t = fmaf(e, t, ODK_Q1); t = fmaf(e, t, ODK_Q0);
+    t = fmaf(e, t, 1.0f);
+    return e * t;
 }
 __device__ __forceinline__ float softplus_fast(float x, float &e) {
     e = ex2_ftz(fabsf(x) * -1.4426950408889634f);
-    const float series = e * (1.0f - e * (0.5f - e * (0.33333334f - 0.25f * e)));
-    const float lg = lg2_ftz(1.0f + e) * 0.6931471805599453f;
-    return fmaxf(x, 0.0f) + (e < 0.03125f ? series : lg);
+    return fmaxf(x, 0.0f) + log1p_unit(e);
 }
 // Blackwell packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2: two fp32 results per issue slot).
 typedef unsigned long long f32x2;
@@ -88,21 +98,21 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
-// softplus of two values at once; same arithmetic as softplus_fast with the polynomial, 1+e and the
-// final sums done as packed pairs.  Returns the packed softplus, e0/e1 = exp(-|x|).
+// softplus of two values at once; same arithmetic as softplus_fast on packed pairs.
+// Returns the packed softplus, e0/e1 = exp(-|x|).
 __device__ __forceinline__ f32x2 softplus_fast2(float x0, float x1, float &e0, float &e1) {
     e0 = ex2_ftz(fabsf(x0) * -1.4426950408889634f);
     e1 = ex2_ftz(fabsf(x1) * -1.4426950408889634f);
-    const f32x2 E = pk2(e0, e1), ONE = pk2(1.0f, 1.0f);
-    float u0, u1, s0, s1;
-    upk2(add2(E, ONE), u0, u1);
-    f32x2 T = fma2(E, pk2(-0.25f, -0.25f), pk2(0.33333334f, 0.33333334f));
-    T = fma2(E, T, pk2(-0.5f, -0.5f));
-    T = fma2(E, T, ONE);
-    upk2(mul2(E, T), s0, s1);
-    const float l0 = lg2_ftz(u0) * 0.6931471805599453f, l1 = lg2_ftz(u1) * 0.6931471805599453f;
-    const float p0 = e0 < 0.03125f ? s0 : l0, p1 = e1 < 0.03125f ? s1 : l1;
-    return add2(pk2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)), pk2(p0, p1));
+    const f32x2 E = pk2(e0, e1);
+    f32x2 T = fma2(E, pk2(ODK_Q7, ODK_Q7), pk2(ODK_Q6, ODK_Q6));
+    T = fma2(E, T, pk2(ODK_Q5, ODK_Q5));
+    T = fma2(E, T, pk2(ODK_Q4, ODK_Q4));
+    T = fma2(E, T, pk2(ODK_Q3, ODK_Q3));
+    T = fma2(E, T, pk2(ODK_Q2, ODK_Q2));
+    T = fma2(E, T, pk2(ODK_Q1, ODK_Q1));
+    T = fma2(E, T, pk2(ODK_Q0, ODK_Q0));
+    T = fma2(E, T, pk2(1.0f, 1.0f));
+    return fma2(E, T, pk2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
 }
 
 __device__ __forceinline__ float sigmoid_from_e(float x, float e) {
@@ -412,7 +422,7 @@ loss_kernel(const __grid_constant__ LossArgs A) {
 
 // ---- cp.async ring kernel (vec4 levels only) -----------------------------------------------------
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const float *gptr) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
