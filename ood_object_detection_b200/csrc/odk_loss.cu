@@ -45,6 +45,7 @@ struct LossArgs {
     int vec[ODK_MAX_LEVELS];   // 4 if the level's planes are 16-byte aligned rows of 4, else 1
     int nq[ODK_MAX_LEVELS];    // position groups per plane
     int B, C, cchunk, nchunk, Mmax;
+    int keys_early;            // ring kernel: an item's assignment keys are requested when the load cursor enters it
     const int32_t *match;
     const float4 *anchors;
     const float4 *gt_boxes;
@@ -169,21 +170,28 @@ __device__ __forceinline__ int level_of_item(const LossArgs &A, unsigned it) {
 }
 
 // class target of each of my positions: >=0 class, -1 background, -2 ignore (+ matched gt row)
+template <int VEC>
+__device__ __forceinline__ void targets_from_match(const LossArgs &A, const Item &it, int (&tc)[VEC], const int (&mt)[VEC]) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) tc[j] = mt[j] >= 0 ? __ldg(A.gt_labels + (size_t)it.b * A.Mmax + mt[j]) - 1 : -1;
+}
+__device__ __forceinline__ int match_of_key(unsigned long long k) {
+    return k ? (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull)) : -1;
+}
 template <int VEC, bool FUSED>
 __device__ __forceinline__ void item_targets(const LossArgs &A, const Item &it, int (&tc)[VEC], int (&mt)[VEC]) {
     const Geo &g = A.g;
+    if (FUSED) {
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        if (FUSED) {
+        for (int j = 0; j < VEC; ++j) {
             const size_t mi = (size_t)it.b * g.Apad + g.off[it.l] + it.a * it.hw + it.s0 + j;
-            if (A.p.match_is_key64) {
-                const unsigned long long k = __ldg(reinterpret_cast<const unsigned long long *>(A.match) + mi);
-                mt[j] = k ? (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull)) : -1;
-            } else {
-                mt[j] = __ldg(A.match + mi);
-            }
-            tc[j] = mt[j] >= 0 ? __ldg(A.gt_labels + (size_t)it.b * A.Mmax + mt[j]) - 1 : -1;
-        } else {
+            if (A.p.match_is_key64) mt[j] = match_of_key(__ldg(reinterpret_cast<const unsigned long long *>(A.match) + mi));
+            else mt[j] = __ldg(A.match + mi);
+        }
+        targets_from_match<VEC>(A, it, tc, mt);
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
             mt[j] = -1;
             tc[j] = (int)__ldg(A.cls_t + (size_t)A.B * g.off[it.l] + ((size_t)it.b * it.hw + it.s0 + j) * g.na + it.a);
         }
@@ -446,11 +454,24 @@ loss_kernel_ring(const __grid_constant__ LossArgs A) {
     unsigned it_ld = first;
     const float *px_ld = nullptr;
     int rows_ld = 0, hw_ld = 0;
-    if (it_ld < total) {
+    // The 4 assignment keys (low words: ~gt index, 0 = unmatched) or match indices of an item are
+    // requested when the load cursor enters it, >= kRingDepth row-groups before the math needs them.
+    // (Registers, not the ring: more shared memory would shrink the L1 the cp.async.ca loads pass through.)
+    const bool keys_early = FUSED && A.keys_early;
+    unsigned nk[4] = {0u, 0u, 0u, 0u};
+    auto enter_item = [&]() {
         const int l = level_of_item(A, it_ld);
         const Item t = decode_item<4>(A, l, it_ld - A.item_off[l]);
         px_ld = A.cls[l] + t.plane0; rows_ld = t.c1 - t.c0; hw_ld = t.hw;
-    }
+        if (keys_early) {
+            const size_t mi = (size_t)t.b * A.g.Apad + A.g.off[l] + t.a * t.hw + t.s0;
+            const unsigned *kp = reinterpret_cast<const unsigned *>(A.match) + (A.p.match_is_key64 ? 2 * mi : mi);
+            const int step = A.p.match_is_key64 ? 2 : 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nk[j] = __ldg(kp + j * step);
+        }
+    };
+    if (it_ld < total) enter_item();
     auto issue_group = [&](int slot) {
         if (it_ld < total) {
             const unsigned dst = ring0 + (unsigned)(slot * 4) * (kLossThreads * 16u);
@@ -468,11 +489,7 @@ loss_kernel_ring(const __grid_constant__ LossArgs A) {
             px_ld += 4 * (size_t)hw_ld;
             if (rows_ld <= 0) {
                 it_ld += stride;
-                if (it_ld < total) {
-                    const int l = level_of_item(A, it_ld);
-                    const Item t = decode_item<4>(A, l, it_ld - A.item_off[l]);
-                    px_ld = A.cls[l] + t.plane0; rows_ld = t.c1 - t.c0; hw_ld = t.hw;
-                }
+                if (it_ld < total) enter_item();
             }
         }
         cp_async_commit();   // always commit so group counting stays uniform
@@ -486,7 +503,13 @@ loss_kernel_ring(const __grid_constant__ LossArgs A) {
         const int l = level_of_item(A, itx);
         const Item it = decode_item<4>(A, l, itx - A.item_off[l]);
         int tc[4], mt[4];
-        item_targets<4, FUSED>(A, it, tc, mt);
+        if (keys_early) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mt[j] = A.p.match_is_key64 ? (nk[j] ? (int)(0xFFFFFFFFu - nk[j]) : -1) : (int)nk[j];
+            targets_from_match<4>(A, it, tc, mt);
+        } else {
+            item_targets<4, FUSED>(A, it, tc, mt);
+        }
         float acc[4] = {0.f, 0.f, 0.f, 0.f}, accx[4] = {0.f, 0.f, 0.f, 0.f};
         float *pg = GRAD ? A.gcls[l] + it.plane0 : nullptr;
         for (int c = it.c0; c < it.c1; c += 4) {
@@ -636,6 +659,10 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
     a.cls_t = cls_targets; a.box_t = box_targets; a.normalizer = normalizer; a.p = *params; a.out = out;
     a.partials = (double *)workspace;
     a.counter = (unsigned *)((char *)workspace + (size_t)kMaxPartials * 2 * sizeof(double));
+
+    // Early key loads need every item to span more row-groups than the ring is deep: the load cursor
+    // must not enter item n+2 before the math has started item n+1 (one set of key registers).
+    a.keys_early = (fused && C - (a.nchunk - 1) * a.cchunk > 4 * kRingDepth) ? 1 : 0;
 
     // split the levels between the two kernels: item_off counts only the levels a launch covers
     LossArgs ring = a, plain = a;
