@@ -14,9 +14,12 @@
 //
 // Two kernels share all the arithmetic:
 //   loss_kernel_ring : levels whose planes are 16-byte aligned rows (H*W % 4 == 0).  Each thread
-//                      keeps a private ring of cp.async (LDGSTS) 16-byte copies in shared memory,
-//                      kRingDepth row-groups (4 rows = 64 B) ahead of the math, so ~150 KB per SM
-//                      is always in flight without spending registers on it.
+//                      keeps a private ring of cp.async.ca (LDGSTS) 16-byte copies in shared memory,
+//                      kRingDepth row-groups (4 rows = 64 B) ahead of the math, without spending
+//                      registers on it.  Measured on B200 (profiles/r1_summary.md): the .cg form
+//                      made L2 look every sector up twice (0.223 ms); with .ca the lines in flight
+//                      live in L1, so a SMALLER ring (more L1 left of the 256 KB) is faster:
+//                      4 / 3 / 2 slots = 0.196 / 0.192 / 0.190 ms.
 //   loss_kernel      : everything else (odd-sized levels such as D3's 7x7), plain register loads.
 #include <string.h>
 
@@ -27,7 +30,7 @@ namespace odk {
 constexpr int kLossThreads = 256;
 constexpr int kMaxPartials = 148 * 16;
 constexpr int kMaxChunk = 48;                  // classes per work item
-constexpr int kRingSlots = 4;                  // row-groups of smem per thread
+constexpr int kRingSlots = 2;                  // row-groups of smem per thread
 constexpr int kRingDepth = kRingSlots - 1;     // row-groups in flight ahead of the math
 constexpr int kRingBytes = kRingSlots * 4 * kLossThreads * 16;
 
