@@ -375,8 +375,8 @@ def run_ours(args):
             'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
                     'steps': e2e_steps},
-            'gpu_launches': 3 * args.steps,
-            'launches_per_step': {'odk::assign_gt_kernel': 1, 'odk::finish_counts_kernel': 1, 'odk::loss_kernel_ring': 1,
+            'gpu_launches': 2 * args.steps,
+            'launches_per_step': {'odk::assign_gt_kernel': 1, 'odk::loss_kernel_ring': 1,
                                   'cudaMemsetAsync': 2},
             'clocks': clocks,
             'fwd_plus_grad': {'ms_per_step': fwd_bwd_ms, 'images_per_s': BATCH / (fwd_bwd_ms * 1e-3),

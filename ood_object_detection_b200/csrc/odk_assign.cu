@@ -327,13 +327,14 @@ targets_kernel(const Geo g, int B, const float4 *__restrict__ anchors, const flo
 // writer of an anchor (old key 0) counts it into num_positives.
 constexpr int kGtcThreads = 256;
 constexpr int kMaxPlanes = ODK_MAX_LEVELS * 16;
+constexpr int kCellsInFlight = 4;
 constexpr int kDescFloats = 12;   // cy0, cx0, sy, sx, hy, hx, area, W, H, off, a, level
 
-__global__ void __launch_bounds__(kGtcThreads)
-assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *__restrict__ desc, int nplanes,
-                 const float4 *__restrict__ gt_boxes, const int32_t *__restrict__ gt_labels,
-                 const int32_t *__restrict__ gt_count, int Mmax, float thr, int filter_valid,
-                 unsigned long long *keys, int32_t *pos_count) {
+__device__ __forceinline__ void assign_one_gt(const Geo &g, const float4 *__restrict__ anchors, const float *__restrict__ desc,
+                                              int nplanes, const float4 *__restrict__ gt_boxes,
+                                              const int32_t *__restrict__ gt_labels, const int32_t *__restrict__ gt_count,
+                                              int Mmax, float thr, int filter_valid, unsigned long long *keys,
+                                              int32_t *pos_count) {
     __shared__ int s_off[kMaxPlanes + 1], s_x0[kMaxPlanes], s_nx[kMaxPlanes], s_y0[kMaxPlanes];
     __shared__ int s_w[kMaxPlanes], s_base[kMaxPlanes], s_sh[kMaxPlanes], s_hw[kMaxPlanes];
     __shared__ unsigned char s_done[kMaxPlanes];
@@ -408,8 +409,8 @@ assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *_
         if (total == 0) continue;   // uniform (pass 0 may select nothing: pass 1 still has to look)
 
         // ---- enumerate the cells ----
-        // a thread's cells c = tid, tid+256, ... ascend, so its plane index only moves forward; two cells
-        // are in flight per iteration (independent anchor gathers)
+        // a thread's cells c = tid, tid+256, ... ascend, so its plane index only moves forward;
+        // kCellsInFlight cells per iteration (independent anchor gathers)
         unsigned long long best = 0ull;
         int kcur = 0;
         auto locate = [&](int c, int &k, int &r, int &p, bool &ok) {
@@ -444,17 +445,17 @@ assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *_
                 }
             }
         };
-        for (int c = tid; c < total; c += 2 * kGtcThreads) {
-            int r0, p0, r1, p1;
-            bool ok0, ok1;
-            locate(c, kcur, r0, p0, ok0);
-            int k1 = kcur;
-            locate(c + kGtcThreads, k1, r1, p1, ok1);
-            const float4 a0 = __ldg(anchors + r0);
-            const float4 a1 = __ldg(anchors + r1);   // r1 = 0 when out of range: a harmless, cached read
-            visit(a0, r0, p0);
-            if (ok1) visit(a1, r1, p1);
-            kcur = k1;
+        for (int c = tid; c < total; c += kCellsInFlight * kGtcThreads) {
+            int r[kCellsInFlight], p[kCellsInFlight];
+            bool ok[kCellsInFlight];
+            float4 a[kCellsInFlight];
+#pragma unroll
+            for (int u = 0; u < kCellsInFlight; ++u) locate(c + u * kGtcThreads, kcur, r[u], p[u], ok[u]);
+#pragma unroll
+            for (int u = 0; u < kCellsInFlight; ++u) a[u] = __ldg(anchors + r[u]);   // r = 0 when out of range: a harmless, cached read
+#pragma unroll
+            for (int u = 0; u < kCellsInFlight; ++u)
+                if (ok[u]) visit(a[u], r[u], p[u]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -481,14 +482,14 @@ assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *_
     }
 }
 
-// keys -> match (gt row or -1) and num_positives; four anchors per thread
-// num_positives per image and the loss normaliser sum + 1 (loss.py:261); one CTA
-__global__ void __launch_bounds__(256)
-finish_counts_kernel(int B, const int32_t *__restrict__ pos_count, float *__restrict__ num_pos, float *__restrict__ normalizer) {
-    __shared__ float s_w[8];
+// num_positives per image and the loss normaliser sum + 1 (loss.py:261), by one CTA
+template <bool COHERENT>
+__device__ __forceinline__ void finish_counts(int B, const int32_t *pos_count, float *num_pos, float *normalizer) {
+    __shared__ float s_w[kGtcThreads / 32];
     float acc = 0.f;
-    for (int b = threadIdx.x; b < B; b += 256) {
-        const float v = (float)__ldg(pos_count + (size_t)b * kCtrStride);
+    for (int b = threadIdx.x; b < B; b += kGtcThreads) {
+        const int32_t *pc = pos_count + (size_t)b * kCtrStride;
+        const float v = (float)(COHERENT ? __ldcg(pc) : __ldg(pc));
         num_pos[b] = v;
         acc += v;   // integer-valued, exact in fp32 below 2^24 like the reference's fp32 sum
     }
@@ -497,9 +498,33 @@ finish_counts_kernel(int B, const int32_t *__restrict__ pos_count, float *__rest
     __syncthreads();
     if (threadIdx.x == 0 && normalizer) {
         float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += s_w[w];
+        for (int w = 0; w < kGtcThreads / 32; ++w) t += s_w[w];
         normalizer[0] = t + 1.0f;
     }
+}
+
+// One CTA per (gt row, image); the CTA that finishes last turns the counters into num_positives and
+// the normaliser, so the loss kernel can follow without another launch.
+__global__ void __launch_bounds__(kGtcThreads)
+assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *__restrict__ desc, int nplanes,
+                 const float4 *__restrict__ gt_boxes, const int32_t *__restrict__ gt_labels,
+                 const int32_t *__restrict__ gt_count, int Mmax, float thr, int filter_valid,
+                 unsigned long long *keys, int32_t *pos_count, unsigned *done, int B, float *num_pos, float *normalizer) {
+    __shared__ bool s_last;
+    assign_one_gt(g, anchors, desc, nplanes, gt_boxes, gt_labels, gt_count, Mmax, thr, filter_valid, keys, pos_count);
+    __threadfence();   // this thread's counter updates are visible before the CTA reports in
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x * gridDim.y - 1u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        finish_counts<true>(B, pos_count, num_pos, normalizer);
+    }
+}
+
+__global__ void __launch_bounds__(kGtcThreads)
+finish_counts_kernel(int B, const int32_t *__restrict__ pos_count, float *__restrict__ num_pos, float *__restrict__ normalizer) {
+    finish_counts<false>(B, pos_count, num_pos, normalizer);
 }
 
 __global__ void __launch_bounds__(256)
@@ -646,18 +671,19 @@ int odk_assign_grid(const float *anchors, const float *plane_desc, int num_plane
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long *keys = (unsigned long long *)workspace;
     int32_t *pos = (int32_t *)((char *)workspace + (size_t)B * g.Apad * sizeof(unsigned long long));
-    cudaError_t e = cudaMemsetAsync(workspace, 0, odk_assign_grid_workspace_bytes(B, g.A) - 16, st);
+    unsigned *done = (unsigned *)((char *)workspace + odk_assign_grid_workspace_bytes(B, g.A) - 16);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, odk_assign_grid_workspace_bytes(B, g.A), st);
     if (e != cudaSuccess) return set_error((int)e, "odk_assign_grid memset: %s", cudaGetErrorString(e));
     if (Mmax > 0) {
         dim3 grid(Mmax, B);
         assign_gt_kernel<<<grid, kGtcThreads, 0, st>>>(g, (const float4 *)anchors, plane_desc, num_planes,
                                                        (const float4 *)gt_boxes, gt_labels, gt_count, Mmax, match_thr,
-                                                       filter_valid, keys, pos);
+                                                       filter_valid, keys, pos, done, B, num_pos, normalizer);
         rc = check_launch("odk_assign_grid/assign_gt_kernel");
-        if (rc) return rc;
+    } else {
+        finish_counts_kernel<<<1, kGtcThreads, 0, st>>>(B, pos, num_pos, normalizer);
+        rc = check_launch("odk_assign_grid/finish_counts_kernel");
     }
-    finish_counts_kernel<<<1, 256, 0, st>>>(B, pos, num_pos, normalizer);
-    rc = check_launch("odk_assign_grid/finish_counts_kernel");
     if (rc || !match) return rc;
     return odk_keys_to_match(keys, B, g.A, match, stream);
 }
