@@ -13,6 +13,7 @@ memory for `e2e`.  `--impl reference` times the CPU restatement of the reference
 (oracle/, OpenMP over all host cores) on a bounded sample of the same workload.
 """
 import argparse
+import gc
 import json
 import os
 import sys
@@ -148,7 +149,8 @@ def run_ours(args):
     from ood_object_detection_b200 import _lib
     from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
     from ood_object_detection_b200.loss import loss_fn_fused
-    from ood_object_detection_b200.distributed import forward_losses_one_collective, global_normalizer, reduce_losses
+    from ood_object_detection_b200.distributed import (LossReducePipeline, all_reduce_partial_sums,
+                                                       forward_losses_one_collective, local_partial_sums)
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -177,30 +179,34 @@ def run_ours(args):
     unit = torch.ones((1,), dtype=torch.float32, device=dev)
 
     def compute():
-        """Our kernels for one batch: labeler -> fused loss (N > 1: partial sums against a unit normaliser)."""
+        """Our kernels for one batch: labeler -> fused loss (N > 1: partial sums against a unit normaliser,
+        both kernels writing into one 4-float buffer, so nothing else runs between them)."""
+        if world > 1:
+            return local_partial_sums(labeler, cls_out, box_out, gt_boxes, gt_cls, unit, **LOSS_KW), None
         lb = labeler.assign(gt_boxes, gt_cls)
-        out = loss_fn_fused(cls_out, box_out, lb, normalizer=unit if world > 1 else None, **LOSS_KW)
-        return out, lb.num_positives
+        return loss_fn_fused(cls_out, box_out, lb, **LOSS_KW), lb.num_positives
+
+    reducer = LossReducePipeline(dev) if world > 1 else None
 
     def finish(out, npos):
+        """N > 1: ONE all-reduce of 4 floats, divided by the global (num_positives + 1) afterwards, all of it
+        on a side stream and collected one step later, so it overlaps the next step's kernels (the loss
+        values are only logged, nothing waits on them).  Returns (losses, event guarding `out`'s reuse)."""
         if world > 1:
-            # ONE all-reduce of 3 floats, divide by the global (num_positives + 1) afterwards.  It runs on
-            # NCCL's stream and is collected one step later, so it overlaps the next step's kernels (the
-            # loss values are only logged, nothing waits on them).
-            pending.append(forward_losses_one_collective(out[1], out[2], npos, LOSS_KW['box_loss_weight'], async_op=True))
-            if len(pending) > 1:
-                return pending.pop(0).result()
-        return out
+            done = reducer.submit(out)
+            if len(reducer) > 1:
+                return reducer.collect()[0], done
+            return None, done
+        return out, None
 
     def step():
-        return finish(*compute())
-
-    pending = []
+        return finish(*compute())[0]
 
     def drain():
         out = None
-        while pending:
-            out = pending.pop(0).result()
+        while reducer is not None and len(reducer):
+            out, done = reducer.collect()
+            torch.cuda.current_stream().wait_event(done)
         return out
 
     def sync_all():
@@ -218,42 +224,67 @@ def run_ours(args):
         # The compute part of a step is a fixed launch sequence (memsets, our kernels, tiny torch kernels):
         # it is captured once into a CUDA graph and replayed, so the timed region measures the GPU, not the
         # python launch path.  The NCCL all-reduce (N > 1) stays outside the graph.
-        graph, graph_out, mode = None, None, 'eager'
+        # N > 1: the all-reduce is captured too, software-pipelined: graph k = [our kernels -> bufs[k]] in
+        # parallel with [all-reduce + normalise bufs[1-k], filled by the previous replay], so a step costs
+        # the host one graph launch and the collective never sits between two steps' kernels.
+        graphs, graph_outs, mode = [], [], 'eager'
+        bufs = [torch.zeros((4,), dtype=torch.float32, device=dev) for _ in range(2)]
         if not args.no_graph:
             try:
-                side = torch.cuda.Stream()
+                side, aux = torch.cuda.Stream(), torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
                     compute()
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph, stream=side):
-                        graph_out = compute()
+                    for k in range(2 if world > 1 else 1):
+                        gr = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gr, stream=side):
+                            if world > 1:
+                                aux.wait_stream(side)                      # fork
+                                with torch.cuda.stream(aux):
+                                    reduced = all_reduce_partial_sums(bufs[1 - k], copy=False)
+                                local_partial_sums(labeler, cls_out, box_out, gt_boxes, gt_cls, unit, buf=bufs[k], **LOSS_KW)
+                                side.wait_stream(aux)                      # join
+                                graph_outs.append(reduced)
+                            else:
+                                graph_outs.append(compute()[0])
+                        graphs.append(gr)
                 torch.cuda.current_stream().wait_stream(side)
                 for _ in range(3):
-                    graph.replay()
+                    for gr in graphs:
+                        gr.replay()
                 torch.cuda.synchronize()
-                mode = 'cuda_graph'
+                mode = 'cuda_graph' if world == 1 else 'cuda_graph (kernels + pipelined all-reduce)'
             except Exception as exc:  # capture is an optimisation, never a requirement
-                graph, mode = None, f'eager (graph capture failed: {type(exc).__name__})'
+                graphs, mode = [], f'eager (graph capture failed: {type(exc).__name__})'
                 torch.cuda.synchronize()
         if sampler:
             sampler.start()
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_start.record()
-        if graph is not None:
+        last = None
+        if graphs:
             for i in range(args.steps):
-                graph.replay()
-                last = finish(*graph_out)
-            if world > 1:
-                last = drain() or last
+                graphs[i % len(graphs)].replay()
+            if world > 1:   # the last step's partial sums are still local: reduce them now, inside the timed region
+                last = all_reduce_partial_sums(bufs[(args.steps - 1) % 2])
+            else:
+                last = graph_outs[0]
         else:
             for i in range(args.steps):
-                last = step()
+                out = step()
+                last = out if out is not None else last
             if world > 1:
-                last = drain() or last
+                last = drain() or last   # the timed region ends after the last collective (drain waits on it)
         t_end.record()
         sync_all()
         total_ms = t_start.elapsed_time(t_end)
+        if world > 1:
+            # graphs that hold NCCL kernels must be gone before the process group is torn down
+            last = [float(x) for x in last]
+            graphs.clear()
+            graph_outs.clear()
+            gc.collect()
+            torch.cuda.synchronize()
         # the dominant kernel alone: K back-to-back launches of the loss on the same inputs (its 4-byte
         # counter memset included), one event pair around them -- the queue stays full, so this is device
         # time per launch, not python time
@@ -384,10 +415,16 @@ def run_ours(args):
                               'note': 'labeler + loss fwd + d total/d outputs written in the same pass + backward()'},
             'extra': extra,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
         dist.barrier()
+        # the line is out: never let a communicator teardown problem hold the launcher
+        guard = threading.Timer(30.0, os._exit, (0,))
+        guard.daemon = True
+        guard.start()
         dist.destroy_process_group()
+        guard.cancel()
 
 
 def postprocess_extra(torch, dev, synth):

@@ -227,8 +227,9 @@ class AnchorLabeler(object):
                 overlapping, _ = (sims > 0.9).max(0) if sims.shape[0] > 0 else (torch.zeros_like(task_mask), None)
                 gt_classes[i][overlapping] = task_cls
 
-    def assign(self, gt_boxes, gt_classes, filter_valid=True, task_cls=None) -> LabelBatch:
-        """Run the assignment kernels; the result feeds either ``targets()`` or the fused loss."""
+    def assign(self, gt_boxes, gt_classes, filter_valid=True, task_cls=None, normalizer_out=None) -> LabelBatch:
+        """Run the assignment kernels; the result feeds either ``targets()`` or the fused loss.
+        ``normalizer_out`` (float32 [1], same device) receives sum(num_positives) + 1 in place."""
         if task_cls is not None:
             self._relabel_task_cls(gt_boxes, gt_classes, task_cls)
         boxes, labels, count = self._pack(gt_boxes, gt_classes, filter_valid)
@@ -249,7 +250,9 @@ class AnchorLabeler(object):
                 # int32 `match` is only materialised if somebody asks for it (LabelBatch.match / targets())
                 ws_bytes = lib.odk_assign_grid_workspace_bytes(B, A)
                 ws = torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=dev)
-                normalizer = torch.empty((1,), dtype=torch.float32, device=dev)
+                normalizer = torch.empty((1,), dtype=torch.float32, device=dev) if normalizer_out is None else normalizer_out
+                if normalizer.dtype != torch.float32 or normalizer.numel() != 1 or normalizer.device != dev:
+                    raise ValueError('normalizer_out must be one float32 element on the gt device')
                 _lib.check(lib.odk_assign_grid(_lib.ptr(anc), _lib.ptr(desc), desc.shape[0], _lib.ptr(boxes),
                                                _lib.ptr(labels), _lib.ptr(count), B, M, _lib.int_array(hw), len(hw), na,
                                                thr, int(bool(filter_valid)), None, _lib.ptr(num_pos),
@@ -264,7 +267,9 @@ class AnchorLabeler(object):
                                           _lib.int_array(hw), len(hw), na, thr, int(bool(filter_valid)),
                                           _lib.ptr(match), _lib.ptr(num_pos), _lib.ptr(ws), ws.numel() * 8,
                                           _lib.stream_ptr(dev)))
-        return LabelBatch(self, boxes, labels, match, num_pos)
+        if normalizer_out is not None:   # this kernel has no normaliser output: loss.py:261 in torch
+            normalizer_out.copy_((num_pos.sum() + 1.0).reshape(normalizer_out.shape))
+        return LabelBatch(self, boxes, labels, match, num_pos, normalizer=normalizer_out)
 
     def _materialize(self, lb: LabelBatch):
         lib = _lib.lib()

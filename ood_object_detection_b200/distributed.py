@@ -74,6 +74,81 @@ def forward_losses_one_collective(cls_unnorm, box_unnorm, num_positives, box_los
     return pending if async_op else pending.result()
 
 
+class PendingPartialSums:
+    """Result of ``all_reduce_partial_sums(..., async_op=True)``; ``result()`` waits and normalises."""
+
+    def __init__(self, packed, work, world):
+        self.packed, self.work, self.world = packed, work, world
+
+    def result(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        # slot 3 is sum_r (sum(num_positives_r) + 1): the global normaliser is that minus (world - 1)
+        res = self.packed[:3] / (self.packed[3] - float(self.world - 1))
+        return res[0], res[1], res[2]
+
+
+def local_partial_sums(labeler, cls_outputs, box_outputs, gt_boxes, gt_classes, unit, buf=None, **loss_kw):
+    """This rank's share of the forward loss with no torch kernel in between: the labeler writes
+    sum(num_positives) + 1 into slot 3 of one 4-float buffer (``buf``, allocated when None) and the
+    fused loss (against the unit normaliser ``unit``) writes [cls + w * box, cls, box] partial sums
+    into slots 0..2."""
+    from .loss import loss_fn_fused
+    if buf is None:
+        buf = torch.empty((4,), dtype=torch.float32, device=gt_boxes.device)
+    lb = labeler.assign(gt_boxes, gt_classes, normalizer_out=buf[3:4])
+    loss_fn_fused(cls_outputs, box_outputs, lb, normalizer=unit, out=buf, **loss_kw)
+    return buf
+
+
+def all_reduce_partial_sums(buf, group=None, async_op=False, copy=True):
+    """ONE all-reduce of the 4 floats of ``local_partial_sums``; returns (total, cls, box) of the GLOBAL
+    batch (or a ``PendingPartialSums``).  With ``copy`` the buffer is cloned first, so the caller may
+    overwrite it right away (the next CUDA-graph replay does) while the collective is still in flight;
+    ``copy=False`` reduces in place (see ``LossReducePipeline`` for the ordering that makes that safe)."""
+    packed = buf.detach().clone() if copy else buf.detach()
+    world, work = 1, None
+    if _active(group):
+        world = dist.get_world_size(group)
+        work = dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    pending = PendingPartialSums(packed, work if async_op else None, world)
+    return pending if async_op else pending.result()
+
+
+class LossReducePipeline:
+    """Keeps the per-step collective and its bookkeeping OFF the compute stream.
+
+    ``submit(buf)`` (called on the compute stream right after the kernels that fill ``buf``) records an
+    event and, on a side stream, waits for it, all-reduces ``buf`` in place and normalises.  The compute
+    stream never waits for the collective: it only has to wait for the returned ``done`` event before
+    the same ``buf`` is written again (two alternating buffers / CUDA graphs make that wait free).
+    ``collect()`` returns the oldest (total, cls, box) -- tensors produced on the side stream -- and its
+    ``done`` event; synchronise on it (or the device) before reading them elsewhere."""
+
+    def __init__(self, device, group=None):
+        self.group = group
+        self.side = torch.cuda.Stream(device=device)
+        self.pending = []
+
+    def submit(self, buf):
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            res = all_reduce_partial_sums(buf, self.group, async_op=True, copy=False).result()
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self.pending.append((res, done))
+        return done
+
+    def collect(self):
+        return self.pending.pop(0)
+
+    def __len__(self):
+        return len(self.pending)
+
+
 def sharded_detection_loss(loss_module, cls_outputs, box_outputs, label_batch, group=None):
     """Local shard's fused loss against the GLOBAL normaliser.
 

@@ -64,7 +64,11 @@ class _DetectionLossFn(torch.autograd.Function):
         for c, b in zip(cls_out, box_out):
             if c.shape[1] != na * C or b.shape[0] != B or c.shape[0] != B:
                 raise ValueError(f'class outputs {tuple(c.shape)} do not match num_classes={C}, anchors/location={na}')
-        out = torch.empty((3,), dtype=torch.float32, device=dev)
+        out = meta.get('out')
+        if out is None:
+            out = torch.empty((3,), dtype=torch.float32, device=dev)
+        elif out.dtype != torch.float32 or out.numel() < 3 or not out.is_contiguous() or out.device != dev:
+            raise ValueError('out= must be a contiguous float32 tensor with >= 3 elements on the outputs\' device')
         ws = torch.empty((lib.odk_loss_workspace_bytes() + 15) // 16 * 2, dtype=torch.int64, device=dev)
         gcls = gbox = None
         gcls_p = gbox_p = None
@@ -163,15 +167,16 @@ def loss_fn(
 
 def loss_fn_fused(cls_outputs, box_outputs, label_batch, num_classes: int, alpha: float, gamma: float, delta: float,
                   box_loss_weight: float, label_smoothing: float = 0., legacy_focal: bool = False,
-                  normalizer: Optional[torch.Tensor] = None):
+                  normalizer: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
     """Same value as ``loss_fn(.., *labeler.batch_label_anchors(..))`` without ever materialising
-    the target tensors: ``label_batch`` is ``AnchorLabeler.assign(...)``."""
+    the target tensors: ``label_batch`` is ``AnchorLabeler.assign(...)``.  ``out`` (float32, >= 3
+    elements) receives [total, cls_loss, box_loss] in place; the returned scalars are views of it."""
     if normalizer is None:
         normalizer = label_batch.normalizer if label_batch.normalizer is not None else _normalizer(label_batch.num_positives)
     meta = dict(levels=len(cls_outputs), num_classes=int(num_classes), alpha=float(alpha), gamma=float(gamma),
                 delta=float(delta), box_loss_weight=float(box_loss_weight), label_smoothing=float(label_smoothing),
                 legacy_focal=bool(legacy_focal), label_batch=label_batch,
-                normalizer=normalizer.float().reshape(1).contiguous())
+                normalizer=normalizer.float().reshape(1).contiguous(), out=out)
     return _DetectionLossFn.apply(meta, *cls_outputs, *box_outputs)
 
 

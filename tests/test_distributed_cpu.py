@@ -48,6 +48,9 @@ def _worker(rank, world, port, out_dir):
     unit = orc.loss_fn([c[lo:hi] for c in co], [b[lo:hi] for b in bo], orc.split_levels(cls_t, fhw),
                        orc.split_levels(box_t, fhw), np.zeros(1, np.float32), C, 0.25, 1.5, 0.1, 50.0)
     one = D.forward_losses_one_collective(torch.tensor(unit[1]), torch.tensor(unit[2]), torch.from_numpy(npos), 50.0)
+    # packed form: [cls + w*box, cls, box, sum(num_positives) + 1] as the two kernels leave it in one buffer
+    buf = torch.tensor([unit[1] + 50.0 * unit[2], unit[1], unit[2], float(npos.sum()) + 1.0], dtype=torch.float32)
+    packed = D.all_reduce_partial_sums(buf, async_op=True).result()
     # ---- detections: each rank post-processes its images, all-gather in rank order ----
     o_cls, o_box, o_idx, o_klass = orc.post_process([c[lo:hi] for c in co], [b[lo:hi] for b in bo], 5, C, 300)
     Dmax = 20
@@ -60,7 +63,7 @@ def _worker(rank, world, port, out_dir):
     g_dets, g_count = D.gather_detections(dets, count)
     if rank == 0:
         np.savez(os.path.join(out_dir, 'sharded.npz'), loss=np.array([tot.item(), cl.item(), bl.item()]),
-                 one=np.array([float(v) for v in one]),
+                 one=np.array([float(v) for v in one]), packed=np.array([float(v) for v in packed]),
                  dets=g_dets.numpy(), count=g_count.numpy(), norm=norm.numpy())
     dist.barrier()
     dist.destroy_process_group()
@@ -83,6 +86,7 @@ def test_sharded_path_matches_single_process(tmp_path):
     np.testing.assert_allclose(got['norm'], npos.sum() + 1.0)
     np.testing.assert_allclose(got['loss'], ref, rtol=1e-6)   # same element values, different summation split
     np.testing.assert_allclose(got['one'], ref, rtol=1e-5)    # one-collective forward form (fp32 wire format)
+    np.testing.assert_allclose(got['packed'], ref, rtol=1e-5)  # same, 4-float buffer written by the kernels
     o_cls, o_box, o_idx, o_klass = orc.post_process(co, bo, 5, C, 300)
     assert got['dets'].shape == (B, 20, 6)
     for i in range(B):
@@ -108,5 +112,7 @@ def test_single_process_helpers_are_identity():
     assert D.global_normalizer(npos).item() == 9.0
     t = D.reduce_losses(torch.tensor(1.5), torch.tensor(1.0), torch.tensor(0.01))
     assert [float(x) for x in t] == [1.5, 1.0, pytest.approx(0.01)]
+    tot, cl, bx = D.all_reduce_partial_sums(torch.tensor([12.0, 2.0, 0.2, 4.0]))
+    assert [float(x) for x in (tot, cl, bx)] == [3.0, 0.5, pytest.approx(0.05)]
     d, c = D.gather_detections(torch.zeros(2, 4, 6), torch.zeros(2, dtype=torch.int32))
     assert d.shape == (2, 4, 6) and c.shape == (2,)

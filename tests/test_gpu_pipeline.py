@@ -55,3 +55,27 @@ def test_detections_for_evaluator():
         np.testing.assert_array_equal(out[i]['cls'], dets[i, :n, 5])
     raw = detections_for_evaluator(torch.from_numpy(dets).to(DEV), torch.from_numpy(count).to(DEV), yxyx=False)
     np.testing.assert_array_equal(raw[0]['bbox'], dets[0, :10, :4])
+
+
+@pytest.mark.parametrize('grid', [True, False])
+def test_partial_sums_buffer_equals_fused_loss(grid):
+    """distributed.local_partial_sums: both kernels write one 4-float buffer; normalising it (what the
+    all-reduce path does on every rank) gives the oracle's loss."""
+    from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
+    from ood_object_detection_b200 import distributed as D
+    size, B, C, M = 256, 4, 20, 6
+    anc = Anchors(3, 7, 3, synth.ASPECTS, 4.0, (size, size)).to(DEV)
+    lab = AnchorLabeler(anc, C)
+    lab.use_grid_kernel = grid
+    gb, gc = synth.gt_boxes(31, B, size, M, C)
+    co, bo = synth.head_outputs(32, B, size, C, tie_free=False)
+    kw = dict(num_classes=C, alpha=0.25, gamma=1.5, delta=0.1, box_loss_weight=50.0)
+    unit = torch.ones((1,), device=DEV)
+    buf = D.local_partial_sums(lab, [torch.from_numpy(x).to(DEV) for x in co], [torch.from_numpy(x).to(DEV) for x in bo],
+                               torch.from_numpy(gb).to(DEV), torch.from_numpy(gc).to(DEV), unit, **kw)
+    oc, ob, onp, _, _ = orc.batch_label_anchors(anc.boxes.cpu().numpy(), list(gb), list(gc))
+    fhw = synth.feat_hw(size)
+    ref = orc.loss_fn(co, bo, orc.split_levels(oc, fhw), orc.split_levels(ob, fhw), onp, C, 0.25, 1.5, 0.1, 50.0)
+    assert float(buf[3]) == float(onp.sum()) + 1.0
+    got = D.all_reduce_partial_sums(buf)      # single process: just the normalisation
+    np.testing.assert_allclose([float(v) for v in got], ref, rtol=1e-5)
