@@ -19,7 +19,7 @@
 //                      registers on it.  Measured on B200 (profiles/r1_summary.md): the .cg form
 //                      made L2 look every sector up twice (0.223 ms); with .ca the lines in flight
 //                      live in L1, so a SMALLER ring (more L1 left of the 256 KB) is faster:
-//                      4 / 3 / 2 slots = 0.196 / 0.192 / 0.190 ms.
+//                      4 / 3 / 2 slots = 0.196 / 0.192 / 0.190 ms (forward).
 //   loss_kernel      : everything else (odd-sized levels such as D3's 7x7), plain register loads.
 #include <string.h>
 
@@ -30,9 +30,11 @@ namespace odk {
 constexpr int kLossThreads = 256;
 constexpr int kMaxPartials = 148 * 16;
 constexpr int kMaxChunk = 48;                  // classes per work item
-constexpr int kRingSlots = 2;                  // row-groups of smem per thread
-constexpr int kRingDepth = kRingSlots - 1;     // row-groups in flight ahead of the math
-constexpr int kRingBytes = kRingSlots * 4 * kLossThreads * 16;
+// row-groups of smem per thread: both passes are fastest with the smallest ring (most L1 left); measured
+// fwd 0.190 ms and fwd+grad step 0.471 ms with 2 slots, 0.192 / 0.485 ms with 3
+__host__ __device__ constexpr int ring_slots(bool grad) { return grad ? 2 : 2; }
+constexpr int kMaxRingDepth = 1;               // row-groups in flight ahead of the math, at most
+__host__ __device__ constexpr int ring_bytes(bool grad) { return ring_slots(grad) * 4 * kLossThreads * 16; }
 
 enum LossMode { kNew = 0, kNewSmooth = 1, kLegacy = 2 };
 
@@ -443,6 +445,7 @@ template <int MODE, bool GRAD, bool FUSED>
 __global__ void __launch_bounds__(kLossThreads, 3)
 loss_kernel_ring(const __grid_constant__ LossArgs A) {
     extern __shared__ __align__(16) unsigned char s_ring[];
+    constexpr int kRingSlots = ring_slots(GRAD), kRingDepth = kRingSlots - 1;
     const float nrm = __ldg(A.normalizer);
     const float inv_n = 1.0f / nrm;
     float csum = 0.f, bsum = 0.f;
@@ -573,8 +576,8 @@ template <int MODE, bool GRAD, bool FUSED>
 static int launch_loss(LossArgs &ring, LossArgs &plain, cudaStream_t st) {
     static int occ_ring = 0, occ_plain = 0;
     if (!occ_ring) {
-        cudaFuncSetAttribute(loss_kernel_ring<MODE, GRAD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ring, loss_kernel_ring<MODE, GRAD, FUSED>, kLossThreads, kRingBytes);
+        cudaFuncSetAttribute(loss_kernel_ring<MODE, GRAD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes(GRAD));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ring, loss_kernel_ring<MODE, GRAD, FUSED>, kLossThreads, ring_bytes(GRAD));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_plain, loss_kernel<MODE, GRAD, FUSED>, kLossThreads, 0);
         if (occ_ring < 1) occ_ring = 1;
         if (occ_plain < 1) occ_plain = 1;
@@ -598,7 +601,7 @@ static int launch_loss(LossArgs &ring, LossArgs &plain, cudaStream_t st) {
     if (n_ring > 0) {
         ring.part_base = g_plain;
         ring.part_total = g_plain + g_ring;
-        loss_kernel_ring<MODE, GRAD, FUSED><<<g_ring, kLossThreads, kRingBytes, st>>>(ring);
+        loss_kernel_ring<MODE, GRAD, FUSED><<<g_ring, kLossThreads, ring_bytes(GRAD), st>>>(ring);
         return check_launch("odk_loss/loss_kernel_ring");
     }
     return ODK_OK;
@@ -665,7 +668,7 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
 
     // Early key loads need every item to span more row-groups than the ring is deep: the load cursor
     // must not enter item n+2 before the math has started item n+1 (one set of key registers).
-    a.keys_early = (fused && C - (a.nchunk - 1) * a.cchunk > 4 * kRingDepth) ? 1 : 0;
+    a.keys_early = (fused && C - (a.nchunk - 1) * a.cchunk > 4 * kMaxRingDepth) ? 1 : 0;
 
     // split the levels between the two kernels: item_off counts only the levels a launch covers
     LossArgs ring = a, plain = a;

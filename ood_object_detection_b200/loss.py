@@ -57,6 +57,7 @@ class _DetectionLossFn(torch.autograd.Function):
         dev = cls_out[0].device
         lib = _lib.lib()
         need_grad = any(ctx.needs_input_grad[1:])
+        ctx.set_materialize_grads(False)   # unused outputs arrive as None in backward: no zero-fill kernels
         B = cls_out[0].shape[0]
         C = meta['num_classes']
         hw = [c.shape[2] * c.shape[3] for c in cls_out]
@@ -106,12 +107,18 @@ class _DetectionLossFn(torch.autograd.Function):
     def backward(ctx, g_total, g_cls, g_box):
         lib = _lib.lib()
         dev = ctx.gcls[0].device
-        zero = torch.zeros((), dtype=torch.float32, device=dev)
-        g_total = zero if g_total is None else g_total.float()
-        # stored: d total / d logits (= d cls_loss / d logits) and d total / d box (= w * d box_loss / d box)
-        s_cls = (g_total + (zero if g_cls is None else g_cls.float())).reshape(1).contiguous()
+        # stored: d total / d logits (= d cls_loss / d logits) and d total / d box (= w * d box_loss / d box);
+        # in the usual total.backward() both factors ARE g_total and no torch kernel runs here
         w = ctx.box_loss_weight
-        s_box = (g_total + (zero if g_box is None or w == 0 else g_box.float() / w)).reshape(1).contiguous()
+
+        def factor(a, b):
+            if a is None and b is None:
+                return torch.zeros((1,), dtype=torch.float32, device=dev)
+            t = a if b is None else (b if a is None else a.float() + b.float())
+            return t.float().reshape(1).contiguous()
+
+        s_cls = factor(g_total, g_cls)
+        s_box = factor(g_total, None if (g_box is None or w == 0) else g_box.float() / w)
         with torch.cuda.device(dev):
             for bufs, sc in ((ctx.gcls, s_cls), (ctx.gbox, s_box)):
                 for lo in range(0, len(bufs), 16):
