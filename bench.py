@@ -149,7 +149,7 @@ def run_ours(args):
     from ood_object_detection_b200 import _lib
     from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
     from ood_object_detection_b200.loss import loss_fn_fused
-    from ood_object_detection_b200.distributed import (LossReducePipeline, all_reduce_partial_sums,
+    from ood_object_detection_b200.distributed import (PeerMailbox, all_reduce_partial_sums,
                                                        forward_losses_one_collective, local_partial_sums)
 
     rank = int(os.environ.get('RANK', '0'))
@@ -179,38 +179,42 @@ def run_ours(args):
     unit = torch.ones((1,), dtype=torch.float32, device=dev)
 
     def compute():
-        """Our kernels for one batch: labeler -> fused loss (N > 1: partial sums against a unit normaliser,
-        both kernels writing into one 4-float buffer, so nothing else runs between them)."""
+        """Our kernels for one batch: labeler -> fused loss.  N > 1: partial sums against a unit normaliser,
+        both kernels writing into one 4-float buffer; with peer mailboxes the loss kernel's finishing CTA also
+        trades them with the other ranks, so the launch sequence is the same as on one GPU."""
         if world > 1:
-            return local_partial_sums(labeler, cls_out, box_out, gt_boxes, gt_cls, unit, **LOSS_KW), None
+            return local_partial_sums(labeler, cls_out, box_out, gt_boxes, gt_cls, unit, mailbox=mailbox, **LOSS_KW), None
         lb = labeler.assign(gt_boxes, gt_cls)
         return loss_fn_fused(cls_out, box_out, lb, **LOSS_KW), lb.num_positives
 
-    reducer = LossReducePipeline(dev) if world > 1 else None
-
-    def finish(out, npos):
-        """N > 1: ONE all-reduce of 4 floats, divided by the global (num_positives + 1) afterwards, all of it
-        on a side stream and collected one step later, so it overlaps the next step's kernels (the loss
-        values are only logged, nothing waits on them).  Returns (losses, event guarding `out`'s reuse)."""
-        if world > 1:
-            done = reducer.submit(out)
-            if len(reducer) > 1:
-                return reducer.collect()[0], done
-            return None, done
-        return out, None
-
+    # N > 1: the only exchange is 4 floats per rank and step.  Preferred: remote stores into peer mailboxes
+    # over NVLink (no collective kernel, ranks not in lockstep); fallback: one NCCL all-reduce.
+    mailbox, exchange = None, 'none'
+    if world > 1:
+        ok, why = 1, ''
+        if args.no_peer:
+            ok, why = 0, 'disabled by --no-peer'
+        else:
+            try:
+                mailbox = PeerMailbox(dev)
+            except Exception as exc:
+                ok, why = 0, f'{type(exc).__name__}: {exc}'
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            mailbox = None
+        exchange = ('peer mailboxes over NVLink, written by the loss kernel (odk_loss_params.exchange)' if mailbox is not None
+                    else f'nccl all-reduce of 4 floats ({why or "a peer could not map the mailboxes"})')
     def step():
-        return finish(*compute())[0]
-
-    def drain():
-        out = None
-        while reducer is not None and len(reducer):
-            out, done = reducer.collect()
-            torch.cuda.current_stream().wait_event(done)
-        return out
+        """One eager step through the public API (warm-up and the untimed clock-sampling load)."""
+        out, _ = compute()
+        if world == 1:
+            return out
+        if mailbox is not None:
+            return mailbox.previous()     # global sums of the step before (this step's are on the wire)
+        return all_reduce_partial_sums(out)
 
     def sync_all():
-        drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -224,9 +228,10 @@ def run_ours(args):
         # The compute part of a step is a fixed launch sequence (memsets, our kernels, tiny torch kernels):
         # it is captured once into a CUDA graph and replayed, so the timed region measures the GPU, not the
         # python launch path.  The NCCL all-reduce (N > 1) stays outside the graph.
-        # N > 1: the all-reduce is captured too, software-pipelined: graph k = [our kernels -> bufs[k]] in
-        # parallel with [all-reduce + normalise bufs[1-k], filled by the previous replay], so a step costs
-        # the host one graph launch and the collective never sits between two steps' kernels.
+        # N > 1: the exchange is captured too, software-pipelined -- a replay collects the PREVIOUS step's
+        # global sums while this step's kernels run, so a step costs the host one graph launch:
+        #   mailboxes: one graph  = [labeler -> loss], whose last CTA collects(previous) and publishes(current);
+        #   nccl     : two graphs = [all-reduce bufs[1-k]] || [labeler], join, [loss -> bufs[k]].
         graphs, graph_outs, mode = [], [], 'eager'
         bufs = [torch.zeros((4,), dtype=torch.float32, device=dev) for _ in range(2)]
         if not args.no_graph:
@@ -235,25 +240,28 @@ def run_ours(args):
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
                     compute()
-                    for k in range(2 if world > 1 else 1):
+                    for k in range(2 if (world > 1 and mailbox is None) else 1):
                         gr = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(gr, stream=side):
-                            if world > 1:
+                            if world == 1 or mailbox is not None:
+                                graph_outs.append(compute()[0])
+                            else:
                                 aux.wait_stream(side)                      # fork
                                 with torch.cuda.stream(aux):
                                     reduced = all_reduce_partial_sums(bufs[1 - k], copy=False)
-                                local_partial_sums(labeler, cls_out, box_out, gt_boxes, gt_cls, unit, buf=bufs[k], **LOSS_KW)
-                                side.wait_stream(aux)                      # join
+                                lb = labeler.assign(gt_boxes, gt_cls, normalizer_out=bufs[k][3:4])
+                                # join BEFORE the loss: its persistent grid fills every SM, so a collective
+                                # kernel still resident would hold one of its CTAs back for the whole pass
+                                side.wait_stream(aux)
+                                loss_fn_fused(cls_out, box_out, lb, normalizer=unit, out=bufs[k], **LOSS_KW)
                                 graph_outs.append(reduced)
-                            else:
-                                graph_outs.append(compute()[0])
                         graphs.append(gr)
                 torch.cuda.current_stream().wait_stream(side)
                 for _ in range(3):
                     for gr in graphs:
                         gr.replay()
                 torch.cuda.synchronize()
-                mode = 'cuda_graph' if world == 1 else 'cuda_graph (kernels + pipelined all-reduce)'
+                mode = 'cuda_graph' if world == 1 else 'cuda_graph (kernels + pipelined exchange)'
             except Exception as exc:  # capture is an optimisation, never a requirement
                 graphs, mode = [], f'eager (graph capture failed: {type(exc).__name__})'
                 torch.cuda.synchronize()
@@ -265,20 +273,21 @@ def run_ours(args):
         if graphs:
             for i in range(args.steps):
                 graphs[i % len(graphs)].replay()
-            if world > 1:   # the last step's partial sums are still local: reduce them now, inside the timed region
-                last = all_reduce_partial_sums(bufs[(args.steps - 1) % 2])
-            else:
+            if world == 1:
                 last = graph_outs[0]
+            elif mailbox is not None:   # the last step's record is still in the mailboxes: inside the timed region
+                last = mailbox.collect()[0]
+            else:
+                last = all_reduce_partial_sums(bufs[(args.steps - 1) % 2])
         else:
             for i in range(args.steps):
-                out = step()
-                last = out if out is not None else last
-            if world > 1:
-                last = drain() or last   # the timed region ends after the last collective (drain waits on it)
+                last = step()
         t_end.record()
         sync_all()
         total_ms = t_start.elapsed_time(t_end)
         if world > 1:
+            if mailbox is not None and int(mailbox.status.item()) != 0:
+                raise RuntimeError('peer mailbox exchange timed out: a rank did not publish its partial sums')
             # graphs that hold NCCL kernels must be gone before the process group is torn down
             last = [float(x) for x in last]
             graphs.clear()
@@ -397,7 +406,7 @@ def run_ours(args):
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': world * BATCH, 'parallelism': f'images sharded x{world}',
-                       'launch': mode,
+                       'launch': mode, 'exchange': exchange,
                        'l2': 'inputs (1.18 GB/step) larger than the 126 MB L2; no flush needed',
                        'loss_out': [float(x) for x in last]},
             'roofline': {'bound': 'hbm', 'kernel': 'odk::loss_kernel_ring<new,fwd,fused>', 'achieved': achieved, 'peak': peak,
@@ -478,6 +487,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-extra', action='store_true', help='skip the D3 post-process extra block')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-peer', action='store_true', help='N > 1: exchange the loss partial sums with an NCCL all-reduce instead of peer mailboxes')
     ap.add_argument('--no-graph', action='store_true', help='launch the timed steps eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define ODK_MAX_LEVELS 8
-#define ODK_VERSION 1
+#define ODK_VERSION 2
 
 /* error codes */
 #define ODK_OK 0
@@ -109,6 +109,19 @@ int odk_targets(const float *anchors, const float *gt_boxes, const int32_t *gt_l
  *   inputs) receiving d total / d input, or NULL for forward only.
  * Workspace: odk_loss_workspace_bytes().
  */
+#define ODK_MAILBOX_MAX_WORLD 32
+/* Optional fused exchange of the loss partial sums between data-parallel ranks (see the mailbox
+ * section below): the CTA of odk_loss that finishes the reduction first collects the record set
+ * of the PREVIOUS step if one is outstanding (-> global_out3, status), then stores this launch's
+ * {out[0], out[1], out[2], *num_pos_plus_1} into every rank's mailbox.  Use with a unit normaliser. */
+typedef struct odk_exchange {
+    void *mailboxes[ODK_MAILBOX_MAX_WORLD]; /* device pointers to every rank's mailbox; entry `rank` is local */
+    int32_t world, rank;
+    const float *num_pos_plus_1;  /* device: this rank's sum(num_positives) + 1 (odk_assign_grid's `normalizer`) */
+    float *global_out3;           /* device: {total, cls_loss, box_loss} of the previous step's GLOBAL batch */
+    int32_t *status;              /* device: 0, or 1 if a peer's record did not arrive in time */
+} odk_exchange;
+
 typedef struct odk_loss_params {
     float alpha;
     float gamma;
@@ -117,6 +130,7 @@ typedef struct odk_loss_params {
     float label_smoothing;
     int32_t legacy_focal;
     int32_t match_is_key64;   /* `match` points at odk_assign_grid's 64-bit keys instead of int32 rows */
+    const odk_exchange *exchange;   /* NULL = no exchange (HOST pointer, read during the call) */
 } odk_loss_params;
 
 size_t odk_loss_workspace_bytes(void);
@@ -132,6 +146,28 @@ int odk_scale_inplace(float *buf, int64_t n, const float *scale, void *stream);
 /* Same for up to ODK_SCALE_MAX separate buffers in ONE launch (bufs / sizes: HOST arrays). */
 #define ODK_SCALE_MAX 16
 int odk_scale_inplace_multi(void *const *bufs, const int64_t *sizes, int count, const float *scale, void *stream);
+
+/* ---- data-parallel loss partial sums over peer memory --------------------------------------
+ * The only exchange of the sharded path (the reference's counterpart is the
+ * all-reduce of its loss scalars, effdet/distributed.py reduce_tensor): every rank owns a MAILBOX
+ * of odk_mailbox_bytes(world) device bytes that all peers can write (CUDA VMM / IPC mapping, e.g.
+ * torch symmetric memory), zero-filled once before first use.
+ *   odk_partials_publish: stores this rank's 4 floats {cls + w*box, cls, box, sum(num_pos) + 1}
+ *     (what odk_assign_grid + odk_loss leave in one buffer against a unit normaliser) into slot
+ *     (seq & 1, rank) of EVERY rank's mailbox with release semantics; seq is a device-side counter
+ *     in the local mailbox, so the call can be replayed from a CUDA graph.  mailboxes: HOST array
+ *     of `world` device pointers (entry `rank` is the local mailbox).  No waiting.
+ *   odk_partials_collect: waits (bounded spin) until all `world` records of the next sequence
+ *     number are in the LOCAL mailbox, sums them in rank order (deterministic) and writes
+ *     out3 = {total, cls_loss, box_loss} of the global batch (sums / (sum(num_pos) + 1), loss.py:261,297);
+ *     *status = 0, or 1 if a peer's record did not arrive in time (out3 is then unspecified).
+ * Every rank must alternate collect(j-1) ... publish(j) in stream order (that ordering is the flow
+ * control that makes two slots enough) and publish once before its first collect.
+ * odk_loss with odk_loss_params.exchange does both inside the loss kernel (collect(j-1) when a record
+ * is outstanding, then publish(j)); odk_partials_collect then only drains the last step. */
+size_t odk_mailbox_bytes(int world);
+int odk_partials_publish(const float *partials4, void *const *mailboxes, int world, int rank, void *stream);
+int odk_partials_collect(void *mailbox_local, int world, float *out3, int32_t *status, void *stream);
 
 /* ---- post-process: top-k -------------------------------------------------------------------
  * Replaces _post_process (bench.py:12-56): concat/permute of the levels, torch.topk over

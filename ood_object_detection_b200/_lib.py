@@ -16,9 +16,19 @@ c_void_p, c_int, c_int64, c_float, c_double, c_size_t = (
     ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_size_t)
 
 
+MAILBOX_MAX_WORLD = 32
+
+
+class Exchange(ctypes.Structure):
+    """odk_exchange (include/odk.h): fused peer-mailbox exchange of the loss partial sums."""
+    _fields_ = [('mailboxes', c_void_p * MAILBOX_MAX_WORLD), ('world', ctypes.c_int32), ('rank', ctypes.c_int32),
+                ('num_pos_plus_1', c_void_p), ('global_out3', c_void_p), ('status', c_void_p)]
+
+
 class LossParams(ctypes.Structure):
     _fields_ = [('alpha', c_float), ('gamma', c_float), ('delta', c_float), ('box_loss_weight', c_float),
-                ('label_smoothing', c_float), ('legacy_focal', ctypes.c_int32), ('match_is_key64', ctypes.c_int32)]
+                ('label_smoothing', c_float), ('legacy_focal', ctypes.c_int32), ('match_is_key64', ctypes.c_int32),
+                ('exchange', ctypes.POINTER(Exchange))]
 
 
 class DetectParams(ctypes.Structure):
@@ -44,6 +54,9 @@ SIGNATURES = {
                          ctypes.POINTER(LossParams), _P, _P, _P, _P, c_size_t, _P]),
     'odk_scale_inplace': (c_int, [_P, c_int64, _P, _P]),
     'odk_scale_inplace_multi': (c_int, [_P, _P, c_int, _P, _P]),
+    'odk_mailbox_bytes': (c_size_t, [c_int]),
+    'odk_partials_publish': (c_int, [_P, _P, c_int, c_int, _P]),
+    'odk_partials_collect': (c_int, [_P, c_int, _P, _P, _P]),
     'odk_topk_workspace_bytes': (c_size_t, [c_int, c_int]),
     'odk_topk': (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     'odk_detect': (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int64, _P, _P, ctypes.POINTER(DetectParams), _P, _P, _P,
@@ -68,7 +81,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the library does not export the symbol
             fn.restype = res
             fn.argtypes = args
-        if handle.odk_version() != 1:
+        if handle.odk_version() != 2:
             raise RuntimeError('libodk.so ABI version mismatch')
         _LIB = handle
     return _LIB

@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include "odk_common.cuh"
+#include "odk_exchange.cuh"
 
 namespace odk {
 
@@ -64,6 +65,12 @@ struct LossArgs {
     int part_total;       // slots the finishing launch sums (0: this launch does not finish)
     unsigned *counter;
     float *out;
+    // optional fused exchange of the partial sums with the other data-parallel ranks (xworld == 0: off)
+    Mailboxes xmb;
+    int xworld, xrank;
+    const float *xnpos;
+    float *xout;
+    int *xstatus;
 };
 
 // ---- element math ----------------------------------------------------------------------------
@@ -378,6 +385,7 @@ __device__ __forceinline__ void loss_item(const LossArgs &A, int l, unsigned loc
 __device__ __forceinline__ void finish_block(const LossArgs &A, float csum, float bsum, float nrm) {
     __shared__ double s_c[kLossThreads / 32], s_b[kLossThreads / 32];
     __shared__ bool s_last;
+    __shared__ float4 s_mine, s_recv[ODK_MAILBOX_MAX_WORLD];
     double dc = warp_sum((double)csum), db = warp_sum((double)bsum);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) { s_c[warp] = dc; s_b[warp] = db; }
@@ -412,6 +420,19 @@ __device__ __forceinline__ void finish_block(const LossArgs &A, float csum, floa
             A.out[2] = box_loss;
             A.out[0] = cls_loss + A.p.box_loss_weight * box_loss;         // loss.py:297
             *A.counter = 0;                                                 // ready for the next call
+            s_mine = make_float4(cls_loss + A.p.box_loss_weight * box_loss, cls_loss, box_loss, 0.f);
+        }
+        if (A.xworld > 0) {
+            // fused exchange: first collect the previous step's record set if one is outstanding (it landed
+            // a whole step ago), then store this step's sums into every rank's mailbox over NVLink
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                unsigned *ctr = mailbox_counters(A.xmb.p[A.xrank], A.xworld);
+                if (ctr[0] > ctr[1]) collect_records(A.xmb.p[A.xrank], A.xworld, s_recv, A.xout, A.xstatus);
+                float4 v = s_mine;
+                v.w = __ldg(A.xnpos);
+                publish_record(A.xmb, A.xworld, A.xrank, v);
+            }
         }
     }
 }
@@ -663,6 +684,18 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
     }
     a.match = match; a.anchors = (const float4 *)anchors; a.gt_boxes = (const float4 *)gt_boxes; a.gt_labels = gt_labels;
     a.cls_t = cls_targets; a.box_t = box_targets; a.normalizer = normalizer; a.p = *params; a.out = out;
+    a.xworld = 0;
+    if (params->exchange) {
+        const odk_exchange *x = params->exchange;
+        if (x->world < 1 || x->world > ODK_MAILBOX_MAX_WORLD || x->rank < 0 || x->rank >= x->world)
+            return set_error(ODK_EINVAL, "odk_loss: exchange needs 1 <= world <= %d and 0 <= rank < world", ODK_MAILBOX_MAX_WORLD);
+        if (!x->num_pos_plus_1 || !x->global_out3 || !x->status) return set_error(ODK_EINVAL, "odk_loss: exchange has a null pointer");
+        for (int r = 0; r < x->world; ++r) {
+            if (!x->mailboxes[r] || ((uintptr_t)x->mailboxes[r] & 15)) return set_error(ODK_EINVAL, "odk_loss: bad mailbox pointer %d", r);
+            a.xmb.p[r] = (unsigned char *)x->mailboxes[r];
+        }
+        a.xworld = x->world; a.xrank = x->rank; a.xnpos = x->num_pos_plus_1; a.xout = x->global_out3; a.xstatus = x->status;
+    }
     a.partials = (double *)workspace;
     a.counter = (unsigned *)((char *)workspace + (size_t)kMaxPartials * 2 * sizeof(double));
 

@@ -89,16 +89,18 @@ class PendingPartialSums:
         return res[0], res[1], res[2]
 
 
-def local_partial_sums(labeler, cls_outputs, box_outputs, gt_boxes, gt_classes, unit, buf=None, **loss_kw):
+def local_partial_sums(labeler, cls_outputs, box_outputs, gt_boxes, gt_classes, unit, buf=None, mailbox=None, **loss_kw):
     """This rank's share of the forward loss with no torch kernel in between: the labeler writes
     sum(num_positives) + 1 into slot 3 of one 4-float buffer (``buf``, allocated when None) and the
     fused loss (against the unit normaliser ``unit``) writes [cls + w * box, cls, box] partial sums
-    into slots 0..2."""
+    into slots 0..2.  With ``mailbox`` (a ``PeerMailbox``) the loss kernel itself trades the four floats
+    with the other ranks: no collective, no further launch."""
     from .loss import loss_fn_fused
     if buf is None:
         buf = torch.empty((4,), dtype=torch.float32, device=gt_boxes.device)
     lb = labeler.assign(gt_boxes, gt_classes, normalizer_out=buf[3:4])
-    loss_fn_fused(cls_outputs, box_outputs, lb, normalizer=unit, out=buf, **loss_kw)
+    loss_fn_fused(cls_outputs, box_outputs, lb, normalizer=unit, out=buf,
+                  exchange=None if mailbox is None else mailbox.attach(buf[3:4]), **loss_kw)
     return buf
 
 
@@ -106,7 +108,8 @@ def all_reduce_partial_sums(buf, group=None, async_op=False, copy=True):
     """ONE all-reduce of the 4 floats of ``local_partial_sums``; returns (total, cls, box) of the GLOBAL
     batch (or a ``PendingPartialSums``).  With ``copy`` the buffer is cloned first, so the caller may
     overwrite it right away (the next CUDA-graph replay does) while the collective is still in flight;
-    ``copy=False`` reduces in place (see ``LossReducePipeline`` for the ordering that makes that safe)."""
+    ``copy=False`` reduces in place (the caller orders the next write after the collective, as bench.py's
+    alternating CUDA graphs do)."""
     packed = buf.detach().clone() if copy else buf.detach()
     world, work = 1, None
     if _active(group):
@@ -116,37 +119,94 @@ def all_reduce_partial_sums(buf, group=None, async_op=False, copy=True):
     return pending if async_op else pending.result()
 
 
-class LossReducePipeline:
-    """Keeps the per-step collective and its bookkeeping OFF the compute stream.
+class PeerMailbox:
+    """The loss partial sums over NVLink peer memory instead of a collective (include/odk.h,
+    ``odk_partials_publish`` / ``odk_partials_collect``): ``publish(buf4)`` stores this rank's 4 floats into
+    every rank's mailbox and returns at once; ``collect()`` (one step later, every rank) sums the records
+    in rank order and returns (total, cls, box) of the global batch plus a status flag.  Both are single
+    tiny kernels with device-side sequence counters, so they can be captured in a CUDA graph.  No
+    collective kernel sits on an SM while the persistent loss grid runs, and ranks are coupled with one
+    step of slack instead of in lockstep.
 
-    ``submit(buf)`` (called on the compute stream right after the kernels that fill ``buf``) records an
-    event and, on a side stream, waits for it, all-reduces ``buf`` in place and normalises.  The compute
-    stream never waits for the collective: it only has to wait for the returned ``done`` event before
-    the same ``buf`` is written again (two alternating buffers / CUDA graphs make that wait free).
-    ``collect()`` returns the oldest (total, cls, box) -- tensors produced on the side stream -- and its
-    ``done`` event; synchronise on it (or the device) before reading them elsewhere."""
+    The mailboxes are torch symmetric memory (CUDA VMM handles exchanged through the process group's
+    store); ``world == 1`` (or ``local_only``) uses plain device memory.  Raises when symmetric memory
+    cannot be set up -- callers fall back to ``all_reduce_partial_sums`` (NCCL)."""
 
-    def __init__(self, device, group=None):
-        self.group = group
-        self.side = torch.cuda.Stream(device=device)
-        self.pending = []
+    def __init__(self, device, group=None, local_only=False):
+        from . import _lib
+        self._lib = _lib
+        lib = _lib.lib()
+        self.device = torch.device(device)
+        active = _active(group) and not local_only
+        self.world = dist.get_world_size(group) if active else 1
+        self.rank = dist.get_rank(group) if active else 0
+        nbytes = int(lib.odk_mailbox_bytes(self.world))
+        if nbytes == 0:
+            raise ValueError(f'world size {self.world} not supported by the mailbox exchange')
+        if active:
+            import torch.distributed._symmetric_memory as symm
+            grp = group if group is not None else dist.group.WORLD
+            enable = getattr(symm, 'enable_symm_mem_for_group', None)
+            if enable is not None:
+                try:
+                    enable(grp.group_name)
+                except Exception:   # newer torch: implicit, the call is deprecated
+                    pass
+            self.buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.buf.zero_()
+            self.handle = symm.rendezvous(self.buf, grp)
+            ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group)          # every mailbox is zero before anybody publishes
+        else:
+            self.buf = torch.zeros((nbytes,), dtype=torch.uint8, device=self.device)
+            self.handle = None
+            ptrs = [self.buf.data_ptr()]
+        self._ptrs = (_lib.ctypes.c_void_p * self.world)(*ptrs)
+        self._ptr_list = ptrs
+        self.published = self.collected = 0
+        self.out3 = torch.zeros((3,), dtype=torch.float32, device=self.device)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=self.device)
 
-    def submit(self, buf):
-        ready = torch.cuda.Event()
-        ready.record()
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(ready)
-            res = all_reduce_partial_sums(buf, self.group, async_op=True, copy=False).result()
-            done = torch.cuda.Event()
-            done.record(self.side)
-        self.pending.append((res, done))
-        return done
+    def attach(self, num_pos_plus_1):
+        """Descriptor for ``loss_fn_fused(..., exchange=...)``: the loss kernel's finishing CTA collects the
+        previous step's records into ``self.out3`` / ``self.status`` (when one is outstanding) and publishes
+        its own sums together with ``num_pos_plus_1`` (float32 [1], what the labeler wrote)."""
+        _lib = self._lib
+        if num_pos_plus_1.dtype != torch.float32 or num_pos_plus_1.numel() != 1 or num_pos_plus_1.device != self.device:
+            raise ValueError('num_pos_plus_1 must be one float32 element on the mailbox device')
+        x = _lib.Exchange()
+        for r, p in enumerate(self._ptr_list):
+            x.mailboxes[r] = p
+        x.world, x.rank = self.world, self.rank
+        x.num_pos_plus_1 = num_pos_plus_1.data_ptr()
+        x.global_out3, x.status = self.out3.data_ptr(), self.status.data_ptr()
+        self._keep = (x, num_pos_plus_1)
+        return x
 
-    def collect(self):
-        return self.pending.pop(0)
+    def previous(self):
+        """(total, cls, box) of the last step a fused launch or ``collect()`` has collected."""
+        return self.out3[0], self.out3[1], self.out3[2]
 
-    def __len__(self):
-        return len(self.pending)
+    def publish(self, buf4):
+        if buf4.dtype != torch.float32 or buf4.numel() < 4 or not buf4.is_contiguous() or buf4.device != self.device:
+            raise ValueError('publish needs a contiguous float32 [4] tensor on the mailbox device')
+        _lib = self._lib
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().odk_partials_publish(_lib.ptr(buf4), self._ptrs, self.world, self.rank,
+                                                       _lib.stream_ptr(self.device)))
+        self.published += 1
+
+    def collect(self, out=None, status=None):
+        """-> ((total, cls, box) views of ``out``, status int32 [1]: 0 ok, 1 a peer's record never arrived)."""
+        _lib = self._lib
+        out = self.out3 if out is None else out
+        status = self.status if status is None else status
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().odk_partials_collect(_lib.ptr(self.buf), self.world, _lib.ptr(out), _lib.ptr(status),
+                                                       _lib.stream_ptr(self.device)))
+        self.collected += 1
+        return (out[0], out[1], out[2]), status
 
 
 def sharded_detection_loss(loss_module, cls_outputs, box_outputs, label_batch, group=None):

@@ -80,8 +80,10 @@ class _DetectionLossFn(torch.autograd.Function):
             gcls_p, gbox_p = _lib.ptr_array(gcls), _lib.ptr_array(gbox)
         fused = meta.get('label_batch')
         use_keys = fused is not None and fused.keys is not None
+        exchange = meta.get('exchange')   # distributed.PeerMailbox.attach(...) descriptor, or None
         params = _lib.LossParams(meta['alpha'], meta['gamma'], meta['delta'], meta['box_loss_weight'],
-                                 meta['label_smoothing'], int(bool(meta['legacy_focal'])), int(use_keys))
+                                 meta['label_smoothing'], int(bool(meta['legacy_focal'])), int(use_keys),
+                                 _lib.ctypes.pointer(exchange) if exchange is not None else None)
         if fused is not None:
             match = fused.keys if use_keys else fused.match
             anchors, gtb, gtl = fused.labeler.anchors.boxes, fused.gt_boxes, fused.gt_labels
@@ -174,16 +176,18 @@ def loss_fn(
 
 def loss_fn_fused(cls_outputs, box_outputs, label_batch, num_classes: int, alpha: float, gamma: float, delta: float,
                   box_loss_weight: float, label_smoothing: float = 0., legacy_focal: bool = False,
-                  normalizer: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+                  normalizer: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, exchange=None):
     """Same value as ``loss_fn(.., *labeler.batch_label_anchors(..))`` without ever materialising
     the target tensors: ``label_batch`` is ``AnchorLabeler.assign(...)``.  ``out`` (float32, >= 3
-    elements) receives [total, cls_loss, box_loss] in place; the returned scalars are views of it."""
+    elements) receives [total, cls_loss, box_loss] in place; the returned scalars are views of it.
+    ``exchange``: ``distributed.PeerMailbox.attach(...)`` -- the kernel also trades the partial sums with
+    the other data-parallel ranks (use with a unit ``normalizer``)."""
     if normalizer is None:
         normalizer = label_batch.normalizer if label_batch.normalizer is not None else _normalizer(label_batch.num_positives)
     meta = dict(levels=len(cls_outputs), num_classes=int(num_classes), alpha=float(alpha), gamma=float(gamma),
                 delta=float(delta), box_loss_weight=float(box_loss_weight), label_smoothing=float(label_smoothing),
                 legacy_focal=bool(legacy_focal), label_batch=label_batch,
-                normalizer=normalizer.float().reshape(1).contiguous(), out=out)
+                normalizer=normalizer.float().reshape(1).contiguous(), out=out, exchange=exchange)
     return _DetectionLossFn.apply(meta, *cls_outputs, *box_outputs)
 
 

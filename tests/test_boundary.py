@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, name), f'libodk.so does not export {name}'
     # and the python binding table covers exactly the header
     assert sorted(_lib.SIGNATURES) == syms
-    assert _lib.lib().odk_version() == 1
+    assert _lib.lib().odk_version() == 2
     assert _lib.lib().odk_planar_stride(49104) == 49104 and _lib.lib().odk_planar_stride(150381) == 150384
 
 

@@ -79,3 +79,74 @@ def test_partial_sums_buffer_equals_fused_loss(grid):
     assert float(buf[3]) == float(onp.sum()) + 1.0
     got = D.all_reduce_partial_sums(buf)      # single process: just the normalisation
     np.testing.assert_allclose([float(v) for v in got], ref, rtol=1e-5)
+
+
+def test_peer_mailbox_single_rank_sequences():
+    """odk_partials_publish / odk_partials_collect with world = 1 (the mailbox is local memory): the
+    alternating slots, the device-side sequence counters and the normalisation (loss.py:261,297)."""
+    from ood_object_detection_b200.distributed import PeerMailbox
+    mb = PeerMailbox(DEV, local_only=True)
+    for step in range(5):
+        vals = torch.tensor([10.0 + step, 4.0 + step, 0.12, 7.0 + step], device=DEV)   # slot 3 = sum(num_pos) + 1
+        mb.publish(vals)
+        (tot, cl, bx), status = mb.collect()
+        assert int(status) == 0
+        n = 7.0 + step
+        np.testing.assert_allclose([float(tot), float(cl), float(bx)], [(10.0 + step) / n, (4.0 + step) / n, 0.12 / n], rtol=1e-6)
+    # a collect with nothing published gives up (bounded spin) and says so instead of hanging the GPU
+    _, status = mb.collect()
+    assert int(status) == 1
+
+
+def test_peer_mailbox_in_cuda_graph():
+    """collect(previous) || kernels -> publish(current), replayed from one graph (what bench.py does at N > 1)."""
+    from ood_object_detection_b200.distributed import PeerMailbox
+    mb = PeerMailbox(DEV, local_only=True)
+    src = torch.zeros(4, device=DEV)
+    out, status = torch.zeros(3, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+    src.copy_(torch.tensor([2.0, 1.0, 0.5, 2.0]))
+    mb.publish(src)                      # prime: one record outstanding
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            mb.collect(out=out, status=status)
+            src.mul_(2.0)                # stands for the step's kernels
+            mb.publish(src)
+    torch.cuda.current_stream().wait_stream(side)
+    expect = [2.0, 1.0, 0.5, 2.0]
+    for _ in range(4):
+        g.replay()
+        torch.cuda.synchronize()
+        assert int(status) == 0
+        np.testing.assert_allclose(out.cpu().numpy(), np.array(expect[:3]) / expect[3], rtol=1e-6)
+        expect = [2 * v for v in expect]
+
+
+def test_loss_kernel_fused_exchange_single_rank():
+    """odk_loss_params.exchange: the loss kernel's finishing CTA publishes its sums and collects the previous
+    step's; with world = 1 the collected value must be the ordinary (normalised) loss of that step."""
+    from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
+    from ood_object_detection_b200 import distributed as D
+    size, B, C, M = 256, 4, 20, 6
+    anc = Anchors(3, 7, 3, synth.ASPECTS, 4.0, (size, size)).to(DEV)
+    lab = AnchorLabeler(anc, C)
+    kw = dict(num_classes=C, alpha=0.25, gamma=1.5, delta=0.1, box_loss_weight=50.0)
+    unit = torch.ones((1,), device=DEV)
+    mb = D.PeerMailbox(DEV, local_only=True)
+    fhw = synth.feat_hw(size)
+    refs = []
+    for step in range(3):
+        gb, gc = synth.gt_boxes(40 + step, B, size, M, C)
+        co, bo = synth.head_outputs(50 + step, B, size, C, tie_free=False)
+        D.local_partial_sums(lab, [torch.from_numpy(x).to(DEV) for x in co], [torch.from_numpy(x).to(DEV) for x in bo],
+                             torch.from_numpy(gb).to(DEV), torch.from_numpy(gc).to(DEV), unit, mailbox=mb, **kw)
+        oc, ob, onp, _, _ = orc.batch_label_anchors(anc.boxes.cpu().numpy(), list(gb), list(gc))
+        refs.append(orc.loss_fn(co, bo, orc.split_levels(oc, fhw), orc.split_levels(ob, fhw), onp, C, 0.25, 1.5, 0.1, 50.0))
+        if step > 0:   # the launch of this step collected the sums of the previous one
+            assert int(mb.status) == 0
+            np.testing.assert_allclose([float(v) for v in mb.previous()], refs[step - 1], rtol=1e-5)
+    got, status = mb.collect()     # drain: the last step's record
+    assert int(status) == 0
+    np.testing.assert_allclose([float(v) for v in got], refs[-1], rtol=1e-5)
