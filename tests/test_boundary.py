@@ -139,3 +139,22 @@ def test_matcher_and_coder_tensor_paths():
     np.testing.assert_allclose(dec.numpy(), gb[0][om[0][pos]], rtol=1e-4, atol=1e-3)
     with pytest.raises(ValueError):
         ArgMaxMatcher(0.4, 0.5)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The ctypes mirrors of the by-pointer parameter structs must have the C compiler's layout."""
+    import ctypes
+    import subprocess
+    from ood_object_detection_b200 import _lib
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "odk.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(odk_loss_params), '
+                   'offsetof(odk_loss_params, exchange), sizeof(odk_exchange), offsetof(odk_exchange, world), '
+                   'offsetof(odk_exchange, num_pos_plus_1), offsetof(odk_exchange, status), sizeof(odk_detect_params)); return 0; }\n')
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), '-o', str(exe), str(src)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(_lib.LossParams), _lib.LossParams.exchange.offset, ctypes.sizeof(_lib.Exchange),
+            _lib.Exchange.world.offset, _lib.Exchange.num_pos_plus_1.offset, _lib.Exchange.status.offset,
+            ctypes.sizeof(_lib.DetectParams)]
+    assert got == want
