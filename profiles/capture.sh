@@ -14,4 +14,5 @@ ncu --set full --clock-control none --import-source on -k regex:'loss_kernel' -s
 python profiles/pp_profile.py d3 32 3 > gpurun_out/${T}_pp_plain.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:'topk_|detect_kernel' -s 10 -c 5 -f \
     -o gpurun_out/${T}_pp python profiles/pp_profile.py d3 32 3 > gpurun_out/${T}_ncu_pp.log 2>&1
-tail -2 gpurun_out/${T}_train_plain.log gpurun_out/${T}_pp_plain.log
+python profiles/run_configs.py > gpurun_out/${T}_configs.log 2> gpurun_out/${T}_configs.err
+tail -n 3 gpurun_out/${T}_train_plain.log gpurun_out/${T}_pp_plain.log gpurun_out/${T}_configs.log
