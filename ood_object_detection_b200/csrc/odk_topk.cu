@@ -368,7 +368,8 @@ __device__ void block_sort_desc(unsigned long long *s) {
 
 template <int E>
 __device__ __forceinline__ unsigned long long sorted_at(const unsigned long long *s, int q) {
-    return s[(q % E) * kSelThreads + q / E];
+    if (E == 0) return s[q];   // linear (bucket-rank path)
+    return s[(q % (E ? E : 1)) * kSelThreads + q / (E ? E : 1)];
 }
 
 template <int E>
@@ -407,74 +408,178 @@ __device__ void emit_topk(const TopkArgs &A, int b, const unsigned long long *s)
     }
 }
 
-// Cut n <= kCap candidates down to just over K before sorting: a 1024-bin histogram on the value-key
-// bits below the collect threshold finds the finest edge T with count(key >= T) >= K; everything
-// below T cannot be in the top K.  Survivors are compacted (order is irrelevant: they are sorted next)
-// so the sort always runs on 8192 slots.  Returns the new count.
+// Cut n <= kCap candidates down to just over K and order them: a 1024-bin histogram on the value-key
+// bits below the collect threshold finds the finest edge T with count(key >= T) >= K; everything below T
+// cannot be in the top K.  The histogram is also a counting sort: the suffix sums give every sub-bin its
+// first rank, survivors are scattered to their sub-bin's range and ranked inside it by direct comparison
+// (a handful of mates per sub-bin on real score distributions), which replaces a 91-stage bitonic sort of
+// 8192 keys.  Heavily tied inputs (a sub-bin with more than kBucketMax keys, or more than 8192 survivors)
+// take the bitonic path instead.
 constexpr int kRefineBins = 1024;
 constexpr int kRefineShift = 14;   // sub-bin = 2^14 key units: 64 sub-bins per 12-bit threshold bin
+constexpr int kBucketMax = 512;    // largest sub-bin the direct ranking accepts
+constexpr int kSortSlots = 8 * kSelThreads;
 
-__device__ int refine_candidates(const TopkArgs &A, int b, int n, unsigned long long *s) {
-    __shared__ unsigned s_rh[kRefineBins];
-    __shared__ unsigned s_edge, s_cnt;
+struct Refined { int m; bool ranked; };   // survivors; ranked: s[kSortSlots + q] is the q-th largest key
+
+// one warp: per-bin first ranks from the top bin down (s_start), stops at the first bin where the running
+// count reaches `need` (returns that bin and the count through lane-uniform values); tracks the largest bin
+__device__ __forceinline__ void suffix_scan(const unsigned *hist, unsigned *start, unsigned need, unsigned first_rank,
+                                            unsigned &edge, unsigned &total, unsigned &biggest, int skip_bin) {
+    const int lane = threadIdx.x & 31;
+    unsigned run = first_rank, big = 0;
+    edge = 0u; total = 0u;
+    for (int c = kRefineBins / 32 - 1; c >= 0; --c) {
+        const int bin = c * 32 + (31 - lane);   // lane 0 holds the highest bin of the chunk
+        const unsigned v = hist[bin];
+        unsigned inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        start[bin] = run + inc - v;   // keys in higher bins = first rank of this one
+        const unsigned hit = __ballot_sync(0xffffffffu, run + inc - first_rank >= need);
+        if (hit) {
+            const int ln = __ffs(hit) - 1;
+            if (lane <= ln && bin != skip_bin) big = max(big, v);
+            edge = (unsigned)__shfl_sync(0xffffffffu, bin, ln);
+            total = __shfl_sync(0xffffffffu, run + inc, ln) - first_rank;
+            break;
+        }
+        if (bin != skip_bin) big = max(big, v);
+        run += __shfl_sync(0xffffffffu, inc, 31);
+        if (c == 0) total = run - first_rank;
+    }
+    biggest = __reduce_max_sync(0xffffffffu, big);
+}
+
+__device__ Refined refine_candidates(const TopkArgs &A, int b, int n, unsigned long long *s) {
+    __shared__ unsigned s_rh[kRefineBins], s_start[kRefineBins], s_fill[kRefineBins];
+    __shared__ unsigned s_rh2[kRefineBins], s_start2[kRefineBins], s_fill2[kRefineBins];
+    __shared__ unsigned s_edge, s_cnt, s_maxbin, s_top, s_wmax[kSelThreads / 32];
     const int tid = threadIdx.x;
     const unsigned base = __ldcg(A.thr + b);   // every candidate key is >= base
     const unsigned long long *cand = A.cand + (size_t)b * kCap;
-    for (int i = tid; i < kRefineBins; i += blockDim.x) s_rh[i] = 0;
-    if (tid == 0) { s_edge = 0u; s_cnt = 0u; }
+    for (int i = tid; i < kRefineBins; i += blockDim.x) { s_rh[i] = 0; s_fill[i] = 0; s_rh2[i] = 0; s_fill2[i] = 0; }
+    if (tid == 0) { s_edge = 0u; s_cnt = 0u; s_maxbin = 0u; }
     __syncthreads();
     unsigned long long mine[kCap / kSelThreads];
+    auto bin_of = [&](unsigned long long key) {
+        return min(((unsigned)(key >> 32) - base) >> kRefineShift, (unsigned)kRefineBins - 1u);
+    };
+    constexpr unsigned kTopBin = kRefineBins - 1;   // also catches everything above the sub-bin range
+    unsigned vmax = 0u;
 #pragma unroll
     for (int k = 0; k < kCap / kSelThreads; ++k) {
         const int i = tid + k * kSelThreads;
         mine[k] = i < n ? __ldcg(cand + i) : 0ull;
         if (i < n) {
-            const unsigned d = ((unsigned)(mine[k] >> 32) - base) >> kRefineShift;
-            atomicAdd(&s_rh[min(d, (unsigned)kRefineBins - 1u)], 1u);
+            atomicAdd(&s_rh[bin_of(mine[k])], 1u);
+            vmax = max(vmax, (unsigned)(mine[k] >> 32));
         }
     }
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    if ((tid & 31) == 0) s_wmax[tid >> 5] = vmax;
     __syncthreads();
-    if (tid < 32) {   // one warp: suffix sums from the top sub-bin, first edge reaching K
-        unsigned run = 0;
-        for (int c = kRefineBins / 32 - 1; c >= 0; --c) {
-            const int bin = c * 32 + (31 - tid);   // lane 0 holds the highest bin of the chunk
-            const unsigned v = s_rh[bin];
-            unsigned inc = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (tid >= o) inc += t;
-            }
-            const unsigned hit = __ballot_sync(0xffffffffu, run + inc >= (unsigned)A.K);
-            if (hit) {
-                const int ln = __ffs(hit) - 1;
-                if (tid == ln) s_edge = (unsigned)bin;
-                break;
-            }
-            run += __shfl_sync(0xffffffffu, inc, 31);
-        }
+    if (tid < 32) {
+        unsigned edge, total, biggest;
+        suffix_scan(s_rh, s_start, (unsigned)A.K, 0u, edge, total, biggest, (int)kTopBin);
+        unsigned top = s_wmax[tid];
+        top = __reduce_max_sync(0xffffffffu, top);
+        if (tid == 0) { s_edge = edge; s_cnt = total; s_maxbin = biggest; s_top = top; }
     }
     __syncthreads();
     const unsigned edge = s_edge;   // keep sub-bins >= edge (edge 0: keep everything)
+    const int m = (int)s_cnt;       // survivors (>= K: the select kernel only runs with n >= K)
+    if (m > kSortSlots) return {m, false};
+    // The top sub-bin also holds every key above the sub-bin range (the strongest scores, often across the
+    // sign change where float bit patterns are sparse): it gets a second histogram that is linear in the VALUE
+    // between the sub-bin's lower edge and the largest candidate.
+    const float x_lo = val_of(base + (kTopBin << kRefineShift));
+    const float x_hi = val_of(s_top);
+    const float scale2 = x_hi > x_lo ? (float)(kRefineBins - 1) / (x_hi - x_lo) : 0.0f;
+    auto bin2_of = [&](unsigned long long key) {
+        const float t = (val_of((unsigned)(key >> 32)) - x_lo) * scale2;   // monotone in the key; NaN/inf -> 0
+        return (unsigned)min(max((int)t, 0), kRefineBins - 1);
+    };
+    const bool two_level = s_rh[kTopBin] > 32u;
+    if (two_level) {
+#pragma unroll
+        for (int k = 0; k < kCap / kSelThreads; ++k) {
+            const int i = tid + k * kSelThreads;
+            if (i < n && bin_of(mine[k]) == kTopBin) atomicAdd(&s_rh2[bin2_of(mine[k])], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            unsigned e2, t2, big2;
+            suffix_scan(s_rh2, s_start2, 0xFFFFFFFFu, 0u, e2, t2, big2, -1);   // the top sub-bin starts at rank 0
+            if (tid == 0) s_maxbin = max(s_maxbin, big2);
+        }
+        __syncthreads();
+    } else if (tid == 0) {
+        s_maxbin = max(s_maxbin, s_rh[kTopBin]);
+    }
+    __syncthreads();
+    const bool ranked = s_maxbin <= (unsigned)kBucketMax;
+    if (!ranked) {
+        // compact in any order, the caller sorts
+        __syncthreads();
+        if (tid == 0) s_cnt = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kCap / kSelThreads; ++k) {
+            const int i = tid + k * kSelThreads;
+            if (i < n && bin_of(mine[k]) >= edge) s[atomicAdd(&s_cnt, 1u)] = mine[k];
+        }
+        __syncthreads();
+        return {m, false};
+    }
+    // counting sort: scatter to the (sub-)bin's rank range ...
 #pragma unroll
     for (int k = 0; k < kCap / kSelThreads; ++k) {
         const int i = tid + k * kSelThreads;
         if (i < n) {
-            const unsigned d = min(((unsigned)(mine[k] >> 32) - base) >> kRefineShift, (unsigned)kRefineBins - 1u);
+            const unsigned d = bin_of(mine[k]);
             if (d >= edge) {
-                const unsigned slot = atomicAdd(&s_cnt, 1u);
-                if (slot < 8u * kSelThreads) s[slot] = mine[k];
+                unsigned pos;
+                if (two_level && d == kTopBin) {
+                    const unsigned d2 = bin2_of(mine[k]);
+                    pos = s_start2[d2] + atomicAdd(&s_fill2[d2], 1u);
+                } else {
+                    pos = s_start[d] + atomicAdd(&s_fill[d], 1u);
+                }
+                s[pos] = mine[k];
             }
         }
     }
     __syncthreads();
-    return (int)s_cnt;
+    // ... then the exact rank inside the bin: keys are unique, so counting the larger mates is a permutation
+    unsigned long long *sorted = s + kSortSlots;
+    for (int p = tid; p < m; p += kSelThreads) {
+        const unsigned long long key = s[p];
+        const unsigned d = bin_of(key);
+        unsigned lo, hi;
+        if (two_level && d == kTopBin) {
+            const unsigned d2 = bin2_of(key);
+            lo = s_start2[d2]; hi = lo + s_rh2[d2];
+        } else {
+            lo = s_start[d]; hi = lo + s_rh[d];
+        }
+        unsigned r = lo;
+        for (unsigned j = lo; j < hi; ++j) r += s[j] > key;
+        sorted[r] = key;
+    }
+    __syncthreads();
+    return {m, true};
 }
 
 __device__ void sort_and_emit(const TopkArgs &A, int b, int n, unsigned long long *s) {
-    int m = refine_candidates(A, b, n, s);
-    if (m <= 8 * kSelThreads) {
-        for (int i = m + threadIdx.x; i < 8 * kSelThreads; i += blockDim.x) s[i] = 0ull;
+    const Refined R = refine_candidates(A, b, n, s);
+    if (R.ranked) {
+        emit_topk<0>(A, b, s + kSortSlots);
+    } else if (R.m <= kSortSlots) {
+        for (int i = R.m + threadIdx.x; i < kSortSlots; i += blockDim.x) s[i] = 0ull;
         __syncthreads();
         block_sort_desc<8>(s);
         emit_topk<8>(A, b, s);
