@@ -372,12 +372,23 @@ __device__ __forceinline__ unsigned long long sorted_at(const unsigned long long
     return s[(q % (E ? E : 1)) * kSelThreads + q / (E ? E : 1)];
 }
 
-template <int E>
-__device__ void emit_topk(const TopkArgs &A, int b, const unsigned long long *s) {
-    // The box regression gather (4 scattered 4-byte loads per row, mostly HBM misses) is the latency
-    // of this phase: kEmitRows rows per thread are resolved and their loads issued before any store.
-    constexpr int kEmitRows = 4;
+// box regression rows of the selected anchors (bench.py:48-49): 4 scattered 4-byte loads per row
+__device__ __forceinline__ float4 gather_box(const TopkArgs &A, int b, int anchor) {
     const Geo &g = A.g;
+    const int l = geo_level(g, anchor);
+    const int loc = anchor - g.off[l];
+    const int sp = loc / g.na, a = loc - sp * g.na;
+    const float *bp = A.box[l] + ((size_t)(b * g.na + a) * 4) * g.hw[l] + sp;
+    float4 r;
+    r.x = __ldg(bp); r.y = __ldg(bp + g.hw[l]); r.z = __ldg(bp + 2 * (size_t)g.hw[l]); r.w = __ldg(bp + 3 * (size_t)g.hw[l]);
+    return r;
+}
+
+// BOXES = false leaves out_box to the cluster kernel that follows (gather_selected_boxes): the scattered
+// gather is LSU-bound on one SM, spread over the 8 CTAs of the image's cluster it is not.
+template <int E, bool BOXES>
+__device__ void emit_topk(const TopkArgs &A, int b, const unsigned long long *s) {
+    constexpr int kEmitRows = 4;   // rows per thread whose gathers are issued before any store
     for (int q0 = threadIdx.x; q0 < A.K; q0 += kEmitRows * blockDim.x) {
         float4 r[kEmitRows];
         unsigned long long key[kEmitRows];
@@ -385,13 +396,10 @@ __device__ void emit_topk(const TopkArgs &A, int b, const unsigned long long *s)
         for (int u = 0; u < kEmitRows; ++u) {
             const int q = q0 + u * blockDim.x;
             key[u] = q < A.K ? sorted_at<E>(s, q) : ~0ull;   // ~0: flat index 0, never stored
-            const unsigned flat = ~(unsigned)(key[u] & 0xFFFFFFFFull);
-            const int anchor = (int)(flat / (unsigned)A.C);
-            const int l = geo_level(g, anchor);
-            const int loc = anchor - g.off[l];
-            const int sp = loc / g.na, a = loc - sp * g.na;
-            const float *bp = A.box[l] + ((size_t)(b * g.na + a) * 4) * g.hw[l] + sp;
-            r[u].x = __ldg(bp); r[u].y = __ldg(bp + g.hw[l]); r[u].z = __ldg(bp + 2 * (size_t)g.hw[l]); r[u].w = __ldg(bp + 3 * (size_t)g.hw[l]);
+            if (BOXES) {
+                const unsigned flat = ~(unsigned)(key[u] & 0xFFFFFFFFull);
+                r[u] = gather_box(A, b, (int)(flat / (unsigned)A.C));
+            }
         }
 #pragma unroll
         for (int u = 0; u < kEmitRows; ++u) {
@@ -403,8 +411,16 @@ __device__ void emit_topk(const TopkArgs &A, int b, const unsigned long long *s)
             A.out_val[o] = val_of((unsigned)(key[u] >> 32));
             A.out_idx[o] = anchor;                                          // bench.py:45
             A.out_cls[o] = (int)(flat - (unsigned)anchor * (unsigned)A.C);  // bench.py:46
-            reinterpret_cast<float4 *>(A.out_box)[o] = r[u];               // bench.py:48-49
+            if (BOXES) reinterpret_cast<float4 *>(A.out_box)[o] = r[u];    // bench.py:48-49
         }
+    }
+}
+
+// rows of an image the select kernel finished: one row per thread of the 8-CTA cluster
+__device__ void gather_selected_boxes(const TopkArgs &A, int b, unsigned cluster_rank) {
+    for (int q = (int)cluster_rank * kSelThreads + threadIdx.x; q < A.K; q += kClusterSize * kSelThreads) {
+        const size_t o = (size_t)b * A.K + q;
+        reinterpret_cast<float4 *>(A.out_box)[o] = gather_box(A, b, (int)A.out_idx[o]);
     }
 }
 
@@ -574,22 +590,23 @@ __device__ Refined refine_candidates(const TopkArgs &A, int b, int n, unsigned l
     return {m, true};
 }
 
+template <bool BOXES>
 __device__ void sort_and_emit(const TopkArgs &A, int b, int n, unsigned long long *s) {
     const Refined R = refine_candidates(A, b, n, s);
     if (R.ranked) {
-        emit_topk<0>(A, b, s + kSortSlots);
+        emit_topk<0, BOXES>(A, b, s + kSortSlots);
     } else if (R.m <= kSortSlots) {
         for (int i = R.m + threadIdx.x; i < kSortSlots; i += blockDim.x) s[i] = 0ull;
         __syncthreads();
         block_sort_desc<8>(s);
-        emit_topk<8>(A, b, s);
+        emit_topk<8, BOXES>(A, b, s);
     } else {   // more than 8192 keys tie inside one sub-bin: sort everything
         const unsigned long long *cand = A.cand + (size_t)b * kCap;
         __syncthreads();
         for (int i = threadIdx.x; i < 16 * kSelThreads; i += blockDim.x) s[i] = i < n ? __ldcg(cand + i) : 0ull;
         __syncthreads();
         block_sort_desc<16>(s);
-        emit_topk<16>(A, b, s);
+        emit_topk<16, BOXES>(A, b, s);
     }
 }
 
@@ -601,7 +618,7 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const __grid_c
         if (threadIdx.x == 0) A.flag[b] = 1u;
         return;
     }
-    sort_and_emit(A, b, (int)n, s_keys);
+    sort_and_emit<false>(A, b, (int)n, s_keys);   // out_box: by the cluster kernel launched next
 }
 
 // ---- P3: exact radix select for flagged images (8-CTA cluster per image) ---------------------
@@ -615,7 +632,10 @@ topk_exact_kernel(const __grid_constant__ TopkArgs A) {
     cg::cluster_group cluster = cg::this_cluster();
     const int b = blockIdx.x / kClusterSize;
     const unsigned rank = cluster.block_rank();
-    if (A.flag[b] == 0u) return;   // uniform across the cluster
+    if (A.flag[b] == 0u) {   // uniform across the cluster: the select kernel did this image, its box rows are left
+        gather_selected_boxes(A, b, rank);
+        return;
+    }
 
     const int lane = threadIdx.x & 31;
     const int W = kClusterSize * (kSelThreads / 32);
@@ -692,7 +712,7 @@ topk_exact_kernel(const __grid_constant__ TopkArgs A) {
         const unsigned n = *(volatile unsigned *)(A.cnt + b);
         if (threadIdx.x == 0) A.thr[b] = (unsigned)(lower >> 32);   // every collected key is >= this
         __syncthreads();
-        sort_and_emit(A, b, (int)min(n, (unsigned)kCap), s_keys);
+        sort_and_emit<true>(A, b, (int)min(n, (unsigned)kCap), s_keys);
     }
     cluster.sync();   // keep peers' shared memory alive until rank 0 is done with DSMEM
 }
