@@ -81,6 +81,28 @@ def test_post_process_degenerate_inputs():
     np.testing.assert_array_equal(flat, np.arange(K))
 
 
+@pytest.mark.parametrize('case', ['sign_change', 'many_positives', 'outlier', 'inf_outlier', 'coarse_ties', 'narrow'])
+def test_post_process_select_paths(case):
+    """The select kernel's counting sort (sub-bins on the key bits, value-linear second level for the top
+    sub-bin) and its bitonic fallback: score distributions that stress each branch, against the oracle
+    (ties: ascending flat index, torch.topk's order on the reference's CPU path)."""
+    from ood_object_detection_b200.bench import _post_process
+    size, B, C, K = 256, 3, 20, 3000
+    mean, std = {'sign_change': (-4.0, 1.5), 'many_positives': (-1.0, 2.0), 'narrow': (-4.6, 0.01)}.get(case, (-4.6, 1.5))
+    co, bo = synth.head_outputs(90 + len(case), B, size, C, mean=mean, std=std, tie_free=(case not in ('coarse_ties', 'narrow')))
+    if case == 'outlier':
+        co[0][:, 3, 1, 1] = 1.0e30          # one huge score stretches the value range of the top sub-bin
+    if case == 'inf_outlier':
+        co[1][:, 5, 0, 2] = np.inf
+    if case == 'coarse_ties':
+        for c in co:
+            c[...] = np.round(c * 16) / 16   # hundreds of equal values per step: big bins, index-order ties
+    ref = orc.post_process(co, bo, 5, C, K)
+    got = _post_process([t(x) for x in co], [t(x) for x in bo], 5, C, K)
+    for r, g_ in zip(ref, got):
+        np.testing.assert_array_equal(g_.cpu().numpy(), r)
+
+
 def test_post_process_errors():
     from ood_object_detection_b200.bench import _post_process
     co, bo = synth.head_outputs(1, 1, 128, 1)
