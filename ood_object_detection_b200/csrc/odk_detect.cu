@@ -110,26 +110,77 @@ __device__ __forceinline__ bool nms_hit(float4 p, float ap, float4 q, float thr_
     return (touch || thr_f < 0.0f) && iou_nms(p, ap, q) > thr_f;
 }
 
+// Rounds are BATCHED: the first kLead alive candidates ("leaders", all earlier candidates are dead) are
+// resolved among themselves in score order -- leader b is kept iff no kept leader a < b suppresses it, which
+// is exactly what the one-at-a-time greedy loop decides for every candidate up to the last leader -- and
+// then every later candidate is tested against all newly kept leaders in one pass.  ~max_keep / kLead
+// rounds of two block barriers instead of max_keep rounds.
+constexpr int kLead = 8;
+
 __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_keep, int *kept, int window, int window_max) {
-    // One block barrier per round: while a warp kills the candidates of its words it also notes its
-    // first survivor; after the barrier every warp reduces the 32 notes to the next pick by itself.
-    __shared__ int s_first[2][kDetWarps];
+    __shared__ int s_lead[kLead];
+    __shared__ float4 s_lbox[kLead];
+    __shared__ float s_larea[kLead];
+    __shared__ int s_g;
+    __shared__ unsigned s_keep;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int limit = min(n, window);   // activated prefix
-    int count = 0, parity = 0;
-    auto first_alive = [&](int from_word, int nwords) {   // this warp's first alive candidate, or INT_MAX
-        for (int w = from_word + ((warp - from_word) & (kDetWarps - 1)); w < nwords; w += kDetWarps) {
-            const unsigned m = S.alive[w];
-            if (m) return w * 32 + __ffs(m) - 1;
-        }
-        return 0x7fffffff;
-    };
-    if (lane == 0) s_first[0][warp] = first_alive(0, (limit + 31) / 32);
+    int count = 0, from = 0;      // words below `from` are dead
     while (count < max_keep) {
-        __syncthreads();
+        __syncthreads();          // the alive words are final, last round's leader slots are free
         const int nwords = (limit + 31) / 32;
-        const int top = __reduce_min_sync(0xffffffffu, s_first[parity][lane]);
-        if (top == 0x7fffffff) {
+        if (warp == 0) {
+            // ---- the first kLead alive candidates, in order ----
+            int g = 0;
+            for (int base = from; base < nwords && g < kLead; base += 32) {
+                const int w = base + lane;
+                const unsigned m = w < nwords ? S.alive[w] : 0u;
+                const int c = __popc(m);
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                unsigned mm = m;
+                for (int r = g + incl - c; mm && r < kLead; ++r) {   // my set bits that rank below kLead
+                    s_lead[r] = w * 32 + __ffs(mm) - 1;
+                    mm &= mm - 1u;
+                }
+                g = min(kLead, g + __shfl_sync(0xffffffffu, incl, 31));
+            }
+            __syncwarp();
+            if (g > 0) {
+                if (lane < g) {
+                    const float4 p = S.box[s_lead[lane]];
+                    s_lbox[lane] = p;
+                    s_larea[lane] = __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y));
+                }
+                __syncwarp();
+                // ---- resolve the leaders among themselves: lane = pair (a < b), pairs ordered by b then a ----
+                const int pb = 1 + (lane >= 1) + (lane >= 3) + (lane >= 6) + (lane >= 10) + (lane >= 15) + (lane >= 21);
+                const int pa = lane - pb * (pb - 1) / 2;
+                bool hit = false;
+                if (lane < kLead * (kLead - 1) / 2 && pb < g) hit = nms_hit(s_lbox[pa], s_larea[pa], s_lbox[pb], thr_f);
+                const unsigned pairs = __ballot_sync(0xffffffffu, hit);
+                unsigned keep_mask = 0u;
+                int taken = 0;
+                for (int bb = 0; bb < g; ++bb) {
+                    const unsigned hb = (pairs >> (bb * (bb - 1) / 2)) & ((1u << bb) - 1u);   // kept a < bb that suppress bb
+                    if (!(hb & keep_mask) && count + taken < max_keep) { keep_mask |= 1u << bb; ++taken; }
+                }
+                if (lane == 0) {
+                    s_keep = keep_mask;
+                    int c = count;
+                    for (int bb = 0; bb < g; ++bb)
+                        if ((keep_mask >> bb) & 1u) kept[c++] = s_lead[bb];
+                }
+            }
+            if (lane == 0) s_g = g;
+        }
+        __syncthreads();
+        const int g = s_g;
+        if (g == 0) {
             if (limit >= n) break;
             // activate the next chunk: a candidate stays alive iff nothing kept so far suppresses it
             window = min(2 * window, window_max);   // chunks grow: 1 word per warp at most
@@ -147,32 +198,32 @@ __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_kee
                 const unsigned k = __ballot_sync(0xffffffffu, !dead);
                 if (lane == 0) S.alive[w] = k;
             }
-            __syncwarp();
-            const int mine = first_alive(limit / 32, (new_limit + 31) / 32);   // own words only: written by this warp
-            if (lane == 0) s_first[parity ^ 1][warp] = mine;
-            parity ^= 1;
+            from = limit / 32;
             limit = new_limit;
             continue;
         }
-        if (threadIdx.x == 0) kept[count] = top;
-        ++count;
-        const int from = top >> 5;
-        const float4 p = S.box[top];
-        const float ap = __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y));
-        int mine = 0x7fffffff;
+        const unsigned keep_mask = s_keep;
+        const int last = s_lead[g - 1];
+        count += __popc(keep_mask);
+        // ---- suppression by the newly kept leaders; every leader leaves the alive set ----
         for (int w = from + ((warp - from) & (kDetWarps - 1)); w < nwords; w += kDetWarps) {
             unsigned m = S.alive[w];   // warp-uniform
             if (!m) continue;
             const int i = w * 32 + lane;
             bool kill = false;
-            if ((m >> lane) & 1u) kill = i == top || (i > top && nms_hit(p, ap, S.box[i], thr_f));
+            if ((m >> lane) & 1u) {
+                if (i <= last) {
+                    kill = true;       // a leader (everything else up to the last leader was dead already)
+                } else {
+                    const float4 q = S.box[i];
+                    for (int bb = 0; bb < g && !kill; ++bb)
+                        if ((keep_mask >> bb) & 1u) kill = nms_hit(s_lbox[bb], s_larea[bb], q, thr_f);
+                }
+            }
             const unsigned k = __ballot_sync(0xffffffffu, kill);
-            m &= ~k;
-            if (lane == 0 && k) S.alive[w] = m;
-            if (m && mine == 0x7fffffff) mine = w * 32 + __ffs(m) - 1;
+            if (lane == 0 && k) S.alive[w] = m & ~k;
         }
-        if (lane == 0) s_first[parity ^ 1][warp] = mine;
-        parity ^= 1;
+        from = last >> 5;
     }
     __syncthreads();
     return count;
