@@ -7,10 +7,10 @@
 // memory.  Both suppressors are "frontier" algorithms that need at most max_det rounds instead
 // of the O(n^2) mask of the classic bitmask NMS, because only the first max_det survivors are
 // ever used (anchors.py:153):
-//   hard NMS : round = take the first still-alive candidate (score order), keep it, kill every
-//              later candidate whose IoU with it exceeds the threshold; a warp owns 32
-//              consecutive candidates = one word of the alive bitmask and updates it with a
-//              ballot, so there are no atomics;
+//   hard NMS : round = take the first 8 still-alive candidates (score order), decide among them which are
+//              kept (the greedy rule), kill every later candidate whose IoU with a newly kept one exceeds
+//              the threshold; a warp owns 32 consecutive candidates = one word of the alive bitmask and
+//              updates it with a ballot, so there are no atomics;
 //   Soft-NMS : round = block-wide arg-max of the current scores (first index on ties), record it,
 //              decay every alive score by exp(-iou^2/sigma), drop those at or below the score
 //              threshold (soft_nms.py:88-110).
