@@ -147,11 +147,14 @@ class PeerMailbox:
             import torch.distributed._symmetric_memory as symm
             grp = group if group is not None else dist.group.WORLD
             enable = getattr(symm, 'enable_symm_mem_for_group', None)
-            if enable is not None:
-                try:
-                    enable(grp.group_name)
-                except Exception:   # newer torch: implicit, the call is deprecated
-                    pass
+            if enable is not None:      # needed by older torch, a deprecated no-op in newer ones
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter('ignore')
+                    try:
+                        enable(grp.group_name)
+                    except Exception:
+                        pass
             self.buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
             self.buf.zero_()
             self.handle = symm.rendezvous(self.buf, grp)
