@@ -7,7 +7,7 @@
 // memory.  Both suppressors are "frontier" algorithms that need at most max_det rounds instead
 // of the O(n^2) mask of the classic bitmask NMS, because only the first max_det survivors are
 // ever used (anchors.py:153):
-//   hard NMS : round = take the first 8 still-alive candidates (score order), decide among them which are
+//   hard NMS : round = take the first 16 still-alive candidates (score order), decide among them which are
 //              kept (the greedy rule), kill every later candidate whose IoU with a newly kept one exceeds
 //              the threshold; a warp owns 32 consecutive candidates = one word of the alive bitmask and
 //              updates it with a ballot, so there are no atomics;
@@ -115,7 +115,9 @@ __device__ __forceinline__ bool nms_hit(float4 p, float ap, float4 q, float thr_
 // is exactly what the one-at-a-time greedy loop decides for every candidate up to the last leader -- and
 // then every later candidate is tested against all newly kept leaders in one pass.  ~max_keep / kLead
 // rounds of two block barriers instead of max_keep rounds.
-constexpr int kLead = 8;
+constexpr int kLead = 16;   // measured at D3 B=32: 8 / 16 / 32 leaders = 57 / 50 / 84 us per detect launch
+constexpr int kPairs = kLead * (kLead - 1) / 2;   // 120 leader pairs (a < b), ordered by b then a
+constexpr int kPairWords = (kPairs + 31) / 32;
 
 __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_keep, int *kept, int window, int window_max) {
     __shared__ int s_lead[kLead];
@@ -157,16 +159,31 @@ __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_kee
                     s_larea[lane] = __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y));
                 }
                 __syncwarp();
-                // ---- resolve the leaders among themselves: lane = pair (a < b), pairs ordered by b then a ----
-                const int pb = 1 + (lane >= 1) + (lane >= 3) + (lane >= 6) + (lane >= 10) + (lane >= 15) + (lane >= 21);
-                const int pa = lane - pb * (pb - 1) / 2;
-                bool hit = false;
-                if (lane < kLead * (kLead - 1) / 2 && pb < g) hit = nms_hit(s_lbox[pa], s_larea[pa], s_lbox[pb], thr_f);
-                const unsigned pairs = __ballot_sync(0xffffffffu, hit);
+                // ---- resolve the leaders among themselves: pair p = b(b-1)/2 + a (a < b), lanes take p, p+32, ... ----
+                unsigned pairs[kPairWords];
+#pragma unroll
+                for (int k = 0; k < kPairWords; ++k) {
+                    const int p = k * 32 + lane;
+                    int pb = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+                    if (pb * (pb - 1) / 2 > p) --pb;
+                    if ((pb + 1) * pb / 2 <= p) ++pb;
+                    const int pa = p - pb * (pb - 1) / 2;
+                    bool hit = false;
+                    if (p < kPairs && pb < g) hit = nms_hit(s_lbox[pa], s_larea[pa], s_lbox[pb], thr_f);
+                    pairs[k] = __ballot_sync(0xffffffffu, hit);
+                }
                 unsigned keep_mask = 0u;
                 int taken = 0;
                 for (int bb = 0; bb < g; ++bb) {
-                    const unsigned hb = (pairs >> (bb * (bb - 1) / 2)) & ((1u << bb) - 1u);   // kept a < bb that suppress bb
+                    const int bit = bb * (bb - 1) / 2;     // first pair of column bb
+                    const int k = bit >> 5, sh = bit & 31;
+                    unsigned lo = 0u, hi = 0u;
+#pragma unroll
+                    for (int j = 0; j < kPairWords; ++j) {
+                        if (j == k) lo = pairs[j];
+                        if (j == k + 1) hi = pairs[j];
+                    }
+                    const unsigned hb = __funnelshift_r(lo, hi, sh) & ((1u << bb) - 1u);   // kept a < bb that suppress bb
                     if (!(hb & keep_mask) && count + taken < max_keep) { keep_mask |= 1u << bb; ++taken; }
                 }
                 if (lane == 0) {
