@@ -43,6 +43,7 @@ struct TopkArgs {
     int vec[ODK_MAX_LEVELS];      // 4 or 1
     int nvec[ODK_MAX_LEVELS];     // vector units per plane
     int nseg[ODK_MAX_LEVELS];     // task segments per plane
+    FastDiv div_nseg[ODK_MAX_LEVELS], div_C;   // the task decode runs once per 16 KB segment, and per SAMPLED unit
     int task_off[ODK_MAX_LEVELS + 1];
     int B, C, K, planes;          // planes = na * C channel planes per level
     long long N;                  // elements per image = A * C
@@ -74,15 +75,20 @@ struct Task {
     unsigned fbase;      // flat index of position 0 of this plane: (off_l + a) * C + c
 };
 
-__device__ __forceinline__ Task decode_task(const TopkArgs &A, int b, int t) {
+__device__ __forceinline__ int task_level(const TopkArgs &A, int t) {
     int l = 0;
 #pragma unroll
     for (int i = 1; i < ODK_MAX_LEVELS; ++i)
         if (i < A.g.nlev && t >= A.task_off[i]) l = i;
+    return l;
+}
+
+__device__ __forceinline__ Task decode_task(const TopkArgs &A, int b, int t) {
+    const int l = task_level(A, t);
     const int local = t - A.task_off[l];
-    const int ch = local / A.nseg[l];
+    const int ch = (int)fd_div((unsigned)local, A.div_nseg[l]);
     const int sg = local - ch * A.nseg[l];
-    const int a = ch / A.C, c = ch - a * A.C;
+    const int a = (int)fd_div((unsigned)ch, A.div_C), c = ch - a * A.C;
     Task k;
     k.base = A.cls[l] + ((size_t)b * A.planes + ch) * A.g.hw[l];
     k.vec = A.vec[l];
@@ -141,6 +147,8 @@ __global__ void __launch_bounds__(kTopkThreads) topk_sample_kernel(const __grid_
                 h ^= h >> 15;
                 const int j = (int)((h * 2246822519u) >> (32 - kSampleShift));
                 if (j * 32 >= kSegVec) continue;   // no segment has that unit: skip the decode (half the tasks)
+                const int l = task_level(A, t);
+                if (A.nseg[l] == 1 && j * 32 >= A.nvec[l]) continue;   // small planes: most units do not exist
                 const Task k = decode_task(A, b, t);
                 const int u = k.u0 + j * 32 + lane;
                 if (u < k.u1) {
@@ -761,6 +769,7 @@ int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B
     if (!workspace || workspace_bytes < odk_topk_workspace_bytes(B, K))
         return set_error(ODK_EWORKSPACE, "odk_topk: workspace too small (%zu < %zu)", workspace_bytes, odk_topk_workspace_bytes(B, K));
     a.B = B; a.C = C; a.K = K; a.planes = na * C;
+    a.div_C = make_fastdiv((unsigned)C);
     int toff = 0;
     for (int l = 0; l < num_levels; ++l) {
         a.cls[l] = (const float *)cls_levels[l];
@@ -769,6 +778,7 @@ int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B
         a.vec[l] = (a.g.hw[l] % 4 == 0 && ((uintptr_t)a.cls[l] & 15) == 0) ? 4 : 1;
         a.nvec[l] = a.g.hw[l] / a.vec[l];
         a.nseg[l] = (a.nvec[l] + kSegVec - 1) / kSegVec;
+        a.div_nseg[l] = make_fastdiv((unsigned)a.nseg[l]);
         a.task_off[l] = toff;
         toff += a.planes * a.nseg[l];
     }
