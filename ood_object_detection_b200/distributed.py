@@ -1,15 +1,19 @@
 """Data-parallel use of the dense per-anchor path: images shard across ranks, nothing else moves.
 
 Every stage is independent per image (reference anchors.py:393, bench.py:44,69); the only
-cross-image coupling is the loss normaliser sum(num_positives)+1 (loss.py:261) and the final sums.
-So the sharded path needs two latency-bound collectives (the shapes the reference's own
-``effdet/distributed.py`` helpers would move, evaluator.py:38-39):
-  * all-reduce(sum) of the scalar normaliser before the loss kernel (gradients are scaled by the
-    GLOBAL 1/N inside the same pass), then all-reduce(sum) of the three loss scalars;
+cross-image coupling is the loss normaliser sum(num_positives)+1 (loss.py:261) and the final sums
+(what the reference's own ``effdet/distributed.py`` helpers would move, evaluator.py:38-39):
+  * forward / logging path: every rank computes partial sums against a unit normaliser and the 4
+    floats [cls + w*box, cls, box, sum(num_pos)+1] are exchanged ONCE per step -- by remote stores into
+    peer mailboxes over NVLink issued by the loss kernel itself (``PeerMailbox``,
+    ``local_partial_sums(..., mailbox=)``), or by one all-reduce (``all_reduce_partial_sums``);
+  * gradient path: all-reduce(sum) of the scalar normaliser BEFORE the loss kernel (gradients are scaled
+    by the GLOBAL 1/N inside the same pass), then all-reduce(sum) of the three loss scalars
+    (``sharded_detection_loss``);
   * all-gather of the padded detections [B_local, D, 6] (+ counts, + OOD scores).
 With these the result equals the single-process reference at the global batch, up to fp32
-summation order.  Works with any initialised ``torch.distributed`` backend (NCCL over NVLink on
-the B200 box, gloo in the CPU tests).
+summation order.  The collective helpers work with any initialised ``torch.distributed`` backend
+(NCCL over NVLink on the B200 box, gloo in the CPU tests); the mailboxes need CUDA peer access.
 """
 from typing import List, Optional
 
