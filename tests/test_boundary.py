@@ -158,3 +158,23 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
             _lib.Exchange.world.offset, _lib.Exchange.num_pos_plus_1.offset, _lib.Exchange.status.offset,
             ctypes.sizeof(_lib.DetectParams)]
     assert got == want
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) must print ONE JSON line with
+    the contract's keys; it runs on the host only, so it is checked here without a GPU."""
+    import json
+    import subprocess
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                                   '--warmup', '1'], cwd=ROOT, timeout=600).decode()
+    lines = [l for l in out.splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['higher_is_better'] is True and d['unit'] == 'images/s'
+    for key in ('metric', 'value', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'scaling', 'vs_baseline', 'dtype', 'data',
+                'config', 'cpu_baseline', 'e2e'):
+        assert key in d, key
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+    assert d['e2e']['value'] == d['value'] and d['value'] > 0
+    assert 'workload' in d['config']
