@@ -47,6 +47,17 @@ def test_abi_argument_errors_without_gpu():
     assert lib.odk_assign_workspace_bytes(4, 100) >= 4 * 100 * 8
     with pytest.raises(RuntimeError):
         _lib.check(rc)
+    # data-parallel exchange (ABI v2): sizes and argument checks
+    assert lib.odk_mailbox_bytes(8) >= 2 * 8 * 32 + 8 and lib.odk_mailbox_bytes(8) % 16 == 0
+    assert lib.odk_mailbox_bytes(0) == 0 and lib.odk_mailbox_bytes(_lib.MAILBOX_MAX_WORLD + 1) == 0
+    assert lib.odk_partials_publish(None, None, 0, 0, None) == -1 and b'world' in lib.odk_last_error()
+    assert lib.odk_partials_publish(None, None, 2, 2, None) == -1
+    assert lib.odk_partials_publish(None, None, 2, 1, None) == -1 and b'partials4' in lib.odk_last_error()
+    assert lib.odk_partials_collect(None, 2, None, None, None) == -1
+    assert lib.odk_partials_collect(None, 99, None, None, None) == -1 and b'world' in lib.odk_last_error()
+    # odk_detect / odk_loss validate their parameter structs before touching the device
+    assert lib.odk_detect(None, None, None, None, 1, 10, None, 100, None, None, None, None, None, None, None) == -1
+    assert b'params' in lib.odk_last_error()
 
 
 def test_shims_refuse_cpu_tensors():
