@@ -2,19 +2,21 @@
 // Replaces _post_process (reference effdet/bench.py:12-56).  See include/odk.h (odk_topk).
 //
 // HBM-bound design: the logits are streamed ONCE.
-//   P0  sample   : ~1/64 of each image (pseudo-random 512-byte units of every channel plane) is
-//                  histogrammed on the top 12 bits of an order-preserving key;
-//   P1  collect  : every CTA derives, from the sample histogram, a threshold bin that keeps
-//                  between K and kCap elements with overwhelming probability, then streams its
-//                  share of the image with 128-bit loads and appends (key, flat index) of the few
-//                  elements above the threshold (~1.5*K per image) to a candidate list;
-//   P2  select   : one CTA per image bitonic-sorts the candidates in shared memory on the 64-bit
-//                  composite key (value desc, flat index asc), emits the top K and gathers the box
-//                  regressions.  If the candidate count is not in [K, kCap] it raises a flag;
-//   P3  exact    : flagged images only (never for i.i.d. logits; e.g. constant inputs): an
-//                  8-CTA thread-block cluster per image runs an exact MSD radix select on the
-//                  composite key (histograms merged through distributed shared memory), collects
-//                  and sorts.  Unflagged clusters exit immediately.
+//   P0  sample   : ~1/64 of each image (pseudo-random 512-byte units of every channel plane); a lane keeps
+//                  the maximum of what it sampled in one of 8192 slots, and the image's last CTA turns
+//                  the slot maxima into a threshold (12-bit key bin) that keeps between K and kCap
+//                  elements with overwhelming probability;
+//   P1  collect  : every CTA streams its share of the image with 128-bit loads and appends (key, flat
+//                  index) of the few elements at or above the threshold (~1.7*K per image) to a
+//                  candidate list;
+//   P2  select   : one CTA per image cuts the candidates to just over K with a 1024-bin histogram, uses
+//                  the same histogram as a counting sort (in-bin ranking by direct comparison; bitonic
+//                  network for heavily tied inputs) on the 64-bit composite key (value desc, flat index
+//                  asc) and emits the top K.  If the candidate count is not in [K, kCap] it raises a flag;
+//   P3  cluster  : an 8-CTA thread-block cluster per image gathers the box regressions of the selected
+//                  anchors; for flagged images (never for i.i.d. logits; e.g. constant inputs) it runs an
+//                  exact MSD radix select on the composite key instead (histograms merged through
+//                  distributed shared memory), collects, sorts and emits everything itself.
 // Composite key: hi32 = order-preserving map of the fp32 logit, lo32 = ~flat_index, so keys are
 // unique and "largest key first" is torch.topk's order with ties broken by ascending index.
 #include <cooperative_groups.h>
