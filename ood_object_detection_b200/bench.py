@@ -88,40 +88,45 @@ def _batch_detection(
     return dets
 
 
-class DetBenchPredict(nn.Module):
+class _Bench(nn.Module):
+    """What the two reference benches share: the wrapped model, the post-process constants read off
+    ``model.config`` (bench.py:80-89, 107-119) and the top-k -> detections chain on libodk."""
+
+    _CONFIG_FIELDS = ('num_levels', 'num_classes', 'max_detection_points', 'max_det_per_image', 'soft_nms')
+
     def __init__(self, model):
         super().__init__()
-        self.model = model
-        self.config = model.config
-        self.num_levels = model.config.num_levels
-        self.num_classes = model.config.num_classes
-        self.anchors = Anchors.from_config(model.config)
-        self.max_detection_points = model.config.max_detection_points
-        self.max_det_per_image = model.config.max_det_per_image
-        self.soft_nms = model.config.soft_nms
-        self.pad_detections = False
+        cfg = model.config
+        self.model, self.config = model, cfg
+        for name in self._CONFIG_FIELDS:
+            setattr(self, name, getattr(cfg, name))
+        self.anchors = Anchors.from_config(cfg)
+        self.pad_detections = False   # True: zero-pad short images instead of the reference's stack error
+
+    def _detections(self, batch_size, cls_levels, box_levels, img_scale, img_size):
+        cls_k, box_k, idx, klass = _post_process(cls_levels, box_levels, num_levels=self.num_levels,
+                                                 num_classes=self.num_classes,
+                                                 max_detection_points=self.max_detection_points)
+        return _batch_detection(batch_size, cls_k, box_k, self.anchors.boxes, idx, klass, img_scale, img_size,
+                                max_det_per_image=self.max_det_per_image, soft_nms=self.soft_nms,
+                                pad=self.pad_detections)
+
+
+class DetBenchPredict(_Bench):
+    """Reference bench.py:79-103: ``forward(x, img_info=None)`` -> detections [B, D, 6]."""
 
     def forward(self, x, img_info: Optional[Dict[str, torch.Tensor]] = None):
-        class_out, box_out = self.model(x)
-        class_out, box_out, indices, classes = _post_process(
-            class_out, box_out, num_levels=self.num_levels, num_classes=self.num_classes,
-            max_detection_points=self.max_detection_points)
-        if img_info is None:
-            img_scale, img_size = None, None
-        else:
-            img_scale, img_size = img_info['img_scale'], img_info['img_size']
-        return _batch_detection(
-            x.shape[0], class_out, box_out, self.anchors.boxes, indices, classes,
-            img_scale, img_size, max_det_per_image=self.max_det_per_image, soft_nms=self.soft_nms,
-            pad=self.pad_detections)
+        cls_levels, box_levels = self.model(x)
+        scale, size = (None, None) if img_info is None else (img_info['img_scale'], img_info['img_size'])
+        return self._detections(x.shape[0], cls_levels, box_levels, scale, size)
 
     def forward_with_ood(self, x, img_info: Optional[Dict[str, torch.Tensor]] = None, temperature: float = 1.0):
         """Extension (north_star piece 4): padded detections plus per-detection energy / max-logit."""
-        class_out_l, box_out_l = self.model(x)
-        return detect_with_ood(class_out_l, box_out_l, self.anchors.boxes, self.num_levels, self.num_classes,
-                               self.max_detection_points, self.max_det_per_image, self.soft_nms,
-                               None if img_info is None else img_info['img_scale'],
-                               None if img_info is None else img_info['img_size'], temperature)
+        cls_levels, box_levels = self.model(x)
+        scale, size = (None, None) if img_info is None else (img_info['img_scale'], img_info['img_size'])
+        return detect_with_ood(cls_levels, box_levels, self.anchors.boxes, self.num_levels, self.num_classes,
+                               self.max_detection_points, self.max_det_per_image, self.soft_nms, scale, size,
+                               temperature)
 
 
 def detect_with_ood(cls_outputs, box_outputs, anchor_boxes, num_levels, num_classes, max_detection_points=5000,
@@ -139,44 +144,33 @@ def detect_with_ood(cls_outputs, box_outputs, anchor_boxes, num_levels, num_clas
     return {'detections': dets, 'count': count, 'energy': energy, 'max_logit': max_logit, 'anchor': anchor_of_det}
 
 
-class DetBenchTrain(nn.Module):
+class DetBenchTrain(_Bench):
+    """Reference bench.py:106-145: ``forward(x, target)`` -> dict(loss, class_loss, box_loss[, detections]).
+    With its own labeler (``create_labeler=True``) the targets are never materialised: the assignment feeds
+    the fused loss kernel directly; otherwise ``target`` carries the collate's ``label_*`` tensors."""
+
     def __init__(self, model, create_labeler=True):
-        super().__init__()
-        self.model = model
-        self.config = model.config
-        self.num_levels = model.config.num_levels
-        self.num_classes = model.config.num_classes
-        self.anchors = Anchors.from_config(model.config)
-        self.max_detection_points = model.config.max_detection_points
-        self.max_det_per_image = model.config.max_det_per_image
-        self.soft_nms = model.config.soft_nms
-        self.anchor_labeler = None
-        if create_labeler:
-            self.anchor_labeler = AnchorLabeler(self.anchors, self.num_classes, match_threshold=0.5)
+        super().__init__(model)
+        self.anchor_labeler = AnchorLabeler(self.anchors, self.num_classes, match_threshold=0.5) if create_labeler else None
         self.loss_fn = DetectionLoss(model.config)
-        self.pad_detections = False
+
+    def _losses(self, cls_levels, box_levels, target):
+        if self.anchor_labeler is not None:
+            return self.loss_fn.forward_fused(cls_levels, box_levels,
+                                              self.anchor_labeler.assign(target['bbox'], target['cls']))
+        if 'label_num_positives' not in target:
+            raise AssertionError('a bench without a labeler needs the pre-computed label_* targets (bench.py:124-128)')
+        levels = range(self.num_levels)
+        return self.loss_fn(cls_levels, box_levels, [target[f'label_cls_{l}'] for l in levels],
+                            [target[f'label_bbox_{l}'] for l in levels], target['label_num_positives'])
 
     def forward(self, x, target: Dict[str, torch.Tensor]):
-        class_out, box_out = self.model(x)
-        if self.anchor_labeler is None:
-            # target should contain pre-computed anchor labels if labeler not present in bench
-            assert 'label_num_positives' in target
-            cls_targets = [target[f'label_cls_{l}'] for l in range(self.num_levels)]
-            box_targets = [target[f'label_bbox_{l}'] for l in range(self.num_levels)]
-            num_positives = target['label_num_positives']
-            loss, class_loss, box_loss = self.loss_fn(class_out, box_out, cls_targets, box_targets, num_positives)
-        else:
-            label_batch = self.anchor_labeler.assign(target['bbox'], target['cls'])
-            loss, class_loss, box_loss = self.loss_fn.forward_fused(class_out, box_out, label_batch)
-        output = {'loss': loss, 'class_loss': class_loss, 'box_loss': box_loss}
-        if not self.training:
-            class_out_pp, box_out_pp, indices, classes = _post_process(
-                class_out, box_out, num_levels=self.num_levels, num_classes=self.num_classes,
-                max_detection_points=self.max_detection_points)
-            output['detections'] = _batch_detection(
-                x.shape[0], class_out_pp, box_out_pp, self.anchors.boxes, indices, classes,
-                target['img_scale'], target['img_size'],
-                max_det_per_image=self.max_det_per_image, soft_nms=self.soft_nms, pad=self.pad_detections)
+        cls_levels, box_levels = self.model(x)
+        total, class_loss, box_loss = self._losses(cls_levels, box_levels, target)
+        output = dict(loss=total, class_loss=class_loss, box_loss=box_loss)
+        if not self.training:   # evaluation also wants the detections (bench.py:136-144)
+            output['detections'] = self._detections(x.shape[0], cls_levels, box_levels, target['img_scale'],
+                                                    target['img_size'])
         return output
 
 

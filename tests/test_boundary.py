@@ -189,3 +189,89 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert d['e2e']['value'] == d['value'] and d['value'] > 0
     assert 'workload' in d['config']
+
+
+def test_bench_wrappers_with_stubbed_kernels(monkeypatch):
+    """DetBenchPredict / DetBenchTrain host logic (reference bench.py:79-145) with the kernel entry points
+    stubbed out: which tensors reach which call, the output dict, the label_* target path, eval-mode
+    detections, unwrap_bench.  (The real kernels behind them are covered by the GPU tests.)"""
+    import types
+    from ood_object_detection_b200 import bench as B
+    cfg = types.SimpleNamespace(min_level=3, max_level=7, num_levels=5, num_scales=3, aspect_ratios=[(1.0, 1.0), (1.4, 0.7), (0.7, 1.4)],
+                                anchor_scale=4.0, image_size=(128, 128), num_classes=7, max_detection_points=50,
+                                max_det_per_image=5, soft_nms=True, alpha=0.25, gamma=1.5, delta=0.1,
+                                box_loss_weight=50.0, label_smoothing=0.0, legacy_focal=False, jit_loss=False)
+
+    class Model(torch.nn.Module):
+        config = cfg
+
+        def forward(self, x):
+            return ['cls_levels', x.shape[0]], ['box_levels']
+
+    calls = {}
+
+    def fake_post_process(cls_outputs, box_outputs, num_levels, num_classes, max_detection_points=5000):
+        calls['pp'] = (cls_outputs, box_outputs, num_levels, num_classes, max_detection_points)
+        return 'cls_k', 'box_k', 'idx', 'klass'
+
+    def fake_batch_detection(batch_size, class_out, box_out, anchor_boxes, indices, classes, img_scale=None, img_size=None,
+                             max_det_per_image=100, soft_nms=False, pad=False):
+        calls['det'] = (batch_size, class_out, box_out, tuple(anchor_boxes.shape), indices, classes, img_scale, img_size,
+                        max_det_per_image, soft_nms, pad)
+        return 'detections'
+
+    monkeypatch.setattr(B, '_post_process', fake_post_process)
+    monkeypatch.setattr(B, '_batch_detection', fake_batch_detection)
+    x = torch.zeros(3, 3, 128, 128)
+
+    pred = B.DetBenchPredict(Model())
+    assert (pred.num_levels, pred.num_classes, pred.max_detection_points, pred.max_det_per_image, pred.soft_nms) == (5, 7, 50, 5, True)
+    assert pred.config is cfg and tuple(pred.anchors.boxes.shape) == (3069, 4)
+    assert pred(x) == 'detections'
+    assert calls['pp'] == (['cls_levels', 3], ['box_levels'], 5, 7, 50)
+    assert calls['det'] == (3, 'cls_k', 'box_k', (3069, 4), 'idx', 'klass', None, None, 5, True, False)
+    pred.pad_detections = True
+    pred(x, {'img_scale': 'scale', 'img_size': 'size'})
+    assert calls['det'][6:] == ('scale', 'size', 5, True, True)
+
+    monkeypatch.setattr(B, 'detect_with_ood', lambda *a, **k: ('ood', a[0], a[1], tuple(a[2].shape), a[3:], k))
+    assert pred.forward_with_ood(x, {'img_scale': 'scale', 'img_size': 'size'}, temperature=2.0) == \
+        ('ood', ['cls_levels', 3], ['box_levels'], (3069, 4), (5, 7, 50, 5, True, 'scale', 'size', 2.0), {})
+
+    train = B.DetBenchTrain(Model(), create_labeler=False)
+    assert train.anchor_labeler is None
+    seen = {}
+
+    class FakeLoss(torch.nn.Module):
+        def forward(self, cls_out, box_out, cls_t, box_t, npos):
+            seen['loss'] = (cls_out, box_out, cls_t, box_t, npos)
+            return 'total', 'cls', 'box'
+
+        def forward_fused(self, cls_out, box_out, label_batch):
+            seen['fused'] = (cls_out, box_out, label_batch)
+            return 't', 'c', 'b'
+
+    train.loss_fn = FakeLoss()
+    target = {f'label_cls_{l}': f'c{l}' for l in range(5)}
+    target.update({f'label_bbox_{l}': f'b{l}' for l in range(5)})
+    target.update(label_num_positives='npos', img_scale='scale', img_size='size')
+    train.train()
+    out = train(x, target)
+    assert out == {'loss': 'total', 'class_loss': 'cls', 'box_loss': 'box'}
+    assert seen['loss'] == (['cls_levels', 3], ['box_levels'], [f'c{l}' for l in range(5)], [f'b{l}' for l in range(5)], 'npos')
+    train.eval()
+    out = train(x, target)
+    assert out['detections'] == 'detections' and calls['det'][6:8] == ('scale', 'size')
+    with pytest.raises(AssertionError):
+        train(x, {'bbox': None, 'cls': None})
+
+    with_labeler = B.DetBenchTrain(Model())   # default: own labeler, fused path
+    assert with_labeler.anchor_labeler is not None and with_labeler.anchor_labeler.num_classes == 7
+    monkeypatch.setattr(with_labeler.anchor_labeler, 'assign', lambda boxes, cls: ('label_batch', boxes, cls))
+    with_labeler.loss_fn = FakeLoss()
+    with_labeler.train()
+    assert with_labeler(x, {'bbox': 'gtb', 'cls': 'gtc'}) == {'loss': 't', 'class_loss': 'c', 'box_loss': 'b'}
+    assert seen['fused'] == (['cls_levels', 3], ['box_levels'], ('label_batch', 'gtb', 'gtc'))
+
+    wrapped = types.SimpleNamespace(module=train)
+    assert isinstance(B.unwrap_bench(wrapped), Model)
