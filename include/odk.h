@@ -160,7 +160,8 @@ int odk_scale_inplace_multi(void *const *bufs, const int64_t *sizes, int count, 
  *   odk_partials_collect: waits (bounded spin) until all `world` records of the next sequence
  *     number are in the LOCAL mailbox, sums them in rank order (deterministic) and writes
  *     out3 = {total, cls_loss, box_loss} of the global batch (sums / (sum(num_pos) + 1), loss.py:261,297);
- *     *status = 0, or 1 if a peer's record did not arrive in time (out3 is then unspecified).
+ *     *status = 0, or 1 if a peer's record did not arrive in time (about a second of polling; out3 is
+ *     then unspecified, later steps are unaffected because records carry their step number).
  * Every rank must alternate collect(j-1) ... publish(j) in stream order (that ordering is the flow
  * control that makes two slots enough) and publish once before its first collect.
  * odk_loss with odk_loss_params.exchange does both inside the loss kernel (collect(j-1) when a record
