@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define ODK_MAX_LEVELS 8
-#define ODK_VERSION 2
+#define ODK_VERSION 3
 
 /* error codes */
 #define ODK_OK 0
@@ -175,9 +175,9 @@ int odk_partials_collect(void *mailbox_local, int world, float *out3, int32_t *s
  * [B, A*C] (k = K, sorted descending; ties broken by ascending flat index), index split and
  * the three gathers.  Outputs: cls_topk [B,K] fp32 (the selected logit), box_topk [B,K,4],
  * indices [B,K] int64 (anchor = flat // C), classes [B,K] int64 (flat % C).
- * Workspace: odk_topk_workspace_bytes(B, K).
+ * Workspace: odk_topk_workspace_bytes(B, C, level_hw, num_levels, na, K).
  */
-size_t odk_topk_workspace_bytes(int B, int K);
+size_t odk_topk_workspace_bytes(int B, int C, const int32_t *level_hw, int num_levels, int na, int K);
 int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B, int C, const int32_t *level_hw,
              int num_levels, int na, int K, float *cls_topk, float *box_topk, int64_t *indices, int64_t *classes,
              void *workspace, size_t workspace_bytes, void *stream);
@@ -206,6 +206,26 @@ typedef struct odk_detect_params {
 int odk_detect(const float *cls_topk, const float *box_topk, const int64_t *indices, const int64_t *classes, int B,
                int N, const float *anchors, int64_t A, const float *img_scale, const float *img_size,
                const odk_detect_params *params, float *dets, int32_t *count, int32_t *src, void *stream);
+
+/* ---- post-process: the whole chain in one pipeline ------------------------------------------------
+ * Replaces DetBenchPredict.forward's post-process (bench.py:93-100: _post_process then
+ * _batch_detection): same results as odk_topk followed by odk_detect (and odk_ood), but the logits are
+ * streamed image-major by one persistent kernel and everything else of an image (select, decode,
+ * suppression, OOD scores) runs while the later images are still streaming.  K <= 6144.
+ *   dets [B,max_det,6], count [B], src [B,max_det] as odk_detect;
+ *   det_anchor [B,max_det] int64 anchor index of every detection (-1 padded), or NULL;
+ *   energy / max_logit [B,max_det] as odk_ood (both or neither; need det_anchor), temperature > 0;
+ *   cls_topk / box_topk / indices / classes: the top-k tensors as odk_topk, all four or all NULL.
+ * Workspace: odk_postprocess_workspace_bytes(B, C, level_hw, num_levels, na, K). */
+size_t odk_postprocess_workspace_bytes(int B, int C, const int32_t *level_hw, int num_levels, int na, int K);
+/* Diagnostics: byte offset inside the workspace of a uint32 [B] array that holds, after the call, 1 for every
+ * image that left the sampled-threshold path (exact radix select + stand-alone detect), else 0. */
+size_t odk_postprocess_flags_offset(int B, int C, const int32_t *level_hw, int num_levels, int na, int K);
+int odk_postprocess(const void *const *cls_levels, const void *const *box_levels, int B, int C, const int32_t *level_hw,
+                    int num_levels, int na, int K, const float *anchors, const float *img_scale, const float *img_size,
+                    const odk_detect_params *params, float temperature, float *dets, int32_t *count, int32_t *src,
+                    int64_t *det_anchor, float *energy, float *max_logit, float *cls_topk, float *box_topk,
+                    int64_t *indices, int64_t *classes, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Stand-alone soft_nms (soft_nms.py:42-112) on one box set [n,4] xyxy: runs until no box is
  * left or max_rounds is reached.  idx_out [n] int64, score_out [n] fp32, count [1] int32. */

@@ -57,10 +57,14 @@ SIGNATURES = {
     'odk_mailbox_bytes': (c_size_t, [c_int]),
     'odk_partials_publish': (c_int, [_P, _P, c_int, c_int, _P]),
     'odk_partials_collect': (c_int, [_P, c_int, _P, _P, _P]),
-    'odk_topk_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'odk_topk_workspace_bytes': (c_size_t, [c_int, c_int, _P, c_int, c_int, c_int]),
     'odk_topk': (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     'odk_detect': (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int64, _P, _P, ctypes.POINTER(DetectParams), _P, _P, _P,
                            _P]),
+    'odk_postprocess_workspace_bytes': (c_size_t, [c_int, c_int, _P, c_int, c_int, c_int]),
+    'odk_postprocess_flags_offset': (c_size_t, [c_int, c_int, _P, c_int, c_int, c_int]),
+    'odk_postprocess': (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, ctypes.POINTER(DetectParams), c_float,
+                                _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     'odk_soft_nms': (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, c_int, _P, _P, _P, _P]),
     'odk_nms_workspace_bytes': (c_size_t, [c_int]),
     'odk_nms': (c_int, [_P, _P, c_int, c_double, _P, _P, _P, c_size_t, _P]),
@@ -81,7 +85,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the library does not export the symbol
             fn.restype = res
             fn.argtypes = args
-        if handle.odk_version() != 2:
+        if handle.odk_version() != 3:
             raise RuntimeError('libodk.so ABI version mismatch')
         _LIB = handle
     return _LIB

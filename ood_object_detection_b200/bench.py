@@ -9,6 +9,7 @@ tensors: odk_assign's ``match`` feeds the fused loss directly.
 """
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -57,13 +58,85 @@ def _post_process(
     box_k = torch.empty((B, K, 4), dtype=torch.float32, device=dev)
     idx = torch.empty((B, K), dtype=torch.int64, device=dev)
     klass = torch.empty((B, K), dtype=torch.int64, device=dev)
-    ws_bytes = lib.odk_topk_workspace_bytes(B, K)
+    ws_bytes = lib.odk_topk_workspace_bytes(B, int(num_classes), _lib.int_array(hw), num_levels, na, K)
     ws = torch.empty(((ws_bytes + 15) // 16 * 2,), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.odk_topk(_lib.ptr_array(cls_l), _lib.ptr_array(box_l), B, int(num_classes), _lib.int_array(hw),
                                 num_levels, na, K, _lib.ptr(cls_k), _lib.ptr(box_k), _lib.ptr(idx), _lib.ptr(klass),
                                 _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr(dev)))
     return cls_k, box_k, idx, klass
+
+
+FUSED_MAX_K = 6144   # odk_postprocess keeps K sorted keys in registers (6 per thread of a 1024-thread CTA)
+
+
+def post_process_detect(cls_outputs, box_outputs, anchor_boxes, num_levels, num_classes, max_detection_points=5000,
+                        max_det_per_image=100, soft_nms=False, img_scale=None, img_size=None, with_ood=False,
+                        temperature=1.0, return_topk=False, return_flags=False):
+    """``_post_process`` + ``_batch_detection`` (+ OOD scores) as ONE pipelined odk_postprocess call
+    (reference bench.py:93-100): the logits are streamed image-major by a persistent kernel and each
+    image's select / decode / suppression / OOD chain runs while the later images are still streaming.
+
+    Returns dict(detections [B, D, 6] zero padded, count [B] int32, src [B, D] int32 rank in the top-k
+    list, anchor [B, D] int64; with_ood: energy, max_logit [B, D]; return_topk: cls [B,K,1], box [B,K,4],
+    indices, classes [B,K])."""
+    lib = _lib.lib()
+    cls_l = _prep_levels(cls_outputs, num_levels)
+    box_l = _prep_levels(box_outputs, num_levels)
+    dev = cls_l[0].device
+    B = cls_l[0].shape[0]
+    na = box_l[0].shape[1] // 4
+    K, D = int(max_detection_points), int(max_det_per_image)
+    hw = [c.shape[2] * c.shape[3] for c in cls_l]
+    total = na * sum(hw) * num_classes
+    if K > total:
+        raise RuntimeError(f'selected index k out of range (k={K}, A*C={total})')
+    if K > FUSED_MAX_K:   # beyond the fused kernel's register budget: the same chain as separate launches
+        cls_k, box_k, idx, klass = _post_process(cls_outputs, box_outputs, num_levels, num_classes, K)
+        dets, count, src = detect_batch(cls_k, box_k, anchor_boxes, idx, klass, img_scale, img_size, D, soft_nms)
+        anchor = torch.gather(idx, 1, src.clamp(min=0).long())
+        out = {'detections': dets, 'count': count, 'src': src, 'anchor': torch.where(src >= 0, anchor, torch.full_like(anchor, -1))}
+        if with_ood:
+            out['energy'], out['max_logit'] = ood_scores(cls_outputs, out['anchor'], num_levels, num_classes, temperature)
+        if return_topk:
+            out.update(cls=cls_k, box=box_k, indices=idx, classes=klass)
+        return out
+    anchor_boxes = anchor_boxes.to(dev, torch.float32).contiguous()
+    dets = torch.empty((B, D, 6), dtype=torch.float32, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    src = torch.empty((B, D), dtype=torch.int32, device=dev)
+    anchor = torch.empty((B, D), dtype=torch.int64, device=dev)
+    energy = max_logit = None
+    if with_ood:
+        energy = torch.empty((B, D), dtype=torch.float32, device=dev)
+        max_logit = torch.empty((B, D), dtype=torch.float32, device=dev)
+    cls_k = box_k = idx = klass = None
+    if return_topk:
+        cls_k = torch.empty((B, K, 1), dtype=torch.float32, device=dev)
+        box_k = torch.empty((B, K, 4), dtype=torch.float32, device=dev)
+        idx = torch.empty((B, K), dtype=torch.int64, device=dev)
+        klass = torch.empty((B, K), dtype=torch.int64, device=dev)
+    scale = None if img_scale is None else img_scale.to(dev, torch.float32).reshape(B).contiguous()
+    size = None if img_size is None else img_size.to(dev, torch.float32).reshape(B, 2).contiguous()
+    params = _lib.DetectParams(D, int(bool(soft_nms)), float(np.float32(0.01)), 0.3, 0.5, 0.3, float(np.float32(0.001)))
+    hw_arr = _lib.int_array(hw)
+    ws_bytes = lib.odk_postprocess_workspace_bytes(B, int(num_classes), hw_arr, num_levels, na, K)
+    ws = torch.empty(((ws_bytes + 15) // 16 * 2,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.odk_postprocess(_lib.ptr_array(cls_l), _lib.ptr_array(box_l), B, int(num_classes), hw_arr, num_levels,
+                                       na, K, _lib.ptr(anchor_boxes), _lib.ptr(scale), _lib.ptr(size), params,
+                                       float(temperature), _lib.ptr(dets), _lib.ptr(count), _lib.ptr(src), _lib.ptr(anchor),
+                                       _lib.ptr(energy), _lib.ptr(max_logit), _lib.ptr(cls_k), _lib.ptr(box_k), _lib.ptr(idx),
+                                       _lib.ptr(klass), _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr(dev)))
+    out = {'detections': dets, 'count': count, 'src': src, 'anchor': anchor}
+    if with_ood:
+        out['energy'], out['max_logit'] = energy, max_logit
+    if return_topk:
+        out.update(cls=cls_k, box=box_k, indices=idx, classes=klass)
+    if return_flags:   # diagnostics: 1 = the image left the sampled-threshold path (exact select)
+        off = lib.odk_postprocess_flags_offset(B, int(num_classes), hw_arr, num_levels, na, K)
+        out['flags'] = ws.view(torch.int32)[off // 4:off // 4 + B]
+    return out
 
 
 def _batch_detection(
@@ -104,12 +177,13 @@ class _Bench(nn.Module):
         self.pad_detections = False   # True: zero-pad short images instead of the reference's stack error
 
     def _detections(self, batch_size, cls_levels, box_levels, img_scale, img_size):
-        cls_k, box_k, idx, klass = _post_process(cls_levels, box_levels, num_levels=self.num_levels,
-                                                 num_classes=self.num_classes,
-                                                 max_detection_points=self.max_detection_points)
-        return _batch_detection(batch_size, cls_k, box_k, self.anchors.boxes, idx, klass, img_scale, img_size,
-                                max_det_per_image=self.max_det_per_image, soft_nms=self.soft_nms,
-                                pad=self.pad_detections)
+        out = post_process_detect(cls_levels, box_levels, self.anchors.boxes, self.num_levels, self.num_classes,
+                                  self.max_detection_points, self.max_det_per_image, self.soft_nms, img_scale, img_size)
+        if not self.pad_detections and int(out['count'].min().item()) < self.max_det_per_image:
+            # the reference stacks per-image results and raises when one is short (bench.py:76)
+            raise RuntimeError('stack expects each tensor to be equal size: an image produced fewer than '
+                               f'max_det_per_image={self.max_det_per_image} detections (set pad_detections=True)')
+        return out['detections'][:batch_size]
 
 
 class DetBenchPredict(_Bench):
@@ -131,17 +205,12 @@ class DetBenchPredict(_Bench):
 
 def detect_with_ood(cls_outputs, box_outputs, anchor_boxes, num_levels, num_classes, max_detection_points=5000,
                     max_det_per_image=100, soft_nms=False, img_scale=None, img_size=None, temperature=1.0):
-    """Whole post-process in four launches: top-k -> detections -> OOD scores.
+    """Whole post-process incl. the per-detection OOD scores in one pipelined odk_postprocess call.
 
-    Returns dict(detections [B, D, 6] zero padded, count [B] int32, energy [B, D], max_logit [B, D]);
+    Returns dict(detections [B, D, 6] zero padded, count [B] int32, energy [B, D], max_logit [B, D], anchor);
     OOD scores are computed over the C raw logits of each detection's source anchor."""
-    cls_k, box_k, idx, klass = _post_process(cls_outputs, box_outputs, num_levels, num_classes, max_detection_points)
-    dets, count, src = detect_batch(cls_k, box_k, anchor_boxes, idx, klass, img_scale, img_size, max_det_per_image,
-                                    soft_nms)
-    anchor_of_det = torch.gather(idx, 1, src.clamp(min=0).long())
-    anchor_of_det = torch.where(src >= 0, anchor_of_det, torch.full_like(anchor_of_det, -1))
-    energy, max_logit = ood_scores(cls_outputs, anchor_of_det, num_levels, num_classes, temperature)
-    return {'detections': dets, 'count': count, 'energy': energy, 'max_logit': max_logit, 'anchor': anchor_of_det}
+    return post_process_detect(cls_outputs, box_outputs, anchor_boxes, num_levels, num_classes, max_detection_points,
+                               max_det_per_image, soft_nms, img_scale, img_size, with_ood=True, temperature=temperature)
 
 
 class DetBenchTrain(_Bench):

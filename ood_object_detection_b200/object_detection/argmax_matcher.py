@@ -1,3 +1,5 @@
+# Interface modelled on the TF object-detection ArgMaxMatcher (Apache-2.0, The TensorFlow Authors / Ross Wightman's
+# effdet port) -- see NOTICE at the repository root.
 """ArgMaxMatcher: columns of a similarity matrix matched to their arg-max row.
 
 API of the reference's effdet/object_detection/argmax_matcher.py:39-174.  The hot path

@@ -1,3 +1,5 @@
+# Interface modelled on the TF object-detection FasterRcnnBoxCoder (Apache-2.0, The TensorFlow Authors / Ross Wightman's
+# effdet port) -- see NOTICE at the repository root.
 """Faster-RCNN box coder: ty=(y-ya)/ha, tx=(x-xa)/wa, th=log(h/ha), tw=log(w/wa).
 
 API of the reference's effdet/object_detection/box_coder.py:56-172.  The labeler's encode runs

@@ -1,72 +1,65 @@
-"""BoxList: a [N, 4] fp32 corner-box tensor plus named per-box fields.
+# Interface modelled on the TF object-detection BoxList (Apache-2.0, The TensorFlow Authors / Ross Wightman's
+# effdet port); this file is an independent, reduced re-statement -- see NOTICE at the repository root.
+"""BoxList: the [N, 4] fp32 corner boxes of one image plus optional per-box fields.
 
-API of the reference's effdet/object_detection/box_list.py:39-197 (a plain python class here;
-the reference scripts it with TorchScript, which the callers on this path never rely on)."""
-from typing import Dict, List, Optional
-
+Holder with the part of the reference's interface (effdet/object_detection/box_list.py:39-197) that
+the labeler path and its callers use: construction checks, ``boxes`` / fields access, ``num_boxes``,
+``device`` and the centre/size view the box coder needs."""
 import torch
+
+_BOXES = 'boxes'
+
+
+def _check_boxes(t, need_fp32):
+    if t.dim() != 2 or t.shape[-1] != 4:
+        raise ValueError('Invalid dimensions for box data.')
+    if need_fp32 and t.dtype != torch.float32:
+        raise ValueError('Invalid tensor type: should be tf.float32')
+    return t
 
 
 class BoxList(object):
+    __slots__ = ('data',)
+
     def __init__(self, boxes):
-        if len(boxes.shape) != 2 or boxes.shape[-1] != 4:
-            raise ValueError('Invalid dimensions for box data.')
-        if boxes.dtype != torch.float32:
-            raise ValueError('Invalid tensor type: should be tf.float32')
-        self.data: Dict[str, torch.Tensor] = {'boxes': boxes}
+        self.data = {_BOXES: _check_boxes(boxes, True)}
 
-    def num_boxes(self):
-        return self.data['boxes'].shape[0]
-
-    def get_all_fields(self):
-        return self.data.keys()
-
-    def get_extra_fields(self):
-        return [k for k in self.data.keys() if k != 'boxes']
-
-    def add_field(self, field: str, field_data: torch.Tensor):
-        self.data[field] = field_data
-
-    def has_field(self, field: str):
-        return field in self.data
-
+    # -- boxes ---------------------------------------------------------------------------------
     def boxes(self):
-        return self.get_field('boxes')
+        return self.data[_BOXES]
 
     def set_boxes(self, boxes):
-        if len(boxes.shape) != 2 or boxes.shape[-1] != 4:
-            raise ValueError('Invalid dimensions for box data.')
-        self.data['boxes'] = boxes
+        self.data[_BOXES] = _check_boxes(boxes, False)
 
-    def get_field(self, field: str):
-        if not self.has_field(field):
-            raise ValueError(f'field {field} does not exist')
-        return self.data[field]
-
-    def set_field(self, field: str, value: torch.Tensor):
-        if not self.has_field(field):
-            raise ValueError(f'field {field} does not exist')
-        self.data[field] = value
-
-    def get_center_coordinates_and_sizes(self):
-        """[ycenter, xcenter, height, width]; centre = min corner + size / 2 (box_list.py:152-164)."""
-        ymin, xmin, ymax, xmax = self.boxes().t().unbind()
-        width, height = xmax - xmin, ymax - ymin
-        return [ymin + height / 2., xmin + width / 2., height, width]
-
-    def transpose_coordinates(self):
-        y_min, x_min, y_max, x_max = self.boxes().chunk(4, dim=1)
-        self.set_boxes(torch.cat([x_min, y_min, x_max, y_max], 1))
-
-    def as_tensor_dict(self, fields: Optional[List[str]] = None):
-        if fields is None:
-            fields = self.get_all_fields()
-        out = {}
-        for field in fields:
-            if not self.has_field(field):
-                raise ValueError('boxlist must contain all specified fields')
-            out[field] = self.get_field(field)
-        return out
+    def num_boxes(self):
+        return int(self.data[_BOXES].shape[0])
 
     def device(self):
-        return self.data['boxes'].device
+        return self.data[_BOXES].device
+
+    def get_center_coordinates_and_sizes(self):
+        """[ycenter, xcenter, height, width], centre = min corner + size / 2 (reference :152-164: NOT
+        (min + max) / 2 -- the two round differently and the encoded targets depend on it)."""
+        b = self.data[_BOXES]
+        h, w = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+        return [b[:, 0] + h / 2., b[:, 1] + w / 2., h, w]
+
+    # -- extra fields --------------------------------------------------------------------------
+    def has_field(self, field):
+        return field in self.data
+
+    def add_field(self, field, field_data):
+        self.data[field] = field_data
+
+    def get_field(self, field):
+        try:
+            return self.data[field]
+        except KeyError:
+            raise ValueError(f'field {field} does not exist') from None
+
+    def set_field(self, field, value):
+        self.get_field(field)
+        self.data[field] = value
+
+    def get_extra_fields(self):
+        return [name for name in self.data if name != _BOXES]

@@ -1,58 +1,56 @@
-"""Match: per-column match results (>=0 matched row, -1 unmatched, -2 ignored).
+# Interface modelled on the TF object-detection Match (Apache-2.0, The TensorFlow Authors / Ross Wightman's
+# effdet port); this file is an independent, reduced re-statement -- see NOTICE at the repository root.
+"""Match: one int per anchor column -- the matched gt row (>= 0), -1 unmatched, -2 ignored.
 
-API of the reference's effdet/object_detection/matcher.py:36-179."""
+Holder with the part of the reference's interface (effdet/object_detection/matcher.py:36-179) that the
+target assigner and the labeler use.  On the hot path the gathers below never run: odk_targets /
+odk_loss read the match vector directly."""
 import torch
+
+UNMATCHED, IGNORED = -1, -2
 
 
 class Match(object):
-    def __init__(self, match_results: torch.Tensor):
-        if len(match_results.shape) != 1:
+    __slots__ = ('match_results',)
+
+    def __init__(self, match_results):
+        if match_results.dim() != 1:
             raise ValueError('match_results should have rank 1')
         if match_results.dtype not in (torch.int32, torch.int64):
             raise ValueError('match_results should be an int32 or int64 scalar tensor')
         self.match_results = match_results
 
-    def _where(self, mask):
-        return torch.nonzero(mask).flatten().long()
-
-    def matched_column_indices(self):
-        return self._where(self.match_results > -1)
-
+    # indicators (bool [N]) and the index lists derived from them
     def matched_column_indicator(self):
-        return self.match_results >= 0
-
-    def num_matched_columns(self):
-        return self.matched_column_indices().numel()
-
-    def unmatched_column_indices(self):
-        return self._where(self.match_results == -1)
+        return self.match_results > UNMATCHED
 
     def unmatched_column_indicator(self):
-        return self.match_results == -1
-
-    def num_unmatched_columns(self):
-        return self.unmatched_column_indices().numel()
-
-    def ignored_column_indices(self):
-        return self._where(self.ignored_column_indicator())
+        return self.match_results == UNMATCHED
 
     def ignored_column_indicator(self):
-        return self.match_results == -2
+        return self.match_results == IGNORED
 
-    def num_ignored_columns(self):
-        return self.ignored_column_indices().numel()
+    def matched_column_indices(self):
+        return self.matched_column_indicator().nonzero().reshape(-1)
 
-    def unmatched_or_ignored_column_indices(self):
-        return self._where(0 > self.match_results)
+    def unmatched_column_indices(self):
+        return self.unmatched_column_indicator().nonzero().reshape(-1)
+
+    def ignored_column_indices(self):
+        return self.ignored_column_indicator().nonzero().reshape(-1)
+
+    def num_matched_columns(self):
+        return int(self.matched_column_indicator().sum())
 
     def matched_row_indices(self):
-        return torch.gather(self.match_results, 0, self.matched_column_indices()).flatten().long()
+        return self.match_results[self.matched_column_indicator()].long()
 
     def gather_based_on_match(self, input_tensor, unmatched_value, ignored_value):
-        """input_tensor[match] for matched columns, the given constants otherwise (matcher.py:151-179)."""
-        if isinstance(ignored_value, torch.Tensor):
-            table = torch.cat([ignored_value, unmatched_value, input_tensor], dim=0)
-        else:
-            head = torch.tensor([ignored_value, unmatched_value], dtype=input_tensor.dtype, device=input_tensor.device)
-            table = torch.cat([head, input_tensor], dim=0)
-        return torch.index_select(table, 0, torch.clamp(self.match_results + 2, min=0).long())
+        """Row ``match`` of ``input_tensor`` for matched columns, the given constants for the others
+        (reference :151-179: one table [ignored, unmatched, rows...] indexed by match + 2)."""
+        def row(v):
+            if isinstance(v, torch.Tensor):
+                return v.to(input_tensor.dtype)
+            return torch.full((1,) + tuple(input_tensor.shape[1:]), v, dtype=input_tensor.dtype, device=input_tensor.device)
+        table = torch.cat([row(ignored_value), row(unmatched_value), input_tensor], dim=0)
+        return table[(self.match_results + 2).clamp(min=0).long()]

@@ -1,3 +1,5 @@
+# Interface modelled on the TF object-detection IouSimilarity (Apache-2.0, The TensorFlow Authors / Ross Wightman's
+# effdet port) -- see NOTICE at the repository root.
 """IoU similarity between two BoxLists on libodk (odk_iou_matrix).
 
 API of the reference's effdet/object_detection/region_similarity_calculator.py:24-101; the

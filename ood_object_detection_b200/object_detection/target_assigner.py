@@ -1,3 +1,5 @@
+# Interface modelled on the TF object-detection TargetAssigner (Apache-2.0, The TensorFlow Authors / Ross
+# Wightman's effdet port) -- see NOTICE at the repository root.
 """TargetAssigner: classification / regression targets for one image's anchors.
 
 API of the reference's effdet/object_detection/target_assigner.py:46-266.  With the
@@ -46,6 +48,10 @@ class TargetAssigner(object):
             raise ValueError('anchors must be an BoxList')
         if not isinstance(groundtruth_boxes, box_list.BoxList):
             raise ValueError('groundtruth_boxes must be an BoxList')
+        # no CPU route: the assignment arithmetic only exists as sm_100a kernels (and CUDA tensor ops for
+        # configurations the kernels do not cover)
+        _lib.require_cuda(anchors.boxes(), 'anchors')
+        _lib.require_cuda(groundtruth_boxes.boxes(), 'groundtruth_boxes')
         if self._fused_ok(groundtruth_boxes, groundtruth_labels):
             return self._assign_fused(anchors, groundtruth_boxes, groundtruth_labels)
         sim = self._similarity_calc.compare(groundtruth_boxes, anchors)

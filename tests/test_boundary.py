@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, name), f'libodk.so does not export {name}'
     # and the python binding table covers exactly the header
     assert sorted(_lib.SIGNATURES) == syms
-    assert _lib.lib().odk_version() == 2
+    assert _lib.lib().odk_version() == 3
     assert _lib.lib().odk_planar_stride(49104) == 49104 and _lib.lib().odk_planar_stride(150381) == 150384
 
 
@@ -43,7 +43,16 @@ def test_abi_argument_errors_without_gpu():
     assert rc == -1 and b'null pointer' in lib.odk_last_error()
     rc = lib.odk_assign(None, None, None, None, 2, 4, hw, 9, 9, 0.5, 1, None, None, None, 0, None)
     assert rc == -1 and b'num_levels' in lib.odk_last_error()
-    assert lib.odk_topk_workspace_bytes(4, 5000) > 4 * 16384 * 8
+    hw5 = _lib.int_array([4096, 1024, 256, 64, 16])
+    assert lib.odk_topk_workspace_bytes(4, 90, hw5, 5, 9, 5000) > 4 * 16384 * 8
+    assert lib.odk_postprocess_workspace_bytes(4, 90, hw5, 5, 9, 5000) > lib.odk_topk_workspace_bytes(4, 90, hw5, 5, 9, 5000)
+    assert 0 < lib.odk_postprocess_flags_offset(4, 90, hw5, 5, 9, 5000) < lib.odk_postprocess_workspace_bytes(4, 90, hw5, 5, 9, 5000)
+    assert lib.odk_postprocess_workspace_bytes(0, 90, hw5, 5, 9, 5000) == 0
+    # odk_postprocess validates sizes before any CUDA call
+    args = [None] * 26
+    rc = lib.odk_postprocess(None, None, 1, 90, hw5, 5, 9, 5000, None, None, None, None, 1.0, None, None, None, None, None, None,
+                             None, None, None, None, None, 0, None)
+    assert rc == -1 and b'null pointer' in lib.odk_last_error()
     assert lib.odk_assign_workspace_bytes(4, 100) >= 4 * 100 * 8
     with pytest.raises(RuntimeError):
         _lib.check(rc)
@@ -210,29 +219,29 @@ def test_bench_wrappers_with_stubbed_kernels(monkeypatch):
 
     calls = {}
 
-    def fake_post_process(cls_outputs, box_outputs, num_levels, num_classes, max_detection_points=5000):
-        calls['pp'] = (cls_outputs, box_outputs, num_levels, num_classes, max_detection_points)
-        return 'cls_k', 'box_k', 'idx', 'klass'
+    def fake_chain(cls_outputs, box_outputs, anchor_boxes, num_levels, num_classes, max_detection_points=5000,
+                   max_det_per_image=100, soft_nms=False, img_scale=None, img_size=None, **kw):
+        calls['det'] = (cls_outputs, box_outputs, tuple(anchor_boxes.shape), num_levels, num_classes, max_detection_points,
+                        max_det_per_image, soft_nms, img_scale, img_size)
+        n = cls_outputs[1]
+        return {'detections': torch.full((n, max_det_per_image, 6), 2.0),
+                'count': torch.full((n,), calls.get('count', max_det_per_image), dtype=torch.int32)}
 
-    def fake_batch_detection(batch_size, class_out, box_out, anchor_boxes, indices, classes, img_scale=None, img_size=None,
-                             max_det_per_image=100, soft_nms=False, pad=False):
-        calls['det'] = (batch_size, class_out, box_out, tuple(anchor_boxes.shape), indices, classes, img_scale, img_size,
-                        max_det_per_image, soft_nms, pad)
-        return 'detections'
-
-    monkeypatch.setattr(B, '_post_process', fake_post_process)
-    monkeypatch.setattr(B, '_batch_detection', fake_batch_detection)
+    monkeypatch.setattr(B, 'post_process_detect', fake_chain)
     x = torch.zeros(3, 3, 128, 128)
 
     pred = B.DetBenchPredict(Model())
     assert (pred.num_levels, pred.num_classes, pred.max_detection_points, pred.max_det_per_image, pred.soft_nms) == (5, 7, 50, 5, True)
     assert pred.config is cfg and tuple(pred.anchors.boxes.shape) == (3069, 4)
-    assert pred(x) == 'detections'
-    assert calls['pp'] == (['cls_levels', 3], ['box_levels'], 5, 7, 50)
-    assert calls['det'] == (3, 'cls_k', 'box_k', (3069, 4), 'idx', 'klass', None, None, 5, True, False)
+    assert tuple(pred(x).shape) == (3, 5, 6)
+    assert calls['det'] == (['cls_levels', 3], ['box_levels'], (3069, 4), 5, 7, 50, 5, True, None, None)
+    calls['count'] = 4          # an image with fewer than max_det rows: the reference's torch.stack raises (bench.py:76)
+    with pytest.raises(RuntimeError, match='equal size'):
+        pred(x)
     pred.pad_detections = True
-    pred(x, {'img_scale': 'scale', 'img_size': 'size'})
-    assert calls['det'][6:] == ('scale', 'size', 5, True, True)
+    assert tuple(pred(x, {'img_scale': 'scale', 'img_size': 'size'}).shape) == (3, 5, 6)
+    assert calls['det'][8:] == ('scale', 'size')
+    calls['count'] = 5
 
     monkeypatch.setattr(B, 'detect_with_ood', lambda *a, **k: ('ood', a[0], a[1], tuple(a[2].shape), a[3:], k))
     assert pred.forward_with_ood(x, {'img_scale': 'scale', 'img_size': 'size'}, temperature=2.0) == \
@@ -261,7 +270,7 @@ def test_bench_wrappers_with_stubbed_kernels(monkeypatch):
     assert seen['loss'] == (['cls_levels', 3], ['box_levels'], [f'c{l}' for l in range(5)], [f'b{l}' for l in range(5)], 'npos')
     train.eval()
     out = train(x, target)
-    assert out['detections'] == 'detections' and calls['det'][6:8] == ('scale', 'size')
+    assert tuple(out['detections'].shape) == (3, 5, 6) and calls['det'][8:] == ('scale', 'size')
     with pytest.raises(AssertionError):
         train(x, {'bbox': None, 'cls': None})
 

@@ -232,3 +232,102 @@ def test_ood_scores_and_fused_entry():
     ref = -2.5 * torch.logsumexp(rows / 2.5, dim=2)
     ok = out['anchor'] >= 0
     np.testing.assert_allclose(e2[ok].cpu().numpy(), ref[ok].cpu().numpy(), rtol=RTOL)
+
+
+# ---- odk_postprocess: the pipelined chain (sample -> persistent stream + per-image tails) ----------------
+def _fused_vs_chain(co, bo, size, C, K, D, soft, scale=None, isz=None, anchor_scale=4.0, ood=False):
+    """post_process_detect must equal (a) the separate odk_topk -> odk_detect launches bit for bit and
+    (b) the oracle chain under the usual bars."""
+    from ood_object_detection_b200.anchors import detect_batch
+    from ood_object_detection_b200.bench import _post_process, post_process_detect
+    B = co[0].shape[0]
+    anc_np = orc.anchor_boxes(3, 7, 3, synth.ASPECTS, anchor_scale, (size, size))
+    tc, tb, ta = [t(x) for x in co], [t(x) for x in bo], t(anc_np)
+    ts = None if scale is None else t(scale)
+    tz = None if isz is None else t(isz)
+    out = post_process_detect(tc, tb, ta, 5, C, K, D, soft, ts, tz, with_ood=ood, return_topk=True)
+    cls_k, box_k, idx, klass = _post_process(tc, tb, 5, C, K)
+    for name, ref in (('cls', cls_k), ('box', box_k), ('indices', idx), ('classes', klass)):
+        assert torch.equal(out[name], ref), name
+    dets, count, src = detect_batch(cls_k, box_k, ta, idx, klass, ts, tz, D, soft)
+    assert torch.equal(out['count'], count)
+    assert torch.equal(out['src'], src)
+    assert torch.equal(out['detections'], dets)
+    anchor = torch.where(src >= 0, torch.gather(idx, 1, src.clamp(min=0).long()), torch.full_like(src, -1).long())
+    assert torch.equal(out['anchor'], anchor)
+    # without the top-k outputs the detections must not change
+    lean = post_process_detect(tc, tb, ta, 5, C, K, D, soft, ts, tz)
+    assert torch.equal(lean['detections'], dets) and torch.equal(lean['count'], count)
+    o_cls, o_box, o_idx, o_klass = orc.post_process(co, bo, 5, C, K)
+    for i in range(B):
+        ref, rsrc = orc.generate_detections(o_cls[i], o_box[i], anc_np, o_idx[i], o_klass[i],
+                                            None if scale is None else scale[i], None if isz is None else isz[i], D, soft,
+                                            return_src=True)
+        n = int(out['count'][i].item())
+        assert n == ref.shape[0]
+        np.testing.assert_array_equal(out['src'][i, :n].cpu().numpy(), rsrc)
+        assert_dets_close(out['detections'][i, :n].cpu().numpy(), ref)
+        assert (out['detections'][i, n:] == 0).all() and (out['src'][i, n:] == -1).all()
+        if ood:
+            rows = orc.gather_logit_rows(co, o_idx[i][rsrc][None].repeat(B, 0), C)[i]
+            e, m = orc.ood_scores(rows, 1.0)
+            np.testing.assert_allclose(out['energy'][i, :n].cpu().numpy(), e, rtol=RTOL)
+            np.testing.assert_array_equal(out['max_logit'][i, :n].cpu().numpy(), m)
+            assert (out['energy'][i, n:] == 0).all()
+    return out
+
+
+@pytest.mark.parametrize('soft', [False, True])
+@pytest.mark.parametrize('sparse', [False, True])
+def test_fused_postprocess_d0(soft, sparse):
+    size, B, C, K, D = 512, 4, 90, 5000, 100
+    co, bo = (synth.planted_outputs if sparse else synth.head_outputs)(310 + sparse, B, size, C)
+    _fused_vs_chain(co, bo, size, C, K, D, soft, ood=True)
+
+
+@pytest.mark.parametrize('soft', [False, True])
+def test_fused_postprocess_d3_odd_level_scaled(soft):
+    """D3's 7x7 level: blocks of odd images start 8 bytes off the 16-byte grid (partial first / last groups);
+    with img_scale / img_size the boxes are clipped and rescaled."""
+    size, B, C, K, D = 896, 3, 90, 5000, 100
+    co, bo = synth.head_outputs(320, B, size, C)
+    scale = np.array([1.0, 1.25, 1.5], np.float32)
+    isz = np.array([[size * 1.1, size * 0.9]] * B, np.float32)
+    _fused_vs_chain(co, bo, size, C, K, D, soft, scale, isz)
+
+
+@pytest.mark.parametrize('name,B,C,K,D', [('d0', 3, 1, 2000, 30), ('d0', 1, 400, 5000, 100), ('d0', 5, 7, 6144, 64),
+                                          ('d0', 2, 90, 300, 100)])
+def test_fused_postprocess_shapes(name, B, C, K, D):
+    size, _ = synth.MODEL_SHAPES[name]
+    co, bo = synth.head_outputs(330 + B + C, B, size, C)
+    _fused_vs_chain(co, bo, size, C, K, D, False)
+    _fused_vs_chain(co, bo, size, C, K, D, True)
+
+
+def test_fused_postprocess_small_and_degenerate():
+    """Tiny pyramids (fewer tasks than warps), images that leave the sampled path (constant, quantised, a
+    huge tied plateau -> flagged, exact radix select + stand-alone detect behind the same entry point) next
+    to ordinary ones in one batch."""
+    size, B, C, K, D = 256, 5, 20, 3000, 50
+    co, bo = synth.head_outputs(71, B, size, C, tie_free=False)
+    for c in co:
+        c[0] = -4.5
+        c[1] = np.round(c[1] * 2) / 2
+        c[2] = np.where(c[2] > -4.6, np.float32(1.25), c[2])
+    synth.make_tie_free([c[3:] for c in co])
+    out = _fused_vs_chain(co, bo, size, C, K, D, False, ood=True)
+    _fused_vs_chain(co, bo, size, C, K, D, True)
+    assert out['count'].shape == (B,)
+    co, bo = synth.head_outputs(72, 2, 128, 3)
+    _fused_vs_chain(co, bo, 128, 3, 200, 20, False)
+    _fused_vs_chain(co, bo, 128, 3, 1000, 20, True)
+
+
+def test_fused_postprocess_above_register_budget_uses_chain():
+    from ood_object_detection_b200.bench import post_process_detect, FUSED_MAX_K
+    size, B, C = 512, 2, 90
+    co, bo = synth.head_outputs(340, B, size, C)
+    anc = anchors_t(size)
+    out = post_process_detect([t(x) for x in co], [t(x) for x in bo], anc, 5, C, FUSED_MAX_K + 1000, 100, False)
+    assert out['detections'].shape == (B, 100, 6) and int(out['count'].min()) > 0
