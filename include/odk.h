@@ -201,7 +201,10 @@ typedef struct odk_detect_params {
     float soft_sigma;       /* 0.5  */
     float soft_iou;         /* 0.3  (unused by the gaussian method) */
     float soft_score_thr;   /* 0.001 */
+    int32_t pipeline;       /* odk_postprocess only: ODK_PIPELINE_STAGED (default) or ODK_PIPELINE_PERSISTENT */
 } odk_detect_params;
+#define ODK_PIPELINE_STAGED 0       /* sample -> one-wave collect -> one tail CTA per image */
+#define ODK_PIPELINE_PERSISTENT 1   /* sample -> one persistent kernel: image-major stream, tails overlap the later images */
 
 int odk_detect(const float *cls_topk, const float *box_topk, const int64_t *indices, const int64_t *classes, int B,
                int N, const float *anchors, int64_t A, const float *img_scale, const float *img_size,
@@ -221,6 +224,10 @@ size_t odk_postprocess_workspace_bytes(int B, int C, const int32_t *level_hw, in
 /* Diagnostics: byte offset inside the workspace of a uint32 [B] array that holds, after the call, 1 for every
  * image that left the sampled-threshold path (exact radix select + stand-alone detect), else 0. */
 size_t odk_postprocess_flags_offset(int B, int C, const int32_t *level_hw, int num_levels, int na, int K);
+/* Diagnostics: byte offset of a uint64 [B*8 + 2] array of %globaltimer nanoseconds: per image {its last logit was
+ * streamed, a CTA took its tail, the tail started, the tail ended, select done, filter + decode done, class offsets
+ * done, suppression done}; then the start and the end of the kernel. */
+size_t odk_postprocess_timeline_offset(int B, int C, const int32_t *level_hw, int num_levels, int na, int K);
 int odk_postprocess(const void *const *cls_levels, const void *const *box_levels, int B, int C, const int32_t *level_hw,
                     int num_levels, int na, int K, const float *anchors, const float *img_scale, const float *img_size,
                     const odk_detect_params *params, float temperature, float *dets, int32_t *count, int32_t *src,

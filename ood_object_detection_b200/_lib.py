@@ -33,7 +33,8 @@ class LossParams(ctypes.Structure):
 
 class DetectParams(ctypes.Structure):
     _fields_ = [('max_det', ctypes.c_int32), ('soft_nms', ctypes.c_int32), ('score_min', c_float),
-                ('nms_iou', c_double), ('soft_sigma', c_float), ('soft_iou', c_float), ('soft_score_thr', c_float)]
+                ('nms_iou', c_double), ('soft_sigma', c_float), ('soft_iou', c_float), ('soft_score_thr', c_float),
+                ('pipeline', ctypes.c_int32)]
 
 
 # every symbol include/odk.h declares: name -> (restype, argtypes)
@@ -63,6 +64,7 @@ SIGNATURES = {
                            _P]),
     'odk_postprocess_workspace_bytes': (c_size_t, [c_int, c_int, _P, c_int, c_int, c_int]),
     'odk_postprocess_flags_offset': (c_size_t, [c_int, c_int, _P, c_int, c_int, c_int]),
+    'odk_postprocess_timeline_offset': (c_size_t, [c_int, c_int, _P, c_int, c_int, c_int]),
     'odk_postprocess': (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, ctypes.POINTER(DetectParams), c_float,
                                 _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     'odk_soft_nms': (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, c_int, _P, _P, _P, _P]),

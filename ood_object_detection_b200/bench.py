@@ -72,14 +72,15 @@ FUSED_MAX_K = 6144   # odk_postprocess keeps K sorted keys in registers (6 per t
 
 def post_process_detect(cls_outputs, box_outputs, anchor_boxes, num_levels, num_classes, max_detection_points=5000,
                         max_det_per_image=100, soft_nms=False, img_scale=None, img_size=None, with_ood=False,
-                        temperature=1.0, return_topk=False, return_flags=False):
+                        temperature=1.0, return_topk=False, return_flags=False, pipeline='staged'):
     """``_post_process`` + ``_batch_detection`` (+ OOD scores) as ONE pipelined odk_postprocess call
     (reference bench.py:93-100): the logits are streamed image-major by a persistent kernel and each
     image's select / decode / suppression / OOD chain runs while the later images are still streaming.
 
     Returns dict(detections [B, D, 6] zero padded, count [B] int32, src [B, D] int32 rank in the top-k
     list, anchor [B, D] int64; with_ood: energy, max_logit [B, D]; return_topk: cls [B,K,1], box [B,K,4],
-    indices, classes [B,K])."""
+    indices, classes [B,K]).  ``pipeline``: 'staged' (sample -> one-wave collect -> one tail CTA per image) or
+    'persistent' (one persistent kernel, the tails overlap the stream of the later images); same results."""
     lib = _lib.lib()
     cls_l = _prep_levels(cls_outputs, num_levels)
     box_l = _prep_levels(box_outputs, num_levels)
@@ -118,7 +119,8 @@ def post_process_detect(cls_outputs, box_outputs, anchor_boxes, num_levels, num_
         klass = torch.empty((B, K), dtype=torch.int64, device=dev)
     scale = None if img_scale is None else img_scale.to(dev, torch.float32).reshape(B).contiguous()
     size = None if img_size is None else img_size.to(dev, torch.float32).reshape(B, 2).contiguous()
-    params = _lib.DetectParams(D, int(bool(soft_nms)), float(np.float32(0.01)), 0.3, 0.5, 0.3, float(np.float32(0.001)))
+    params = _lib.DetectParams(D, int(bool(soft_nms)), float(np.float32(0.01)), 0.3, 0.5, 0.3, float(np.float32(0.001)),
+                               {'staged': 0, 'persistent': 1}[pipeline])
     hw_arr = _lib.int_array(hw)
     ws_bytes = lib.odk_postprocess_workspace_bytes(B, int(num_classes), hw_arr, num_levels, na, K)
     ws = torch.empty(((ws_bytes + 15) // 16 * 2,), dtype=torch.int64, device=dev)
@@ -136,6 +138,8 @@ def post_process_detect(cls_outputs, box_outputs, anchor_boxes, num_levels, num_
     if return_flags:   # diagnostics: 1 = the image left the sampled-threshold path (exact select)
         off = lib.odk_postprocess_flags_offset(B, int(num_classes), hw_arr, num_levels, na, K)
         out['flags'] = ws.view(torch.int32)[off // 4:off // 4 + B]
+        off = lib.odk_postprocess_timeline_offset(B, int(num_classes), hw_arr, num_levels, na, K)
+        out['timeline'] = ws[off // 8:off // 8 + 16 * B + 2]   # ns: [B, 16] marks (odk_post.cu PostArgs.timeline), kernel start, end
     return out
 
 

@@ -29,7 +29,7 @@ __device__ __forceinline__ DetSmem carve(unsigned char *raw, int cap) {
     return s;
 }
 static inline size_t det_base_bytes(int cap) { return (size_t)cap * 24 + (size_t)(cap / 32) * 4 + 16; }
-static inline size_t det_smem_bytes(int cap) { return det_base_bytes(cap) + 8192; }   // + hard-NMS window masks
+static inline size_t det_smem_bytes(int cap) { return det_base_bytes(cap) + 2048; }   // + hard-NMS window masks
 
 // decode_box_outputs(output_xyxy=True) + optional clip, reference anchors.py:51-92 (fp32 op order)
 __device__ __forceinline__ float4 decode_xyxy(float4 a, float4 r, bool clip, float lim_x, float lim_y) {
@@ -95,35 +95,37 @@ __device__ __forceinline__ bool nms_hit(float4 p, float ap, float4 q, float thr_
 }
 
 // Window bitmask: the candidates are taken kNmsWin at a time in score order.  For a window, (1) every candidate
-// is tested against everything kept in EARLIER windows (4 threads share a candidate), (2) the suppression mask
-// of the still-alive candidates among themselves is computed by the whole block (row i, bit c: kept i would
-// suppress the later candidate c), and (3) one thread replays the greedy rule over the alive bits in order --
-// keep the first alive candidate, clear everything its row suppresses, repeat -- which is exactly the
-// one-at-a-time loop of torchvision::nms restricted to the window.  Only the first max_keep survivors are
-// ever used (anchors.py:153), so the walk stops there: typically inside the first window (~6 us) instead of
-// ~max_keep/16 rounds of two block barriers with a dependent one-warp chain in between (31 us).
-constexpr int kNmsWin = 256;
+// is tested against everything kept in EARLIER windows (8 threads share a candidate), (2) the suppression mask
+// of the still-alive candidates among themselves is built by the whole block -- a warp per row, its lanes test 32
+// later candidates at once and a ballot is the mask word (row i, bit c: kept i would suppress the later
+// candidate c) -- and (3) one thread replays the greedy rule over the alive bits in order: keep the first alive
+// candidate, clear everything its row suppresses, repeat -- which is exactly the one-at-a-time loop of
+// torchvision::nms restricted to the window.  Only the first max_keep survivors are ever used (anchors.py:153),
+// so the walk stops there: typically after one or two windows (~7 us) instead of ~max_keep/16 rounds of two
+// block barriers with a dependent one-warp chain in between (31 us).
+constexpr int kNmsWin = 128;
 constexpr int kNmsWinWords = kNmsWin / 32;
-
-constexpr size_t kNmsMaskBytes = (size_t)kNmsWin * kNmsWinWords * 4;   // 8 KB of (dynamic) shared memory from the caller
+constexpr int kNmsParts = kDetWarps / kNmsWinWords;   // threads that share a candidate in step 1
+constexpr size_t kNmsMaskBytes = (size_t)kNmsWin * kNmsWinWords * 4;   // 2 KB of (dynamic) shared memory from the caller
 
 static __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int max_keep, int *kept, unsigned *mask_mem) {
     unsigned (*s_mask)[kNmsWinWords] = reinterpret_cast<unsigned (*)[kNmsWinWords]>(mask_mem);
-    __shared__ unsigned s_dead[4][kNmsWinWords];
+    __shared__ unsigned s_dead[kNmsParts][kNmsWinWords];
     __shared__ unsigned s_alive[kNmsWinWords];
     __shared__ int s_count;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int count = 0;
     for (int base = 0; base < n && count < max_keep; base += kNmsWin) {
         const int W = min(kNmsWin, n - base);
-        // 1. against everything kept in earlier windows: warp -> (word of the window, quarter of the kept list)
-        if (warp < 4 * kNmsWinWords) {
-            const int word = warp & (kNmsWinWords - 1), part = warp / kNmsWinWords;
+        const int nwords = (W + 31) / 32;
+        // 1. against everything kept in earlier windows: warp -> (word of the window, slice of the kept list)
+        {
+            const int word = warp % kNmsWinWords, part = warp / kNmsWinWords;
             const int c = word * 32 + lane;
             bool dead = false;
             if (c < W && count > 0) {
                 const float4 q = S.box[base + c];
-                for (int j = part; j < count && !dead; j += 4) {
+                for (int j = part; j < count && !dead; j += kNmsParts) {
                     const float4 p = S.box[kept[j]];
                     dead = nms_hit(p, __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y)), q, thr_f);
                 }
@@ -135,27 +137,25 @@ static __device__ int hard_nms_rounds(const DetSmem &S, int n, float thr_f, int 
         if (tid < kNmsWinWords) {
             const int lo = tid * 32;
             const unsigned valid = lo + 32 <= W ? 0xFFFFFFFFu : (lo < W ? ((1u << (W - lo)) - 1u) : 0u);
-            s_alive[tid] = valid & ~(s_dead[0][tid] | s_dead[1][tid] | s_dead[2][tid] | s_dead[3][tid]);
+            unsigned d = 0u;
+#pragma unroll
+            for (int p = 0; p < kNmsParts; ++p) d |= s_dead[p][tid];
+            s_alive[tid] = valid & ~d;
         }
         __syncthreads();
-        // 2. suppression masks inside the window: only alive rows, only alive candidates after the row
-        for (int e = tid; e < kNmsWin * kNmsWinWords; e += blockDim.x) {
-            const int row = e / kNmsWinWords, word = e % kNmsWinWords;
-            unsigned m = 0u;
-            if (row < W && ((s_alive[row >> 5] >> (row & 31)) & 1u) && word >= (row >> 5)) {
-                unsigned cand = s_alive[word];
-                if (word == (row >> 5)) cand &= ~(0xFFFFFFFFu >> (31 - (row & 31)));   // strictly after the row
-                if (cand) {
-                    const float4 p = S.box[base + row];
-                    const float ap = __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y));
-                    while (cand) {
-                        const int bit = __ffs(cand) - 1;
-                        cand &= cand - 1u;
-                        if (nms_hit(p, ap, S.box[base + word * 32 + bit], thr_f)) m |= 1u << bit;
-                    }
-                }
+        // 2. suppression masks inside the window: alive rows only, words from the row's own word on (the scan
+        //    below reads nothing else)
+        for (int row = warp; row < W; row += kDetWarps) {
+            if (!((s_alive[row >> 5] >> (row & 31)) & 1u)) continue;   // warp-uniform
+            const float4 p = S.box[base + row];
+            const float ap = __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y));
+            for (int word = row >> 5; word < nwords; ++word) {
+                const int c = word * 32 + lane;
+                bool hit = c > row && ((s_alive[word] >> lane) & 1u);
+                if (hit) hit = nms_hit(p, ap, S.box[base + c], thr_f);
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) s_mask[row][word] = m;
             }
-            s_mask[row][word] = m;
         }
         __syncthreads();
         // 3. the greedy rule over the alive bits in score order

@@ -19,6 +19,8 @@
 //              then return to the queue.  Nothing ever waits on another CTA.
 // Images whose candidate count leaves [K, kCap] (constant / heavily tied logits) are only flagged here; the
 // exact cluster radix select of odk_topk.cu and the stand-alone detect kernel pick them up afterwards.
+#include <stdlib.h>
+
 #include "odk_stream.cuh"
 #include "odk_detect.cuh"
 
@@ -26,22 +28,29 @@ namespace cg = cooperative_groups;
 
 namespace odk {
 
+__device__ __forceinline__ unsigned long long global_ns() {   // (stamp() of odk_topk.cuh for the per-image marks)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 constexpr int kPostThreads = 1024;
 constexpr int kPostWarps = kPostThreads / 32;
-constexpr int kWarpStage = 48;        // staged hits per warp and task (~2.6 expected)
+constexpr int kWarpStage = 24;        // staged hits per warp, task and buffer (~2.6 expected)
 constexpr int kPostKeys = 6;          // sorted keys per thread: K <= 6144
 constexpr int kPostMaxK = kPostKeys * kPostThreads;
-constexpr int kSampleThreads = 256;
+constexpr int kSampleThreads = 512;
 constexpr int kSampleWarps = kClusterSize * (kSampleThreads / 32);
 
 // ---- sample ---------------------------------------------------------------------------------------------
-// Task t of image b contributes its 512-byte unit j = hash(b, t) >> 26 when j < 32 (and the unit exists), so
-// every unit is taken with probability 1/64.  Lane maxima over `tps` consecutive tasks form one slot group.
+// Task t of image b contributes its 512-byte unit j = hash(b, t) >> (32 - shift) when j < 64 (and the task has that
+// many), so every unit is taken with probability 2^-shift.  Lane maxima over `tps` consecutive tasks form one slot group.
 // The slots live in the shared memory of the cluster's leader CTA: the other CTAs merge their maxima into
 // them with distributed-shared-memory atomics, so the threshold statistics never touch global memory.
+static_assert(kUnitsPerTask <= (1 << kSampleShift), "one sampled unit per task at most");
 constexpr int kSampleBatch = 8;   // 128-bit loads per lane in flight
 
-__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSampleThreads)
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSampleThreads, 2)
 sample_kernel(const __grid_constant__ SampleLaunch S) {
     extern __shared__ unsigned s_slots[];   // leader only: [nslots]
     cg::cluster_group cluster = cg::this_cluster();
@@ -66,8 +75,8 @@ sample_kernel(const __grid_constant__ SampleLaunch S) {
         {
             const int t = t0 + lane;
             if (t < ntask) {
-                const unsigned j = stream_hash((unsigned)b, (unsigned)t) >> 26;
-                if (j < 32u) {
+                const unsigned j = stream_hash((unsigned)b, (unsigned)t) >> (32 - S.shift);   // 1 unit of 2^shift
+                if (j < (unsigned)kUnitsPerTask) {
                     const STask k = stream_task(S.G, b, t);
                     const int g = k.g0 + (int)j * 32;
                     const int lo = max(k.f0 - g, 0), hi = min(k.f1 - g, 32);
@@ -115,13 +124,17 @@ sample_kernel(const __grid_constant__ SampleLaunch S) {
     }
     cluster.sync();   // every maximum has landed in the leader's slots
     if (rank == 0) {
-        const unsigned thr = threshold_from_slots<kSampleThreads>(s_slots, nslots, S.N, S.K);
+        const uint2 thr = threshold_from_slots<kSampleThreads>(s_slots, nslots, S.N, S.K, S.shift);
         if (threadIdx.x == 0) {
-            S.thr[b] = (S.N <= kCap) ? 0u : thr;
+            S.thr[b] = (S.N <= kCap) ? 0u : thr.x;
+            S.thr_hi[b] = thr.y;
             if (S.zero0) S.zero0[b] = 0u;
             if (S.zero1) S.zero1[b] = 0u;
             if (S.zero2) S.zero2[b] = 0u;
-            if (b == 0 && S.zero_scalar) *S.zero_scalar = 0u;
+            if (S.zero3) S.zero3[b] = 0u;
+            if (b == 0 && S.zero_scalar)
+                for (int i = 0; i < S.zero_scalars; ++i) S.zero_scalar[i] = 0u;
+            if (b == 0 && S.zero_u64) *S.zero_u64 = 0ull;
         }
     }
 }
@@ -132,6 +145,13 @@ struct PostArgs {
     TopkArgs T;               // geometry, box levels, K, thr / cnt / flag / cand, top-k outputs (always valid)
     int emit_topk;            // also write the top-k tensors of every image (the caller asked for them)
     unsigned *queue, *done;   // next task; completed tasks per image
+    unsigned *tq_img;         // [B] completed images in completion order (image + 1; 0 = not yet published)
+    unsigned *tq_pushed, *tq_claimed;   // completed images; images some CTA has taken the tail of
+    int chunk, ahead;                   // tasks per global queue access (power of two); chunks the bookkeeper stays ahead
+    int debug_skip_tails;               // diagnostics (ODK_POST_SKIP_TAILS=1): stream only, every image is left to the exact path
+    unsigned long long *timeline;       // [B][kStampSlots] globaltimer ns: 0 stream complete, 1 tail claimed, 2 tail start, 3 tail end,
+                                        // 4 select done, 5 filter + compaction, 6 gathers + decode, 7 class offsets, 8 suppression,
+                                        // 9-12 inside select: histogram, scans, scatter, ranks; then kernel start, kernel end
     unsigned total_tasks;
     const float4 *anchors;
     const float *scale, *size;
@@ -148,7 +168,8 @@ struct PostArgs {
 static inline size_t post_det_bytes(int cap) { return (size_t)cap * 26 + (size_t)(cap / 32) * 4 + 16 + kNmsMaskBytes; }
 
 // rows of one image out of the sorted keys each thread holds (rank = tid + k * 1024)
-static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned long long (&keys)[kPostKeys], unsigned char *raw) {
+static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned long long (&keys)[kPostKeys],
+                                     const int (&cpos)[kPostKeys], unsigned char *raw) {
     __shared__ int s_cnt[kPostKeys * kPostWarps + 1];
     __shared__ float s_wmax[kPostWarps];
     __shared__ int s_kept[1024];
@@ -195,6 +216,7 @@ static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned lo
         if (lane == 31) s_cnt[kPostKeys * kPostWarps] = inc;
     }
     __syncthreads();
+    stamp(P.timeline, b, 5);
     const int n = s_cnt[kPostKeys * kPostWarps];
     int kept_n = 0;
     if (n > 0) {   // uniform
@@ -214,7 +236,8 @@ static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned lo
                     const unsigned flat = ~(unsigned)(keys[k] & 0xFFFFFFFFull);
                     const int anchor = (int)fd_div(flat, P.T.div_C);
                     an[j] = __ldg(P.anchors + anchor);
-                    rg[j] = gather_box(P.T, b, anchor);
+                    // the collect stage left every candidate's regression row next to its key: one sector instead of four
+                    rg[j] = cpos[k] >= 0 ? __ldcg(P.T.cand_box + (size_t)b * kCap + cpos[k]) : gather_box(P.T, b, anchor);
                 }
             }
 #pragma unroll
@@ -235,6 +258,7 @@ static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned lo
         if (lane == 0) s_wmax[warp] = mx;
         init_alive(alive, n, cap);
         __syncthreads();
+        stamp(P.timeline, b, 6);
         mx = s_wmax[0];
         for (int w = 1; w < kPostWarps; ++w) mx = fmaxf(mx, s_wmax[w]);
         const float mul = __fadd_rn(mx, 1.0f);
@@ -250,6 +274,7 @@ static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned lo
             }
         }
         __syncthreads();
+        stamp(P.timeline, b, 7);
         // 4. suppression, first D survivors (the candidates are in descending score order by construction)
         DetSmem S;
         S.box = sbox; S.score = sscore; S.src = nullptr; S.alive = alive;
@@ -259,6 +284,7 @@ static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned lo
         else
             kept_n = hard_nms_rounds(S, n, P.nms_thr_f, D, s_kept, alive + cap / 32 + 4);
         __syncthreads();
+        stamp(P.timeline, b, 8);
     }
     // 5. rows: boxes (re-decoded, unoffset) * img_scale, score, class + 1 (anchors.py:153-166)
     float *dets = P.dets + (size_t)b * D * 6;
@@ -297,33 +323,41 @@ static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned lo
 }
 
 template <int E>
-__device__ __forceinline__ void load_sorted(const unsigned long long *s, int K, unsigned long long (&keys)[kPostKeys]) {
+__device__ __forceinline__ void load_sorted(const unsigned long long *s, const unsigned short *srcpos, int K,
+                                            unsigned long long (&keys)[kPostKeys], int (&cpos)[kPostKeys]) {
 #pragma unroll
     for (int k = 0; k < kPostKeys; ++k) {
         const int i = threadIdx.x + k * kPostThreads;
         keys[k] = i < K ? sorted_at<E>(s, i) : 0ull;
+        cpos[k] = (i < K && srcpos) ? (int)srcpos[i] : -1;   // -1: position unknown (bitonic paths), gather from the level
     }
 }
 
 // everything of image b that is not streaming, by the whole CTA
 static __device__ void run_tail(const PostArgs &P, int b, unsigned long long *s) {
+    stamp(P.timeline, b, 2);
     __threadfence();   // acquire side of the done-counter hand-off: the candidates of every other SM are visible
     const unsigned n = __ldcg(P.T.cnt + b);
-    if (n < (unsigned)P.T.K || n > (unsigned)kCap) {   // uniform: the exact path (odk_topk.cu) takes this image
+    if (n < (unsigned)P.T.K || n > (unsigned)kCap || P.debug_skip_tails) {   // uniform: the exact path (odk_topk.cu) takes this image
         if (threadIdx.x == 0) P.T.flag[b] = 1u;
         return;
     }
     unsigned long long keys[kPostKeys];
+    int cpos[kPostKeys];
     const Refined R = refine_candidates(P.T, b, (int)n, s);
+    if (threadIdx.x == 0 && P.timeline) {
+        P.timeline[(size_t)b * kStampSlots + 13] = n;
+        P.timeline[(size_t)b * kStampSlots + 14] = (unsigned long long)R.m | (R.ranked ? 1ull << 32 : 0ull);
+    }
     if (R.ranked) {
         if (P.emit_topk) emit_topk<0, true>(P.T, b, s + kSortSlots);
-        load_sorted<0>(s + kSortSlots, P.T.K, keys);
+        load_sorted<0>(s + kSortSlots, P.T.cand_box ? R.srcpos : nullptr, P.T.K, keys, cpos);
     } else if (R.m <= kSortSlots) {
         for (int i = R.m + threadIdx.x; i < kSortSlots; i += blockDim.x) s[i] = 0ull;
         __syncthreads();
         block_sort_desc<8>(s);
         if (P.emit_topk) emit_topk<8, true>(P.T, b, s);
-        load_sorted<8>(s, P.T.K, keys);
+        load_sorted<8>(s, nullptr, P.T.K, keys, cpos);
     } else {   // more than 8192 keys tie inside one sub-bin: sort everything
         const unsigned long long *cand = P.T.cand + (size_t)b * kCap;
         __syncthreads();
@@ -331,62 +365,232 @@ static __device__ void run_tail(const PostArgs &P, int b, unsigned long long *s)
         __syncthreads();
         block_sort_desc<16>(s);
         if (P.emit_topk) emit_topk<16, true>(P.T, b, s);
-        load_sorted<16>(s, P.T.K, keys);
+        load_sorted<16>(s, nullptr, P.T.K, keys, cpos);
     }
     __syncthreads();   // the keys are in registers: the buffer becomes the detection arrays
-    detect_sorted(P, b, keys, reinterpret_cast<unsigned char *>(s));
+    stamp(P.timeline, b, 4);
+    detect_sorted(P, b, keys, cpos, reinterpret_cast<unsigned char *>(s));
+    stamp(P.timeline, b, 3);
 }
+
+// Staged pipeline: the tails of all images as one launch after the collect kernel of odk_topk.cu
+__global__ void __launch_bounds__(kPostThreads, 1) post_tail_kernel(const __grid_constant__ PostArgs P) {
+    extern __shared__ __align__(16) unsigned long long s_dyn[];
+    run_tail(P, (int)blockIdx.x, s_dyn);
+}
+
+// Streaming warps only ever touch shared memory between tasks; everything that needs a global round trip is
+// done by ONE warp per CTA, the bookkeeper, and aggregated, because 4.6 k warps hammering single addresses
+// (a task counter, an image's candidate and completion counters) is what limits a naive scheme (measured: one
+// atomicAdd per task on one queue word caps the kernel at ~5.7 ns per 16 KB task = 2.9 TB/s):
+//   tasks          : the bookkeeper takes CHUNKS of consecutive tasks from the global queue (one atomic per
+//                    256 KB) and keeps two chunks ahead; streaming warps draw tickets from a shared counter;
+//   streaming warp : stages its hits in one of its private buffers, posts a record {image, hits, warp, buffer}
+//                    into the CTA's ring and goes on with the next task in the next buffer;
+//   bookkeeper     : lane i takes record i; lanes of the same image combine: one atomicAdd on the image's
+//                    candidate counter, the warp copies the staged hits to the candidate list, frees the
+//                    buffers, fences once, one atomicAdd on the image's completed-task counter -- the lane that
+//                    completes an image queues the image's tail for this CTA.
+constexpr int kBookWarp = kPostWarps - 1;
+constexpr int kStreamWarps = kPostWarps - 1;
+constexpr int kStageBufs = 4;         // staging buffers per streaming warp: a buffer is free again ~2 bookkeeper rounds after its task
+constexpr int kRecCap = 256;          // ring of task records (at most kStageBufs per streaming warp are outstanding)
+constexpr int kChunkRing = 16;        // published chunk bases (the bookkeeper is at most `ahead` + 1 chunks ahead)
 
 __global__ void __launch_bounds__(kPostThreads, 1) post_fused_kernel(const __grid_constant__ PostArgs P) {
     extern __shared__ __align__(16) unsigned long long s_dyn[];
-    __shared__ unsigned long long s_wst[kPostWarps][kWarpStage];
-    __shared__ unsigned s_wn[kPostWarps];
+    // the staging buffers alias the head of the dynamic buffer: the CTA only meets for a tail once every record is
+    // flushed, i.e. while all of them are empty
+    unsigned long long (*s_wst)[kStageBufs][kWarpStage] = reinterpret_cast<unsigned long long (*)[kStageBufs][kWarpStage]>(s_dyn);
+    __shared__ unsigned s_wn[kStreamWarps];
+    __shared__ unsigned s_busy[kStreamWarps][kStageBufs];
+    __shared__ unsigned s_rec[kRecCap], s_rec_seq[kRecCap];
+    __shared__ unsigned s_rec_head, s_arrived, s_drained;
+    __shared__ unsigned s_ticket, s_chunks, s_chunk_base[kChunkRing];
     __shared__ int s_tailq[64];
     __shared__ unsigned s_tail_n, s_tail_done;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_tail_n = 0u; s_tail_done = 0u; }
-    if (tid < kPostWarps) s_wn[tid] = 0u;
+    if (tid == 0) { s_tail_n = 0u; s_tail_done = 0u; s_rec_head = 0u; s_arrived = 0u; s_drained = 0u; s_ticket = 0u; s_chunks = 0u; }
+    if (tid < kStreamWarps) {
+        s_wn[tid] = 0u;
+        for (int i = 0; i < kStageBufs; ++i) s_busy[tid][i] = 0u;
+    }
+    for (int i = tid; i < kRecCap; i += kPostThreads) s_rec_seq[i] = 0u;
     __syncthreads();
 
     const unsigned total = P.total_tasks;
     const int ntask = P.G.ntask_img;
-    auto grab = [&]() {
-        unsigned t = 0u;
-        if (lane == 0) t = atomicAdd(P.queue, 1u);
-        return __shfl_sync(0xffffffffu, t, 0);
-    };
-    // A task a warp holds but has not streamed yet keeps its image open, so no warp may sit on one while its
-    // CTA runs a tail (the image would wait for the tail, and the CTA would then finish -- and inherit the tail
-    // of -- every following image too): the next task is only taken ahead of time while no hand-off is pending.
-    constexpr unsigned kNoTask = 0xFFFFFFFFu;
+    if (blockIdx.x == 0 && tid == 0) P.timeline[(size_t)P.T.B * kStampSlots] = global_ns();
     auto tail_pending = [&]() {
         unsigned p = 0u;
         if (lane == 0) p = *(volatile unsigned *)&s_tail_n != *(volatile unsigned *)&s_tail_done;
         return __shfl_sync(0xffffffffu, p, 0) != 0u;
     };
+    // meeting point of the CTA: every image it has taken is processed by all 32 warps; returns true when every
+    // streaming warp is out of tasks and the bookkeeper has seen every image of the batch taken by some CTA
+    auto meet = [&](bool drained) {
+        __syncthreads();   // all 32 warps are here: nobody is streaming, every record is flushed, the queue is stable
+        const unsigned n1 = s_tail_n, d0 = s_tail_done;
+        for (unsigned i = d0; i != n1; ++i) run_tail(P, s_tailq[i & 63u], s_dyn);
+        __syncthreads();
+        if (tid == 0) { s_tail_done = n1; s_arrived = 0u; }
+        return __syncthreads_and(drained ? 1 : 0) != 0;
+    };
+
+    if (warp == kBookWarp) {
+        // ---- bookkeeper ----
+        unsigned tail = 0u, chunks = 0u;
+        bool exhausted = false;
+        for (;;) {
+            // keep the CTA kChunksAhead chunks of tasks ahead of its ticket counter (past the end of the queue the
+            // chunks are still published: their tasks are >= total, which is how the streaming warps learn to stop)
+            while (chunks < *(volatile unsigned *)&s_ticket / (unsigned)P.chunk + (unsigned)P.ahead) {
+                unsigned base = total;
+                if (!exhausted) {
+                    if (lane == 0) base = atomicAdd(P.queue, (unsigned)P.chunk);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    exhausted = base >= total;
+                }
+                if (lane == 0) {
+                    s_chunk_base[chunks % kChunkRing] = base;
+                    __threadfence_block();
+                    *(volatile unsigned *)&s_chunks = chunks + 1u;
+                }
+                ++chunks;
+            }
+            const unsigned head = *(volatile unsigned *)&s_rec_head;
+            const unsigned take = min(head - tail, 32u);
+            // Any CTA may run the tail of any completed image (if the CTA that reports an image's last task always
+            // ran it, the CTA that is last once would be last for every later image too and run all their tails in
+            // series): take one from the global queue unless this CTA already has one.
+            bool all_taken = false;
+            if (*(volatile unsigned *)&s_tail_n == *(volatile unsigned *)&s_tail_done) {
+                unsigned img1 = 0u;
+                if (lane == 0) {
+                    const unsigned claimed = __ldcg(P.tq_claimed), pushed = __ldcg(P.tq_pushed);
+                    all_taken = claimed >= (unsigned)P.T.B;
+                    if (claimed < pushed && atomicCAS(P.tq_claimed, claimed, claimed + 1u) == claimed) {
+                        while ((img1 = __ldcg(P.tq_img + claimed)) == 0u) __nanosleep(50);   // published right after the count
+                        __threadfence();   // acquire: the image's candidates
+                        P.timeline[(size_t)(img1 - 1u) * kStampSlots + 1] = global_ns();
+                        const unsigned q = atomicAdd(&s_tail_n, 1u);
+                        s_tailq[q & 63u] = (int)(img1 - 1u);
+                    }
+                }
+                all_taken = __shfl_sync(0xffffffffu, all_taken ? 1 : 0, 0) != 0;
+            }
+            if (take == 0u) {
+                // nothing to flush: join the streaming warps once all of them wait at the meeting point -- for a tail,
+                // or at the very end (all drained, every image taken by some CTA)
+                if (*(volatile unsigned *)&s_arrived == (unsigned)kStreamWarps) {
+                    if (*(volatile unsigned *)&s_rec_head != tail) continue;   // a record slipped in before the last arrival
+                    const bool pending = *(volatile unsigned *)&s_tail_n != *(volatile unsigned *)&s_tail_done;
+                    const bool finished = *(volatile unsigned *)&s_drained == (unsigned)kStreamWarps && all_taken;
+                    if (pending || finished) {
+                        if (meet(finished)) {
+                            if (lane == 0) atomicMax(P.timeline + (size_t)P.T.B * kStampSlots + 1, global_ns());
+                            break;
+                        }
+                    } else {
+                        __nanosleep(200);   // drained, but some image is still open elsewhere: keep polling the queue
+                    }
+                } else {
+                    __nanosleep(100);
+                }
+                continue;
+            }
+            const unsigned active = take >= 32u ? 0xFFFFFFFFu : ((1u << take) - 1u);
+            unsigned rec = 0xFFFF0000u;   // idle lanes: an image number no record can carry (B <= 65535)
+            if ((unsigned)lane < take) {
+                const unsigned slot = (tail + (unsigned)lane) % kRecCap;
+                while (*(volatile unsigned *)&s_rec_seq[slot] != tail + (unsigned)lane + 1u) { }   // written right after the claim
+                rec = s_rec[slot];
+            }
+            const unsigned rb = rec >> 16, rn = (rec >> 8) & 0xFFu, rw = (rec >> 3) & 0x1Fu, rbuf = rec & 7u;
+            // lanes of the same image combine: hits before mine, hits and tasks of the group
+            unsigned before = 0u, hits = 0u, tasks = 0u, leader = 32u;
+            for (unsigned j = 0; j < take; ++j) {
+                const unsigned jb = __shfl_sync(0xffffffffu, rb, j), jn = __shfl_sync(0xffffffffu, rn, j);
+                if (jb == rb) {
+                    if (leader == 32u) leader = j;
+                    if (j < (unsigned)lane) before += jn;
+                    hits += jn;
+                    ++tasks;
+                }
+            }
+            const bool lead = (unsigned)lane < take && leader == (unsigned)lane;
+            unsigned pos = 0u;
+            if (lead && hits) pos = atomicAdd(P.T.cnt + rb, hits);
+            pos = __shfl_sync(0xffffffffu, pos, leader & 31u) + before;
+            for (unsigned j = 0; j < take; ++j) {
+                const unsigned jn = __shfl_sync(0xffffffffu, rn, j);
+                if (jn == 0u) continue;
+                const unsigned jb = __shfl_sync(0xffffffffu, rb, j), jpos = __shfl_sync(0xffffffffu, pos, j);
+                const unsigned jw = __shfl_sync(0xffffffffu, rw, j), jbuf = __shfl_sync(0xffffffffu, rbuf, j);
+                if ((unsigned)lane < jn && jpos + (unsigned)lane < (unsigned)kCap)
+                    P.T.cand[(size_t)jb * kCap + jpos + lane] = s_wst[jw][jbuf][lane];
+            }
+            __syncwarp();
+            if ((unsigned)lane < take) *(volatile unsigned *)&s_busy[rw][rbuf] = 0u;   // the staging buffer may be reused
+            // release: the candidate stores of the whole batch are visible before any of its tasks is reported done
+            __threadfence();
+            __syncwarp();
+            if (lead) {
+                const unsigned d = atomicAdd(P.done + rb, tasks);
+                if (d + tasks == (unsigned)ntask) {   // the image is complete: publish it for whichever CTA polls next
+                    const unsigned q = atomicAdd(P.tq_pushed, 1u);
+                    P.timeline[(size_t)rb * kStampSlots] = global_ns();
+                    __threadfence();
+                    atomicExch(P.tq_img + q, rb + 1u);
+                }
+            }
+            __syncwarp();
+            (void)active;
+            tail += take;
+        }
+        return;
+    }
+
+    // ---- streaming warps ----
+    // No task is taken while a hand-off is pending: a task a warp holds but has not streamed keeps its image open,
+    // the image would wait for this CTA's tail, and the CTA would then finish -- and inherit the tail of -- every
+    // following image too.
+    auto grab = [&]() {
+        unsigned t = 0u;
+        if (lane == 0) {
+            const unsigned k = atomicAdd(&s_ticket, 1u);
+            const unsigned c = k / (unsigned)P.chunk;
+            while (*(volatile unsigned *)&s_chunks <= c) __nanosleep(20);   // the bookkeeper is two chunks ahead
+            t = *(volatile unsigned *)&s_chunk_base[c % kChunkRing];
+            t = t >= total ? total : t + k % (unsigned)P.chunk;
+        }
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    static_assert(kWarpStage <= 32, "one staged hit per bookkeeper lane");
     bool drained = false;
-    unsigned next = grab();
+    unsigned buf = 0u;
     for (;;) {
-        if (!drained) {
-            if (next == kNoTask) next = grab();
-            const unsigned cur = next;
+        if (!drained && !tail_pending()) {
+            const unsigned cur = grab();
             if (cur < total) {
-                next = tail_pending() ? kNoTask : grab();   // its latency hides behind this task's loads
                 const unsigned b = fd_div(cur, P.G.div_ntask);
                 const STask k = stream_task(P.G, (int)b, (int)(cur - b * (unsigned)ntask));
                 const float thr_f = thr_float(__ldcg(P.T.thr + b));
-                unsigned *cnt = P.T.cnt + b;
-                unsigned long long *cand = P.T.cand + (size_t)b * kCap;
+                // the buffer this task stages into must have been flushed (it was posted kStageBufs tasks ago)
+                if (lane == 0) while (*(volatile unsigned *)&s_busy[warp][buf]) __nanosleep(50);
+                __syncwarp();
+                bool overflowed = false;
                 auto hit = [&](float x, int e) {
                     if (x >= thr_f) {
                         const unsigned long long key = ((unsigned long long)vkey_of(x) << 32) |
                                                        (unsigned long long)(~stream_flat(P.G, k.l, (unsigned)e));
                         const unsigned slot = atomicAdd(&s_wn[warp], 1u);
                         if (slot < (unsigned)kWarpStage) {
-                            s_wst[warp][slot] = key;
+                            s_wst[warp][buf][slot] = key;
                         } else {   // staging full (threshold far too low): straight to the global list
-                            const unsigned pos = atomicAdd(cnt, 1u);
-                            if (pos < (unsigned)kCap) cand[pos] = key;
+                            const unsigned pos = atomicAdd(P.T.cnt + b, 1u);
+                            if (pos < (unsigned)kCap) P.T.cand[(size_t)b * kCap + pos] = key;
+                            overflowed = true;
                         }
                     }
                 };
@@ -423,40 +627,27 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_fused_kernel(const __gri
                         if (e >= 0 && (unsigned)e < k.lb) hit(ld_stream1(k.blk + e), e);
                     }
                 }
+                if (__any_sync(0xffffffffu, overflowed)) __threadfence();   // direct stores before the record is posted
                 __syncwarp();
-                const unsigned nst = min(*(volatile unsigned *)&s_wn[warp], (unsigned)kWarpStage);
-                if (nst) {   // warp-uniform
-                    unsigned pos0 = 0u;
-                    if (lane == 0) pos0 = atomicAdd(cnt, nst);
-                    pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-                    for (unsigned i = lane; i < nst; i += 32)
-                        if (pos0 + i < (unsigned)kCap) cand[pos0 + i] = s_wst[warp][i];
-                    __syncwarp();
-                    if (lane == 0) s_wn[warp] = 0u;
+                if (lane == 0) {   // post the task: the bookkeeper does everything that needs a global round trip
+                    const unsigned nst = min(*(volatile unsigned *)&s_wn[warp], (unsigned)kWarpStage);
+                    s_wn[warp] = 0u;
+                    *(volatile unsigned *)&s_busy[warp][buf] = 1u;
+                    const unsigned slot = atomicAdd(&s_rec_head, 1u);
+                    s_rec[slot % kRecCap] = (b << 16) | (nst << 8) | ((unsigned)warp << 3) | buf;
+                    __threadfence_block();
+                    *(volatile unsigned *)&s_rec_seq[slot % kRecCap] = slot + 1u;
                 }
-                // release: every lane's candidate stores are visible before the task is reported done
-                __threadfence();
-                __syncwarp();
-                unsigned d = 0u;
-                if (lane == 0) d = atomicAdd(P.done + b, 1u);
-                d = __shfl_sync(0xffffffffu, d, 0);
-                if (d == (unsigned)ntask - 1u && lane == 0) {   // the image is complete: hand it to this CTA
-                    const unsigned slot = atomicAdd(&s_tail_n, 1u);
-                    s_tailq[slot & 63u] = (int)b;
-                }
+                buf = (buf + 1u) % kStageBufs;
                 __syncwarp();
             } else {
                 drained = true;
+                if (lane == 0) atomicAdd(&s_drained, 1u);
             }
         }
         if (drained || tail_pending()) {
-            if (!drained && next != kNoTask) continue;   // stream the task in hand first (nothing new is taken)
-            __syncthreads();   // all 32 warps are here: nobody is streaming, the tail queue is stable
-            const unsigned n1 = s_tail_n, d0 = s_tail_done;
-            for (unsigned i = d0; i != n1; ++i) run_tail(P, s_tailq[i & 63u], s_dyn);
-            __syncthreads();
-            if (tid == 0) s_tail_done = n1;
-            if (__syncthreads_and(drained ? 1 : 0)) break;   // every warp is out of tasks, every hand-off served
+            if (lane == 0) { __threadfence_block(); atomicAdd(&s_arrived, 1u); }   // after this warp's last record
+            if (meet(drained)) break;
         }
     }
 }
@@ -495,7 +686,12 @@ size_t sample_slot_stride(const StreamGeo &G, int *tps_out) {
     return (size_t)((G.ntask_img + tps - 1) / tps) * 32;
 }
 
-int launch_sample(const SampleLaunch &s, cudaStream_t st) {
+int launch_sample(const SampleLaunch &s0, cudaStream_t st) {
+    // The exposed cost of the sample is its scattered 512-byte reads (~1 TB/s): large images are sampled at 1/128
+    // (the rank statistics still see ~100 k values and ~40 exceedances; the 5-sigma margin then keeps ~2.2 K
+    // candidates instead of ~1.7 K), small ones at 1/64.
+    SampleLaunch s = s0;
+    s.shift = s.N >= (1ll << 23) ? kSampleShift + 1 : kSampleShift;
     const size_t smem = (size_t)((s.G.ntask_img + s.tps - 1) / s.tps) * 32 * sizeof(unsigned);
     if (smem > 64 * 1024) return set_error(ODK_EUNSUPPORTED, "odk sample: %zu bytes of slots", smem);
     if (smem > 32 * 1024) {
@@ -507,7 +703,7 @@ int launch_sample(const SampleLaunch &s, cudaStream_t st) {
 }
 
 struct PostWs {
-    size_t slots, thr, cnt, flag, done, queue, cand, tk_val, tk_box, tk_idx, tk_cls, total;
+    size_t slots, thr, thr_hi, cnt, flag, done, tq_img, queue, timeline, cand, cand_box, tk_val, tk_box, tk_idx, tk_cls, total;
     int slot_stride, tps;
 };
 
@@ -518,11 +714,15 @@ static PostWs post_ws_layout(const StreamGeo &G, int B, int K) {
     size_t off = 0;
     w.slots = off; off = al(off + (size_t)B * w.slot_stride * 4);
     w.thr = off; off = al(off + (size_t)B * 4);
+    w.thr_hi = off; off = al(off + (size_t)B * 4);
     w.cnt = off; off = al(off + (size_t)B * 4);
     w.flag = off; off = al(off + (size_t)B * 4);
     w.done = off; off = al(off + (size_t)B * 4);
-    w.queue = off; off = al(off + 4);
+    w.tq_img = off; off = al(off + (size_t)B * 4);
+    w.queue = off; off = al(off + 16);   // queue, tq_pushed, tq_claimed
+    w.timeline = off; off = al(off + ((size_t)B * kStampSlots + 2) * 8);
     w.cand = off; off = al(off + (size_t)B * kCap * 8);
+    w.cand_box = off; off = al(off + (size_t)B * kCap * 16);
     w.tk_val = off; off = al(off + (size_t)B * K * 4);
     w.tk_box = off; off = al(off + (size_t)B * K * 16);
     w.tk_idx = off; off = al(off + (size_t)B * K * 8);
@@ -533,6 +733,7 @@ static PostWs post_ws_layout(const StreamGeo &G, int B, int K) {
 
 // defined in odk_topk.cu / odk_detect.cu: the exact path for the images the fused kernel flagged
 int launch_topk_exact_flagged(const TopkArgs &a, cudaStream_t st);
+int launch_topk_collect(const TopkArgs &a, int ntasks, cudaStream_t st);
 int launch_detect_flagged(const float *cls_topk, const float *box_topk, const int64_t *indices, const int64_t *classes, int B,
                           int N, const float *anchors, int64_t A, const float *img_scale, const float *img_size,
                           const odk_detect_params *params, float *dets, int32_t *count, int32_t *src, int64_t *det_anchor,
@@ -566,6 +767,11 @@ size_t odk_postprocess_workspace_bytes(int B, int C, const int32_t *level_hw, in
 size_t odk_postprocess_flags_offset(int B, int C, const int32_t *level_hw, int num_levels, int na, int K) {
     odk::PostWs w;
     return post_ws_for(B, C, level_hw, num_levels, na, K, &w) ? 0 : w.flag;
+}
+
+size_t odk_postprocess_timeline_offset(int B, int C, const int32_t *level_hw, int num_levels, int na, int K) {
+    odk::PostWs w;
+    return post_ws_for(B, C, level_hw, num_levels, na, K, &w) ? 0 : w.timeline;
 }
 
 int odk_postprocess(const void *const *cls_levels, const void *const *box_levels, int B, int C, const int32_t *level_hw,
@@ -620,6 +826,7 @@ int odk_postprocess(const void *const *cls_levels, const void *const *box_levels
     char *ws = (char *)workspace;
     a.slots = (unsigned *)(ws + w.slots); a.thr = (unsigned *)(ws + w.thr); a.cnt = (unsigned *)(ws + w.cnt);
     a.flag = (unsigned *)(ws + w.flag); a.cand = (unsigned long long *)(ws + w.cand);
+    a.thr_hi = (unsigned *)(ws + w.thr_hi); a.cand_box = (float4 *)(ws + w.cand_box);
     a.out_val = want_topk ? cls_topk : (float *)(ws + w.tk_val);
     a.out_box = want_topk ? box_topk : (float *)(ws + w.tk_box);
     a.out_idx = want_topk ? (long long *)indices : (long long *)(ws + w.tk_idx);
@@ -627,6 +834,19 @@ int odk_postprocess(const void *const *cls_levels, const void *const *box_levels
     a.fused = 1;
     P.emit_topk = want_topk ? 1 : 0;
     P.queue = (unsigned *)(ws + w.queue); P.done = (unsigned *)(ws + w.done);
+    P.timeline = (unsigned long long *)(ws + w.timeline);
+    a.stamp = P.timeline;
+    {
+        const char *dbg = getenv("ODK_POST_SKIP_TAILS");
+        P.debug_skip_tails = (dbg && dbg[0] == '1') ? 1 : 0;
+        // a chunk is what one queue access takes; the bookkeeper keeps `ahead` chunks published beyond the one in use:
+        // enough to hide the atomic's latency, little enough that images still complete in order
+        P.chunk = 8; P.ahead = 2;
+        const char *ec = getenv("ODK_POST_CHUNK"), *ea = getenv("ODK_POST_AHEAD");
+        if (ec && atoi(ec) >= 1 && atoi(ec) <= 64 && (atoi(ec) & (atoi(ec) - 1)) == 0) P.chunk = atoi(ec);
+        if (ea && atoi(ea) >= 1 && atoi(ea) <= 8) P.ahead = atoi(ea);
+    }
+    P.tq_img = (unsigned *)(ws + w.tq_img); P.tq_pushed = P.queue + 1; P.tq_claimed = P.queue + 2;
     P.total_tasks = (unsigned)B * (unsigned)P.G.ntask_img;
     if ((long long)B * P.G.ntask_img > 0x7fffffffll) return set_error(ODK_EUNSUPPORTED, "odk_postprocess: too many tasks");
     P.anchors = (const float4 *)anchors; P.scale = img_scale; P.size = img_size;
@@ -636,27 +856,43 @@ int odk_postprocess(const void *const *cls_levels, const void *const *box_levels
     P.energy = energy; P.max_logit = max_logit; P.ood_T = temperature;
 
     cudaStream_t st = (cudaStream_t)stream;
+    const bool persistent = params->pipeline == ODK_PIPELINE_PERSISTENT;
+    if (persistent) a.cand_box = nullptr;   // (its bookkeeper does not gather the rows: the tail reads them from the levels)
     SampleLaunch s;
     memset(&s, 0, sizeof(s));
     s.G = P.G; s.B = B; s.K = K; s.N = a.N; s.slots = a.slots; s.slot_stride = w.slot_stride; s.tps = w.tps; s.thr = a.thr;
-    s.zero0 = a.cnt; s.zero1 = a.flag; s.zero2 = P.done; s.zero_scalar = P.queue;
+    s.thr_hi = (unsigned *)(ws + w.thr_hi);
+    s.zero0 = a.cnt; s.zero1 = a.flag; s.zero2 = P.done; s.zero3 = P.tq_img; s.zero_scalar = P.queue; s.zero_scalars = 3;
+    s.zero_u64 = P.timeline + (size_t)B * kStampSlots + 1;
     rc = launch_sample(s, st);
     if (rc) return rc;
 
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms < 1) sms = 148;
-    size_t smem = (size_t)kCap * 8;
+    size_t smem = kSelSmemBytes;
     if (post_det_bytes(P.cap) > smem) smem = post_det_bytes(P.cap);
-    cudaError_t e = cudaFuncSetAttribute(post_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error((int)e, "odk_postprocess: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
-    unsigned grid = (unsigned)sms;
-    const unsigned useful = (P.total_tasks + kPostWarps - 1) / kPostWarps;
-    if (grid > useful) grid = useful;
-    if (grid < 1) grid = 1;
-    post_fused_kernel<<<grid, kPostThreads, smem, st>>>(P);
-    rc = check_launch("odk_postprocess/post_fused_kernel");
+    if (persistent) {
+        // one persistent kernel: image-major stream + tails of the earlier images (see the top of this file)
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms < 1) sms = 148;
+        cudaError_t e = cudaFuncSetAttribute(post_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error((int)e, "odk_postprocess: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+        unsigned grid = (unsigned)sms;
+        const unsigned useful = (P.total_tasks + kStreamWarps - 1) / kStreamWarps;
+        if (grid > useful) grid = useful;
+        if (grid < 1) grid = 1;
+        post_fused_kernel<<<grid, kPostThreads, smem, st>>>(P);
+        rc = check_launch("odk_postprocess/post_fused_kernel");
+    } else {
+        // staged: the one-wave collect kernel of odk_topk.cu streams the whole batch, then one CTA per image runs
+        // the image's tail (with B <= #SMs both pipelines expose exactly one tail after the last logit is read)
+        rc = launch_topk_collect(a, toff, st);
+        if (rc) return rc;
+        cudaError_t e = cudaFuncSetAttribute(post_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error((int)e, "odk_postprocess: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+        post_tail_kernel<<<B, kPostThreads, smem, st>>>(P);
+        rc = check_launch("odk_postprocess/post_tail_kernel");
+    }
     if (rc) return rc;
     // flagged images only (none for real score distributions): exact select, then their detections / OOD scores
     rc = launch_topk_exact_flagged(a, st);

@@ -4,7 +4,7 @@
 // Per (image b, level l) the NCHW head output is ONE contiguous block of lb = na*C*H*W floats.  A block is
 // cut into 16-byte GROUPS on the address grid (the block of image b starts `mis` elements past a 16-byte
 // boundary, mis = 0..3, so at most its first and last group are partial) and a TASK is a run of up to
-// kGroupsPerTask groups (16 KB): every task of a level has the same size whatever the plane size is, which
+// kGroupsPerTask groups (32 KB): every task of a level has the same size whatever the plane size is, which
 // the per-plane segments of odk_topk.cu's collect kernel do not give (D3: half of its tasks are < 1 KB).
 // Tasks are numbered image-major: g = b * ntask_img + t, so a grid that takes them in order finishes the
 // images in order.
@@ -13,7 +13,8 @@
 
 namespace odk {
 
-constexpr int kGroupsPerTask = 1024;   // 16 KB of logits
+constexpr int kGroupsPerTask = 2048;   // 32 KB of logits
+constexpr int kUnitsPerTask = kGroupsPerTask / 32;   // 512-byte warp units; the sample takes at most one per task
 
 struct StreamGeo {
     const float *cls[ODK_MAX_LEVELS];
@@ -76,11 +77,16 @@ struct SampleLaunch {
     unsigned *slots;      // unused (the slots live in the leader CTA's shared memory)
     int slot_stride;
     int tps;              // tasks per slot group (power of two)
+    int shift;            // 2^-shift of the 512-byte units are sampled (set by launch_sample from N)
     unsigned *thr;        // [B] out: collect threshold (value key)
-    unsigned *zero0;      // up to three [B] arrays and one scalar zeroed for the kernels that follow
+    unsigned *thr_hi;     // [B] out: estimate of the key ~K/16 elements exceed (select's bin edge hint)
+    unsigned *zero0;      // up to four [B] arrays and a few consecutive scalars zeroed for the kernels that follow
     unsigned *zero1;
     unsigned *zero2;
+    unsigned *zero3;
     unsigned *zero_scalar;
+    int zero_scalars;
+    unsigned long long *zero_u64;   // one 64-bit word, or null
 };
 size_t sample_slot_stride(const StreamGeo &G, int *tps_out);
 int launch_sample(const SampleLaunch &s, cudaStream_t st);

@@ -54,7 +54,10 @@ __global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const __grid
                     s_stage[slot] = key;
                 } else {   // staging full (threshold far too low): straight to the global list
                     const unsigned pos = atomicAdd(cnt, 1u);
-                    if (pos < (unsigned)kCap) cand[pos] = key;
+                    if (pos < (unsigned)kCap) {
+                        cand[pos] = key;
+                        if (A.cand_box) A.cand_box[(size_t)b * kCap + pos] = gather_box(A, b, (int)(flat / (unsigned)A.C));
+                    }
                 }
             }
         };
@@ -72,8 +75,16 @@ __global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const __grid
     if (threadIdx.x == 0) s_base = n ? atomicAdd(cnt, n) : 0u;
     __syncthreads();
     const unsigned base = s_base;
-    for (unsigned i = threadIdx.x; i < n; i += kTopkThreads)
-        if (base + i < (unsigned)kCap) cand[base + i] = s_stage[i];
+    for (unsigned i = threadIdx.x; i < n; i += kTopkThreads) {
+        if (base + i < (unsigned)kCap) {
+            const unsigned long long key = s_stage[i];
+            cand[base + i] = key;
+            // the detection stage needs the candidate's box regression (4 scattered sectors): gather it here, spread
+            // over all SMs and hidden behind the stream, and leave it next to the key (one sector per row later)
+            if (A.cand_box)
+                A.cand_box[(size_t)b * kCap + base + i] = gather_box(A, b, (int)(~(unsigned)(key & 0xFFFFFFFFull) / (unsigned)A.C));
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const __grid_constant__ TopkArgs A) {
@@ -183,7 +194,7 @@ topk_exact_kernel(const __grid_constant__ TopkArgs A) {
     cluster.sync();   // keep peers' shared memory alive until rank 0 is done with DSMEM
 }
 
-struct TopkWs { size_t slots, thr, cnt, flag, cand, total; int slot_stride, tps; };
+struct TopkWs { size_t slots, thr, thr_hi, cnt, flag, cand, total; int slot_stride, tps; };
 
 static TopkWs topk_ws_layout(const StreamGeo &G, int B) {
     TopkWs w;
@@ -192,6 +203,7 @@ static TopkWs topk_ws_layout(const StreamGeo &G, int B) {
     size_t off = 0;
     w.slots = off; off = al(off + (size_t)B * w.slot_stride * 4);
     w.thr = off; off = al(off + (size_t)B * 4);
+    w.thr_hi = off; off = al(off + (size_t)B * 4);
     w.cnt = off; off = al(off + (size_t)B * 4);
     w.flag = off; off = al(off + (size_t)B * 4);
     w.cand = off; off = al(off + (size_t)B * kCap * sizeof(unsigned long long));
@@ -199,9 +211,27 @@ static TopkWs topk_ws_layout(const StreamGeo &G, int B) {
     return w;
 }
 
+// one co-resident wave of collect CTAs over the whole batch (per-plane task model)
+int launch_topk_collect(const TopkArgs &a, int ntasks, cudaStream_t st) {
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 1) sms = 148;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topk_collect_kernel, kTopkThreads, 0);
+    if (occ < 1) occ = 1;
+    const int warps_per_cta = kTopkThreads / 32;
+    int per_image = (sms * occ) / a.B;                           // all CTAs co-resident: exactly one wave
+    const int max_useful = (ntasks + warps_per_cta - 1) / warps_per_cta;
+    if (per_image > max_useful) per_image = max_useful;
+    if (per_image < 1) per_image = 1;
+    dim3 grid(per_image, a.B);
+    topk_collect_kernel<<<grid, kTopkThreads, 0, st>>>(a);
+    return check_launch("odk_topk/collect");
+}
+
 int launch_topk_exact_flagged(const TopkArgs &a, cudaStream_t st) {
-    cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * 8);
-    topk_exact_kernel<<<a.B * kClusterSize, kSelThreads, kCap * 8, st>>>(a);
+    cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmemBytes);
+    topk_exact_kernel<<<a.B * kClusterSize, kSelThreads, kSelSmemBytes, st>>>(a);
     return check_launch("odk_topk/exact");
 }
 
@@ -265,34 +295,22 @@ int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B
     char *ws = (char *)workspace;
     a.slots = (unsigned *)(ws + w.slots); a.thr = (unsigned *)(ws + w.thr); a.cnt = (unsigned *)(ws + w.cnt);
     a.flag = (unsigned *)(ws + w.flag); a.cand = (unsigned long long *)(ws + w.cand);
+    a.thr_hi = (unsigned *)(ws + w.thr_hi); a.cand_box = nullptr;
     a.out_val = cls_topk; a.out_box = box_topk; a.out_idx = (long long *)indices; a.out_cls = (long long *)classes;
 
     cudaStream_t st = (cudaStream_t)stream;
     // sample + threshold per image; the same launch zeroes the candidate counters and flags (no memset)
     SampleLaunch sl;
     memset(&sl, 0, sizeof(sl));
-    sl.G = G; sl.B = B; sl.K = K; sl.N = a.N; sl.slots = a.slots; sl.slot_stride = w.slot_stride; sl.tps = w.tps; sl.thr = a.thr;
+    sl.G = G; sl.B = B; sl.K = K; sl.N = a.N; sl.slots = a.slots; sl.slot_stride = w.slot_stride; sl.tps = w.tps; sl.thr = a.thr; sl.thr_hi = (unsigned *)(ws + w.thr_hi);
     sl.zero0 = a.cnt; sl.zero1 = a.flag;
     rc = launch_sample(sl, st);
     if (rc) return rc;
 
-    int dev = 0, sms = 0, occ = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms < 1) sms = 148;
-    cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCap * 8);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topk_collect_kernel, kTopkThreads, 0);
-    if (occ < 1) occ = 1;
-    const int warps_per_cta = kTopkThreads / 32;
-    int per_image = (sms * occ) / B;                             // all CTAs co-resident: exactly one wave
-    const int max_useful = (toff + warps_per_cta - 1) / warps_per_cta;
-    if (per_image > max_useful) per_image = max_useful;
-    if (per_image < 1) per_image = 1;
-    dim3 grid(per_image, B);
-    topk_collect_kernel<<<grid, kTopkThreads, 0, st>>>(a);
-    rc = check_launch("odk_topk/collect");
+    rc = launch_topk_collect(a, toff, st);
     if (rc) return rc;
-    topk_select_kernel<<<B, kSelThreads, kCap * 8, st>>>(a);
+    cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmemBytes);
+    topk_select_kernel<<<B, kSelThreads, kSelSmemBytes, st>>>(a);
     rc = check_launch("odk_topk/select");
     if (rc) return rc;
     return launch_topk_exact_flagged(a, st);

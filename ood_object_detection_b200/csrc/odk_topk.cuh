@@ -13,7 +13,7 @@ constexpr int kSelThreads = 1024;
 constexpr int kCap = 16384;            // candidate capacity per image (128 KB of 64-bit keys)
 constexpr int kHistBins = 4096;        // top 12 bits of the value key
 constexpr int kSlots = 8192;           // per-image sample slots (lane maxima)
-constexpr int kSampleShift = 6;        // sample 1 / 64 of the 512-byte units
+constexpr int kSampleShift = 6;        // sample 1 / 64 of the 512-byte units (1 / 128 of large images, odk_stream.cuh)
 constexpr int kSegVec = 1024;          // vec4 units per task segment
 constexpr int kClusterSize = 8;
 constexpr int kRadixBits = 11;
@@ -31,6 +31,8 @@ struct TopkArgs {
     long long N;                  // elements per image = A * C
     unsigned *slots;              // [B][kSlots] value keys: maxima of the sampled units of one lane
     unsigned *thr;                // [B] threshold key of the collect pass
+    const unsigned *thr_hi;       // [B] sampled estimate of the key ~K/16 elements exceed (bin edge hint), or null
+    float4 *cand_box;             // [B][kCap] box regression of every candidate (same order as cand), or null
     int nslots;                   // slots actually used per image
     unsigned *cnt;                // [B]
     unsigned *flag;               // [B]
@@ -40,7 +42,17 @@ struct TopkArgs {
     long long *out_idx;           // [B][K]
     long long *out_cls;           // [B][K]
     int fused;                    // called behind odk_postprocess: unflagged images are already complete
+    unsigned long long *stamp;    // diagnostics: [B][kStampSlots] %globaltimer marks (odk_postprocess), or null
 };
+
+constexpr int kStampSlots = 16;
+__device__ __forceinline__ void stamp(unsigned long long *base, int b, int slot) {
+    if (base && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        base[(size_t)b * kStampSlots + slot] = t;
+    }
+}
 
 __device__ __forceinline__ unsigned vkey_of(float x) {
     const unsigned u = __float_as_uint(x + 0.0f);   // -0.0 -> +0.0: they compare equal in torch.topk
@@ -107,16 +119,16 @@ __device__ __forceinline__ void visit_task(const Task &k, int lane, F4 f4, F1 f1
 // located in a 4096-bin histogram of the top 12 key bits, then inside that bin on key bits 19..12 (a 12-bit
 // bin alone is 2^-3 of the value wide and can hold most of a steep score distribution).
 template <int NT>
-static __device__ unsigned threshold_from_slots(const unsigned *sl, int nslots, long long N, int K) {
-    static_assert(kHistBins % NT == 0 && NT % 32 == 0, "bins per thread");
+static __device__ uint2 threshold_from_slots(const unsigned *sl, int nslots, long long N, int K, int sample_shift) {
+    static_assert(kHistBins % NT == 0 && NT % 32 == 0 && NT >= 256, "bins per thread");
     constexpr int kPer = kHistBins / NT, kWarps = NT / 32;
     __shared__ unsigned s_hist[kHistBins];
-    __shared__ unsigned s_wsum[kWarps], s_wtot[kWarps], s_sub[256];
-    __shared__ unsigned s_coarse, s_above;
+    __shared__ unsigned s_wsum[kWarps], s_wtot[kWarps], s_sub[2][256];
+    __shared__ unsigned s_coarse[2], s_above[2], s_fine[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < kHistBins; i += NT) s_hist[i] = 0u;
-    if (tid < 256) s_sub[tid] = 0u;
-    if (tid == 0) { s_coarse = 0u; s_above = 0u; }
+    if (tid < 256) { s_sub[0][tid] = 0u; s_sub[1][tid] = 0u; }
+    if (tid < 2) { s_coarse[tid] = 0u; s_above[tid] = 0u; s_fine[tid] = 0u; }
     __syncthreads();
     unsigned used = 0u;
     for (int i = tid; i < nslots; i += NT) {
@@ -130,7 +142,7 @@ static __device__ unsigned threshold_from_slots(const unsigned *sl, int nslots, 
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) Lu += s_wsum[w];
     const float L = (float)Lu;
-    const float n_per = fmaxf((float)N / (float)(1 << kSampleShift) / fmaxf(L, 1.0f), 1.0f);
+    const float n_per = fmaxf((float)N / (float)(1 << sample_shift) / fmaxf(L, 1.0f), 1.0f);
     const float need = (float)K / (float)N;
     unsigned r = 0u;   // every thread runs the same search: no broadcast needed
     if (L >= 16.0f) {
@@ -146,7 +158,11 @@ static __device__ unsigned threshold_from_slots(const unsigned *sl, int nslots, 
             r = lo;
         }
     }
-    if (r == 0u) return 0u;   // uniform: keep everything (the select step then flags the image)
+    if (r == 0u) return make_uint2(0u, 0u);   // uniform: keep everything (the select step then flags the image)
+    // second rank: the slot maxima expected above the value that K/16 elements exceed (no margin: only a hint)
+    unsigned rk[2];
+    rk[0] = r;
+    rk[1] = max(4u, (unsigned)(L * (1.0f - expf(-n_per * need * (1.0f / 16.0f)))));
     // ranks from the top bin down: thread t owns the kPer bins below hi = kHistBins - 1 - t * kPer
     const int hi = kHistBins - 1 - tid * kPer;
     unsigned mine = 0u;
@@ -162,28 +178,47 @@ static __device__ unsigned threshold_from_slots(const unsigned *sl, int nslots, 
     __syncthreads();
     unsigned before = inc - mine;
     for (int w = 0; w < warp; ++w) before += s_wtot[w];
-    if (before < r && before + mine >= r) {   // exactly one thread
-        unsigned run = before;
-        for (int i = 0; i < kPer; ++i) {
-            const unsigned c = s_hist[hi - i];
-            if (run + c >= r) { s_coarse = (unsigned)(hi - i) << 20; s_above = run; break; }
-            run += c;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (before < rk[q] && before + mine >= rk[q]) {   // exactly one thread per rank
+            unsigned run = before;
+            for (int i = 0; i < kPer; ++i) {
+                const unsigned c = s_hist[hi - i];
+                if (run + c >= rk[q]) { s_coarse[q] = (unsigned)(hi - i) << 20; s_above[q] = run; break; }
+                run += c;
+            }
         }
     }
     __syncthreads();
-    const unsigned coarse = s_coarse;
+    const unsigned c0 = s_coarse[0], c1 = s_coarse[1];
     for (int i = tid; i < nslots; i += NT) {
         const unsigned k = sl[i];
-        if (k && (k >> 20) == (coarse >> 20)) atomicAdd(&s_sub[(k >> 12) & 255u], 1u);
+        if (k && (k >> 20) == (c0 >> 20)) atomicAdd(&s_sub[0][(k >> 12) & 255u], 1u);
+        if (k && (k >> 20) == (c1 >> 20)) atomicAdd(&s_sub[1][(k >> 12) & 255u], 1u);
     }
     __syncthreads();
-    unsigned run = s_above;
-    int sub = 255;
-    for (; sub > 0; --sub) {   // every thread walks the same 256 counters (broadcast reads)
-        run += s_sub[sub];
-        if (run >= r) break;
+    // rank inside the coarse bin: warps 0 and 1 scan the 256 sub-bins of rank 0 and 1 from the top (8 per lane)
+    if (warp < 2) {
+        const unsigned *sub = s_sub[warp];
+        unsigned v[8], tot = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[j] = sub[255 - (lane * 8 + j)]; tot += v[j]; }
+        unsigned incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        unsigned run = s_above[warp] + incl - tot;
+        const unsigned want = rk[warp];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (run < want && run + v[j] >= want) s_fine[warp] = (unsigned)(255 - (lane * 8 + j));
+            run += v[j];
+        }
     }
-    return coarse | ((unsigned)sub << 12);
+    __syncthreads();
+    return make_uint2(c0 | (s_fine[0] << 12), c1 | (s_fine[1] << 12));
 }
 
 __device__ __forceinline__ float thr_float(unsigned thr_key) {
@@ -322,91 +357,112 @@ static __device__ void gather_selected_boxes(const TopkArgs &A, int b, unsigned 
 // 8192 keys.  Heavily tied inputs (a sub-bin with more than kBucketMax keys, or more than 8192 survivors)
 // take the bitonic path instead.
 constexpr int kRefineBins = 1024;
-constexpr int kRefineShift = 14;   // sub-bin = 2^14 key units: 64 sub-bins per 12-bit threshold bin
 constexpr int kBucketMax = 512;    // largest sub-bin the direct ranking accepts
 constexpr int kSortSlots = 8 * kSelThreads;
 
-struct Refined { int m; bool ranked; };   // survivors; ranked: s[kSortSlots + q] is the q-th largest key
+// survivors; ranked: s[kSortSlots + q] is the q-th largest key and srcpos[q] its position in the candidate list
+struct Refined { int m; bool ranked; const unsigned short *srcpos; };
+// dynamic shared memory of every kernel that selects: kCap keys + two position arrays
+constexpr size_t kSelSmemBytes = (size_t)kCap * 8 + 2 * (size_t)(8 * kSelThreads) * 2;
 
-// one warp: per-bin first ranks from the top bin down (s_start), stops at the first bin where the running
-// count reaches `need` (returns that bin and the count through lane-uniform values); tracks the largest bin
-__device__ __forceinline__ void suffix_scan(const unsigned *hist, unsigned *start, unsigned need, unsigned first_rank,
-                                            unsigned &edge, unsigned &total, unsigned &biggest, int skip_bin) {
-    const int lane = threadIdx.x & 31;
-    unsigned run = first_rank, big = 0;
-    edge = 0u; total = 0u;
-    for (int c = kRefineBins / 32 - 1; c >= 0; --c) {
-        const int bin = c * 32 + (31 - lane);   // lane 0 holds the highest bin of the chunk
-        const unsigned v = hist[bin];
-        unsigned inc = v;
+// whole block (kSelThreads == kRefineBins: one bin per thread, top bin first): per-bin first ranks (start), the
+// first bin from the top at which the running count reaches `need` (edge; 0 if it never does) with the count
+// down to and including it (total), and the largest bin at or above the edge other than skip_bin (biggest).
+// Two block barriers; the one-warp version of this scan was 15-25 us of a 30 us select.
+static __device__ void block_suffix_scan(const unsigned *hist, unsigned *start, unsigned need, unsigned &edge, unsigned &total,
+                                         unsigned &biggest, int skip_bin) {
+    static_assert(kRefineBins == kSelThreads, "one bin per thread");
+    __shared__ unsigned s_wt[kSelThreads / 32];
+    __shared__ unsigned s_r_edge, s_r_total, s_r_big;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int bin = kRefineBins - 1 - t;
+    const unsigned v = hist[bin];
+    unsigned inc = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        start[bin] = run + inc - v;   // keys in higher bins = first rank of this one
-        const unsigned hit = __ballot_sync(0xffffffffu, run + inc - first_rank >= need);
-        if (hit) {
-            const int ln = __ffs(hit) - 1;
-            if (lane <= ln && bin != skip_bin) big = max(big, v);
-            edge = (unsigned)__shfl_sync(0xffffffffu, bin, ln);
-            total = __shfl_sync(0xffffffffu, run + inc, ln) - first_rank;
-            break;
-        }
-        if (bin != skip_bin) big = max(big, v);
-        run += __shfl_sync(0xffffffffu, inc, 31);
-        if (c == 0) total = run - first_rank;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
     }
-    biggest = __reduce_max_sync(0xffffffffu, big);
+    if (lane == 31) s_wt[warp] = inc;
+    if (t == 0) { s_r_edge = 0u; s_r_total = 0u; s_r_big = 0u; }
+    __syncthreads();
+    unsigned incl = inc;
+    for (int w = 0; w < warp; ++w) incl += s_wt[w];
+    const unsigned excl = incl - v;
+    start[bin] = excl;
+    if (incl >= need && excl < need) { s_r_edge = (unsigned)bin; s_r_total = incl; }
+    if (bin == 0 && incl < need) s_r_total = incl;   // never reached: everything is kept
+    unsigned big = (excl < need && bin != skip_bin) ? v : 0u;   // bins at or above the edge
+    big = __reduce_max_sync(0xffffffffu, big);
+    if (lane == 0 && big) atomicMax(&s_r_big, big);
+    __syncthreads();
+    edge = s_r_edge; total = s_r_total; biggest = s_r_big;
+    __syncthreads();   // the result words may be reused by the next call
 }
 
 static __device__ Refined refine_candidates(const TopkArgs &A, int b, int n, unsigned long long *s) {
     __shared__ unsigned s_rh[kRefineBins], s_start[kRefineBins], s_fill[kRefineBins];
     __shared__ unsigned s_rh2[kRefineBins], s_start2[kRefineBins], s_fill2[kRefineBins];
-    __shared__ unsigned s_edge, s_cnt, s_maxbin, s_top, s_wmax[kSelThreads / 32];
+    __shared__ unsigned s_cnt, s_maxbin, s_wmax[kSelThreads / 32], s_wmin[kSelThreads / 32];
     const int tid = threadIdx.x;
     const unsigned base = __ldcg(A.thr + b);   // every candidate key is >= base
+    const unsigned hint = A.thr_hi ? __ldcg(A.thr_hi + b) : 0u;
     const unsigned long long *cand = A.cand + (size_t)b * kCap;
+    unsigned short *pos1 = reinterpret_cast<unsigned short *>(s + 2 * kSortSlots);   // candidate-list position of s[p]
+    unsigned short *pos2 = pos1 + kSortSlots;                                       // ... of the q-th largest key
     for (int i = tid; i < kRefineBins; i += blockDim.x) { s_rh[i] = 0; s_fill[i] = 0; s_rh2[i] = 0; s_fill2[i] = 0; }
-    if (tid == 0) { s_edge = 0u; s_cnt = 0u; s_maxbin = 0u; }
-    __syncthreads();
+    if (tid == 0) { s_cnt = 0u; s_maxbin = 0u; }
     unsigned long long mine[kCap / kSelThreads];
-    auto bin_of = [&](unsigned long long key) {
-        return min(((unsigned)(key >> 32) - base) >> kRefineShift, (unsigned)kRefineBins - 1u);
-    };
-    constexpr unsigned kTopBin = kRefineBins - 1;   // also catches everything above the sub-bin range
-    unsigned vmax = 0u;
+    unsigned vmax = 0u, vmin = 0xFFFFFFFFu;
 #pragma unroll
     for (int k = 0; k < kCap / kSelThreads; ++k) {
         const int i = tid + k * kSelThreads;
         mine[k] = i < n ? __ldcg(cand + i) : 0ull;
         if (i < n) {
-            atomicAdd(&s_rh[bin_of(mine[k])], 1u);
             vmax = max(vmax, (unsigned)(mine[k] >> 32));
+            vmin = min(vmin, (unsigned)(mine[k] >> 32));
         }
     }
     vmax = __reduce_max_sync(0xffffffffu, vmax);
-    if ((tid & 31) == 0) s_wmax[tid >> 5] = vmax;
+    vmin = __reduce_min_sync(0xffffffffu, vmin);
+    if ((tid & 31) == 0) { s_wmax[tid >> 5] = vmax; s_wmin[tid >> 5] = vmin; }
     __syncthreads();
-    if (tid < 32) {
-        unsigned edge, total, biggest;
-        suffix_scan(s_rh, s_start, (unsigned)A.K, 0u, edge, total, biggest, (int)kTopBin);
-        unsigned top = s_wmax[tid];
-        top = __reduce_max_sync(0xffffffffu, top);
-        if (tid == 0) { s_edge = edge; s_cnt = total; s_maxbin = biggest; s_top = top; }
-    }
+#pragma unroll 4
+    for (int w = 0; w < kSelThreads / 32; ++w) { vmax = max(vmax, s_wmax[w]); vmin = min(vmin, s_wmin[w]); }
+    // Bins are LINEAR IN THE VALUE between the smallest candidate and an upper edge: the sampled estimate of the
+    // value ~K/16 elements exceed (A.thr_hi) when it lies inside the candidates' range, else the largest
+    // candidate.  A score distribution's tail decays roughly exponentially, so between those two edges the
+    // densest of 1023 bins holds ~n*ln(16n/K)/1023 keys -- a few dozen -- wherever the values sit (bins on the
+    // key BITS degenerate near zero, where a float's exponent field eats the range).  Everything at or above the
+    // upper edge -- the strongest scores, possibly with far outliers -- shares the top bin, which gets a second
+    // histogram, linear between that edge and the largest candidate.
+    constexpr unsigned kTopBin = kRefineBins - 1;
+    const unsigned key_lo = max(base, vmin);
+    const bool has_top = hint > key_lo && hint < vmax;
+    const unsigned top_key = has_top ? hint : 0xFFFFFFFFu;
+    const float x_lo = val_of(key_lo);
+    const float x_top = val_of(has_top ? hint : vmax);
+    const float scale1 = x_top > x_lo ? (float)(kRefineBins - 2) / (x_top - x_lo) : 0.0f;
+    auto bin_of = [&](unsigned long long key) {
+        const unsigned kv = (unsigned)(key >> 32);
+        if (has_top && kv >= top_key) return kTopBin;
+        const float t = (val_of(kv) - x_lo) * scale1;   // monotone in the key; NaN -> 0
+        return (unsigned)min(max((int)t, 0), kRefineBins - 2);
+    };
+#pragma unroll
+    for (int k = 0; k < kCap / kSelThreads; ++k)
+        if (tid + k * kSelThreads < n) atomicAdd(&s_rh[bin_of(mine[k])], 1u);
     __syncthreads();
-    const unsigned edge = s_edge;   // keep sub-bins >= edge (edge 0: keep everything)
-    const int m = (int)s_cnt;       // survivors (>= K: the select kernel only runs with n >= K)
-    if (m > kSortSlots) return {m, false};
-    // The top sub-bin also holds every key above the sub-bin range (the strongest scores, often across the
-    // sign change where float bit patterns are sparse): it gets a second histogram that is linear in the VALUE
-    // between the sub-bin's lower edge and the largest candidate.
-    const float x_lo = val_of(base + (kTopBin << kRefineShift));
-    const float x_hi = val_of(s_top);
-    const float scale2 = x_hi > x_lo ? (float)(kRefineBins - 1) / (x_hi - x_lo) : 0.0f;
+    stamp(A.stamp, b, 9);
+    unsigned edge, total0, biggest0;   // keep bins >= edge (edge 0: keep everything)
+    block_suffix_scan(s_rh, s_start, (unsigned)A.K, edge, total0, biggest0, (int)kTopBin);
+    if (tid == 0) s_maxbin = biggest0;
+    const int m = (int)total0;       // survivors (>= K: the select step only runs with n >= K)
+    if (m > kSortSlots) return {m, false, nullptr};
+    const float x_hi = val_of(vmax);
+    const float scale2 = x_hi > x_top ? (float)(kRefineBins - 1) / (x_hi - x_top) : 0.0f;
     auto bin2_of = [&](unsigned long long key) {
-        const float t = (val_of((unsigned)(key >> 32)) - x_lo) * scale2;   // monotone in the key; NaN/inf -> 0
+        const float t = (val_of((unsigned)(key >> 32)) - x_top) * scale2;   // monotone in the key; NaN/inf -> 0
         return (unsigned)min(max((int)t, 0), kRefineBins - 1);
     };
     const bool two_level = s_rh[kTopBin] > 32u;
@@ -417,12 +473,9 @@ static __device__ Refined refine_candidates(const TopkArgs &A, int b, int n, uns
             if (i < n && bin_of(mine[k]) == kTopBin) atomicAdd(&s_rh2[bin2_of(mine[k])], 1u);
         }
         __syncthreads();
-        if (tid < 32) {
-            unsigned e2, t2, big2;
-            suffix_scan(s_rh2, s_start2, 0xFFFFFFFFu, 0u, e2, t2, big2, -1);   // the top sub-bin starts at rank 0
-            if (tid == 0) s_maxbin = max(s_maxbin, big2);
-        }
-        __syncthreads();
+        unsigned e2, t2, big2;
+        block_suffix_scan(s_rh2, s_start2, 0xFFFFFFFFu, e2, t2, big2, -1);   // the top bin starts at rank 0
+        if (tid == 0) s_maxbin = max(s_maxbin, big2);
     } else if (tid == 0) {
         s_maxbin = max(s_maxbin, s_rh[kTopBin]);
     }
@@ -430,17 +483,15 @@ static __device__ Refined refine_candidates(const TopkArgs &A, int b, int n, uns
     const bool ranked = s_maxbin <= (unsigned)kBucketMax;
     if (!ranked) {
         // compact in any order, the caller sorts
-        __syncthreads();
-        if (tid == 0) s_cnt = 0u;
-        __syncthreads();
 #pragma unroll
         for (int k = 0; k < kCap / kSelThreads; ++k) {
             const int i = tid + k * kSelThreads;
             if (i < n && bin_of(mine[k]) >= edge) s[atomicAdd(&s_cnt, 1u)] = mine[k];
         }
         __syncthreads();
-        return {m, false};
+        return {m, false, nullptr};
     }
+    stamp(A.stamp, b, 10);
     // counting sort: scatter to the (sub-)bin's rank range ...
 #pragma unroll
     for (int k = 0; k < kCap / kSelThreads; ++k) {
@@ -456,10 +507,12 @@ static __device__ Refined refine_candidates(const TopkArgs &A, int b, int n, uns
                     pos = s_start[d] + atomicAdd(&s_fill[d], 1u);
                 }
                 s[pos] = mine[k];
+                pos1[pos] = (unsigned short)i;
             }
         }
     }
     __syncthreads();
+    stamp(A.stamp, b, 11);
     // ... then the exact rank inside the bin: keys are unique, so counting the larger mates is a permutation
     unsigned long long *sorted = s + kSortSlots;
     for (int p = tid; p < m; p += kSelThreads) {
@@ -475,9 +528,11 @@ static __device__ Refined refine_candidates(const TopkArgs &A, int b, int n, uns
         unsigned r = lo;
         for (unsigned j = lo; j < hi; ++j) r += s[j] > key;
         sorted[r] = key;
+        pos2[r] = pos1[p];
     }
     __syncthreads();
-    return {m, true};
+    stamp(A.stamp, b, 12);
+    return {m, true, pos2};
 }
 
 template <bool BOXES>

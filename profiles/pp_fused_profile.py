@@ -22,6 +22,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else 'd3'
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 regimes = (sys.argv[4] if len(sys.argv) > 4 else 'dense,planted').split(',')
+pipelines = (sys.argv[5] if len(sys.argv) > 5 else 'staged,persistent').split(',')
+show_timeline = os.environ.get('ODK_SHOW_TIMELINE', '1') == '1'
 size, scale = synth.MODEL_SHAPES[name]
 C, K, D = 90, 5000, 100
 dev = torch.device('cuda:0')
@@ -95,15 +97,35 @@ for regime in regimes:
     cls_out, box_out = make(regime)
     for soft in (False, True):
         for ood in ((False, True) if name == 'd5' else (False,)):
-            def fused():
-                return post_process_detect(cls_out, box_out, anchors.boxes, 5, C, K, D, soft, with_ood=ood, return_flags=True)
-
             def chain():
                 pp = _post_process(cls_out, box_out, 5, C, K)
                 return detect_batch(pp[0], pp[1], anchors.boxes, pp[2], pp[3], None, None, D, soft)
-            mf, ef, wf, out = timed(fused)
             mc, ec, wc, ref = timed(chain)
-            same = bool(torch.equal(out['detections'], ref[0]) and torch.equal(out['count'], ref[1]))
-            print(f'{name} B={B} {regime} soft={soft} ood={ood}: fused graph {mf:.4f} ms (eager {ef:.4f}, worst call {wf:.4f}) = '
-                  f'{GB / mf * 1e3:.0f} GB/s | chain graph {mc:.4f} ms (eager {ec:.4f}, worst call {wc:.4f}) | equal {same} | '
-                  f'kept min {int(out["count"].min())} | flagged images {int(out["flags"].sum())}/{B}', flush=True)
+            print(f'{name} B={B} {regime} soft={soft} ood={ood}: odk_topk + odk_detect chain: graph {mc:.4f} ms (eager {ec:.4f}, worst call {wc:.4f})', flush=True)
+            for pipe in pipelines:
+                def fused():
+                    return post_process_detect(cls_out, box_out, anchors.boxes, 5, C, K, D, soft, with_ood=ood, return_flags=True,
+                                               pipeline=pipe)
+                mf, ef, wf, out = timed(fused)
+                same = bool(torch.equal(out['detections'], ref[0]) and torch.equal(out['count'], ref[1]))
+                print(f'  odk_postprocess[{pipe}]: graph {mf:.4f} ms (eager {ef:.4f}, worst call {wf:.4f}) = {GB / mf * 1e3:.0f} GB/s '
+                      f'= {GB / mf * 1e3 / 6521.4:.3f} of peak | equal to chain {same} | kept min {int(out["count"].min())} | '
+                      f'flagged images {int(out["flags"].sum())}/{B}', flush=True)
+                if not show_timeline:
+                    continue
+                tl = out['timeline'].cpu().numpy().astype(np.int64)
+                ev = tl[:-2].reshape(B, 16).astype(np.float64)
+                t0 = float(tl[-2]) if pipe == 'persistent' else float(ev[:, 2].min())
+                ev = (ev - t0) / 1e3
+                if pipe == 'persistent':
+                    print(f'    persistent kernel (start -> last CTA out): {(tl[-1] - tl[-2]) / 1e3:.1f} us')
+                print('    per image, us: streamed claimed | tail start..end = select (hist scans scatter rank rest) filter decode offsets nms rows')
+                raw = tl[:-2].reshape(B, 16)
+                print('    candidates per image:', raw[:, 13].tolist())
+                print('    survivors (ranked):  ', [(int(v & 0xFFFFFFFF), int(v >> 32)) for v in raw[:, 14]])
+                order = np.argsort(ev[:, 2])
+                for i in list(order[:3]) + list(order[-3:]):
+                    e = ev[i]
+                    print(f'    {i:2d}: {e[0]:7.1f} {e[1]:7.1f} | {e[2]:7.1f}..{e[3]:7.1f} = {e[3] - e[2]:6.1f}: select {e[4] - e[2]:5.1f} '
+                          f'({e[9] - e[2]:4.1f} {e[10] - e[9]:4.1f} {e[11] - e[10]:4.1f} {e[12] - e[11]:4.1f} {e[4] - e[12]:4.1f}) '
+                          f'filter {e[5] - e[4]:5.1f} decode {e[6] - e[5]:5.1f} offsets {e[7] - e[6]:5.1f} nms {e[8] - e[7]:5.1f} rows {e[3] - e[8]:5.1f}')

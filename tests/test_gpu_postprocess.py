@@ -235,7 +235,7 @@ def test_ood_scores_and_fused_entry():
 
 
 # ---- odk_postprocess: the pipelined chain (sample -> persistent stream + per-image tails) ----------------
-def _fused_vs_chain(co, bo, size, C, K, D, soft, scale=None, isz=None, anchor_scale=4.0, ood=False):
+def _fused_vs_chain(co, bo, size, C, K, D, soft, scale=None, isz=None, anchor_scale=4.0, ood=False, pipeline='staged'):
     """post_process_detect must equal (a) the separate odk_topk -> odk_detect launches bit for bit and
     (b) the oracle chain under the usual bars."""
     from ood_object_detection_b200.anchors import detect_batch
@@ -245,7 +245,7 @@ def _fused_vs_chain(co, bo, size, C, K, D, soft, scale=None, isz=None, anchor_sc
     tc, tb, ta = [t(x) for x in co], [t(x) for x in bo], t(anc_np)
     ts = None if scale is None else t(scale)
     tz = None if isz is None else t(isz)
-    out = post_process_detect(tc, tb, ta, 5, C, K, D, soft, ts, tz, with_ood=ood, return_topk=True)
+    out = post_process_detect(tc, tb, ta, 5, C, K, D, soft, ts, tz, with_ood=ood, return_topk=True, pipeline=pipeline)
     cls_k, box_k, idx, klass = _post_process(tc, tb, 5, C, K)
     for name, ref in (('cls', cls_k), ('box', box_k), ('indices', idx), ('classes', klass)):
         assert torch.equal(out[name], ref), name
@@ -256,7 +256,7 @@ def _fused_vs_chain(co, bo, size, C, K, D, soft, scale=None, isz=None, anchor_sc
     anchor = torch.where(src >= 0, torch.gather(idx, 1, src.clamp(min=0).long()), torch.full_like(src, -1).long())
     assert torch.equal(out['anchor'], anchor)
     # without the top-k outputs the detections must not change
-    lean = post_process_detect(tc, tb, ta, 5, C, K, D, soft, ts, tz)
+    lean = post_process_detect(tc, tb, ta, 5, C, K, D, soft, ts, tz, pipeline=pipeline)
     assert torch.equal(lean['detections'], dets) and torch.equal(lean['count'], count)
     o_cls, o_box, o_idx, o_klass = orc.post_process(co, bo, 5, C, K)
     for i in range(B):
@@ -277,35 +277,42 @@ def _fused_vs_chain(co, bo, size, C, K, D, soft, scale=None, isz=None, anchor_sc
     return out
 
 
+PIPELINES = ['staged', 'persistent']
+
+
+@pytest.mark.parametrize('pipeline', PIPELINES)
 @pytest.mark.parametrize('soft', [False, True])
 @pytest.mark.parametrize('sparse', [False, True])
-def test_fused_postprocess_d0(soft, sparse):
+def test_fused_postprocess_d0(soft, sparse, pipeline):
     size, B, C, K, D = 512, 4, 90, 5000, 100
     co, bo = (synth.planted_outputs if sparse else synth.head_outputs)(310 + sparse, B, size, C)
-    _fused_vs_chain(co, bo, size, C, K, D, soft, ood=True)
+    _fused_vs_chain(co, bo, size, C, K, D, soft, ood=True, pipeline=pipeline)
 
 
+@pytest.mark.parametrize('pipeline', PIPELINES)
 @pytest.mark.parametrize('soft', [False, True])
-def test_fused_postprocess_d3_odd_level_scaled(soft):
+def test_fused_postprocess_d3_odd_level_scaled(soft, pipeline):
     """D3's 7x7 level: blocks of odd images start 8 bytes off the 16-byte grid (partial first / last groups);
     with img_scale / img_size the boxes are clipped and rescaled."""
     size, B, C, K, D = 896, 3, 90, 5000, 100
     co, bo = synth.head_outputs(320, B, size, C)
     scale = np.array([1.0, 1.25, 1.5], np.float32)
     isz = np.array([[size * 1.1, size * 0.9]] * B, np.float32)
-    _fused_vs_chain(co, bo, size, C, K, D, soft, scale, isz)
+    _fused_vs_chain(co, bo, size, C, K, D, soft, scale, isz, pipeline=pipeline)
 
 
 @pytest.mark.parametrize('name,B,C,K,D', [('d0', 3, 1, 2000, 30), ('d0', 1, 400, 5000, 100), ('d0', 5, 7, 6144, 64),
                                           ('d0', 2, 90, 300, 100)])
-def test_fused_postprocess_shapes(name, B, C, K, D):
+@pytest.mark.parametrize('pipeline', PIPELINES)
+def test_fused_postprocess_shapes(name, B, C, K, D, pipeline):
     size, _ = synth.MODEL_SHAPES[name]
     co, bo = synth.head_outputs(330 + B + C, B, size, C)
-    _fused_vs_chain(co, bo, size, C, K, D, False)
-    _fused_vs_chain(co, bo, size, C, K, D, True)
+    _fused_vs_chain(co, bo, size, C, K, D, False, pipeline=pipeline)
+    _fused_vs_chain(co, bo, size, C, K, D, True, pipeline=pipeline)
 
 
-def test_fused_postprocess_small_and_degenerate():
+@pytest.mark.parametrize('pipeline', PIPELINES)
+def test_fused_postprocess_small_and_degenerate(pipeline):
     """Tiny pyramids (fewer tasks than warps), images that leave the sampled path (constant, quantised, a
     huge tied plateau -> flagged, exact radix select + stand-alone detect behind the same entry point) next
     to ordinary ones in one batch."""
@@ -316,12 +323,12 @@ def test_fused_postprocess_small_and_degenerate():
         c[1] = np.round(c[1] * 2) / 2
         c[2] = np.where(c[2] > -4.6, np.float32(1.25), c[2])
     synth.make_tie_free([c[3:] for c in co])
-    out = _fused_vs_chain(co, bo, size, C, K, D, False, ood=True)
-    _fused_vs_chain(co, bo, size, C, K, D, True)
+    out = _fused_vs_chain(co, bo, size, C, K, D, False, ood=True, pipeline=pipeline)
+    _fused_vs_chain(co, bo, size, C, K, D, True, pipeline=pipeline)
     assert out['count'].shape == (B,)
     co, bo = synth.head_outputs(72, 2, 128, 3)
-    _fused_vs_chain(co, bo, 128, 3, 200, 20, False)
-    _fused_vs_chain(co, bo, 128, 3, 1000, 20, True)
+    _fused_vs_chain(co, bo, 128, 3, 200, 20, False, pipeline=pipeline)
+    _fused_vs_chain(co, bo, 128, 3, 1000, 20, True, pipeline=pipeline)
 
 
 def test_fused_postprocess_above_register_budget_uses_chain():
