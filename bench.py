@@ -1,16 +1,30 @@
 #!/usr/bin/env python
-"""Benchmark of the dense per-anchor hot path (BASELINE.json metric: images/sec).
+"""Benchmark of the dense per-anchor hot path (BASELINE.json metric: images/sec labeler+loss+postprocess).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME] [--only]
 
-Workload at every N (weak scaling, one process per GPU): BASELINE.json configs[1] --
-EfficientDet-D0 512x512 (49104 anchors, 90 classes), batch 64 per GPU, 10 gt boxes per image,
-training-target path = AnchorLabeler assignment + fused focal/Huber loss (forward, the pass
-the reference's DetBenchTrain.forward runs).  A "step" is one pass of that path over one batch of
-synthetic head outputs; inputs are resident in HBM for `value` (1.18 GB per step, far larger
-than the 126 MB L2, so nothing is served from cache between steps) and start in pinned HOST
-memory for `e2e`.  `--impl reference` times the CPU restatement of the reference path
-(oracle/, OpenMP over all host cores) on a bounded sample of the same workload.
+One JSON line.  Its top-level keys are the driver's contract for the HEADLINE workload; the other
+BASELINE.json configurations are measured in the same run and carried, each with its own value /
+roofline / cpu_baseline / e2e, under "workloads":
+
+  train_d0     (headline) configs[1]: EfficientDet-D0 512^2 (49104 anchors, 90 classes), batch 64 per GPU,
+               10 gt boxes per image: AnchorLabeler assignment + fused focal/Huber loss, FORWARD AND
+               GRADIENT (what DetBenchTrain.forward + loss.backward() run, reference bench.py:122-135,
+               pretrain.py:233-236).  Weak scaling; the loss sums cross ranks through NVLink peer mailboxes.
+  post_d3      configs[2]: D3 896^2 (150381 anchors), batch 32: top-5000 + decode + NMS-100 / soft-NMS
+               (DetBenchPredict's post-process, bench.py:93-100).  N > 1: the batch is sharded (strong
+               scaling) and the detections are all-gathered over NCCL (evaluator.py:38-39).
+  post_d5_ood  configs[3]: D5 1280^2 (306900 anchors), batch 32: post-process + per-detection OOD scores.
+  train_d7     configs[4]: D7 1536^2 (441936 anchors), batch 128, 100 gt/img: labeler + loss fwd+grad; N > 1:
+               sharded (strong scaling).
+  chain_d0_b8  configs[0]: the reference's CPU-runnable case, D0 batch 8: labeler + loss + top-5000 + NMS-100.
+
+A "step" is one pass of the path over one batch of synthetic head outputs.  `value` times it with the
+inputs resident in HBM (every input set is far larger than the 126 MB L2, so nothing is served from cache
+between steps), as a CUDA-graph replay bracketed by CUDA events, barrier + synchronize on both sides, max
+over ranks.  `e2e` times the same public-API call from pinned HOST buffers, host<->device copies inside the
+timed region.  `--impl reference` times the CPU restatement of the reference path (oracle/, OpenMP over
+all host cores) on a bounded sample of the headline workload.
 """
 import argparse
 import gc
@@ -26,10 +40,20 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 import numpy as np  # noqa: E402
 
-SIZE, SCALE, NUM_CLASSES, BATCH, NUM_GT = 512, 4.0, 90, 64, 10
+NUM_CLASSES = 90
 LOSS_KW = dict(num_classes=NUM_CLASSES, alpha=0.25, gamma=1.5, delta=0.1, box_loss_weight=50.0)
-WORKLOAD = 'D0-512 A=49104 C=90 B=64/GPU M=10: AnchorLabeler + fused focal/huber loss (fwd)'
-METRIC = 'images/sec labeler+loss (D0 512x512 batch 64 training-target path)'
+K_TOP, D_MAX = 5000, 100
+METRIC = 'images/sec labeler+loss+postprocess at D0/D3 (headline: D0 512x512 batch 64 labeler + loss fwd+grad)'
+
+# survey-time measurements of the UNMODIFIED reference (torch 2.11 CPU, 8 threads): the
+# reference tree cannot travel to the GPU box, so its own numbers are carried next to the C port's
+TORCH_REFERENCE_SURVEY = {
+    'source': 'BASELINE.md section 2: reference python path imported from /root/reference, torch 2.11 CPU, 8 threads, best of 3',
+    'd0_b8_m10': {'labeler_s': 0.039, 'loss_fwd_s': 0.425, 'post_process_s': 0.188, 'nms_s': 0.078, 'images_per_s': 11.0},
+    'd0_b8_labeler_plus_loss_images_per_s': 17.2,
+    'd3_b4_m10': {'labeler_s': 0.042, 'loss_fwd_s': 0.567, 'post_process_s': 0.339, 'nms_s': 0.036, 'images_per_s': 4.1},
+    'd0_b8_soft_nms_images_per_s': 0.38,
+}
 
 
 def peaks():
@@ -40,54 +64,83 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
-# --------------------------------------------------------------------------------- CPU baseline
-class CpuReference:
-    """The oracle (CPU restatement of anchors.py:384-438 + loss.py:224-298) on a fixed synthetic
-    sample of the workload; inputs are generated once, only the path itself is timed."""
+# --------------------------------------------------------------------------------- CPU baselines (oracle/)
+class CpuTrain:
+    """The oracle (CPU restatement of anchors.py:384-438 + loss.py:224-298, forward and gradient) on a fixed
+    synthetic sample; inputs are generated once, only the path itself is timed."""
 
-    def __init__(self, batch):
+    def __init__(self, model, batch, num_gt):
         import synth
         from oracle import oracle as orc
         self.orc, self.batch = orc, batch
         self.threads = orc.use_all_cores()
-        self.anchors = orc.anchor_boxes(3, 7, 3, synth.ASPECTS, SCALE, (SIZE, SIZE))
-        self.gb, self.gc = synth.gt_boxes(7, batch, SIZE, NUM_GT, NUM_CLASSES)
-        self.co, self.bo = synth.head_outputs(8, batch, SIZE, NUM_CLASSES, tie_free=False)
-        self.fhw = synth.feat_hw(SIZE)
+        size, scale = synth.MODEL_SHAPES[model]
+        self.anchors = orc.anchor_boxes(3, 7, 3, synth.ASPECTS, scale, (size, size))
+        self.gb, self.gc = synth.gt_boxes(7, batch, size, num_gt, NUM_CLASSES)
+        self.co, self.bo = synth.head_outputs(8, batch, size, NUM_CLASSES, tie_free=False)
+        self.fhw = synth.feat_hw(size)
 
-    def step(self):
+    def step(self, grad=True):
         orc = self.orc
         t0 = time.perf_counter()
         cls_t, box_t, npos, _, _ = orc.batch_label_anchors(self.anchors, list(self.gb), list(self.gc))
         out = orc.loss_fn(self.co, self.bo, orc.split_levels(cls_t, self.fhw), orc.split_levels(box_t, self.fhw), npos,
-                          NUM_CLASSES, LOSS_KW['alpha'], LOSS_KW['gamma'], LOSS_KW['delta'], LOSS_KW['box_loss_weight'])
-        return time.perf_counter() - t0, out
+                          NUM_CLASSES, LOSS_KW['alpha'], LOSS_KW['gamma'], LOSS_KW['delta'], LOSS_KW['box_loss_weight'],
+                          want_grad=grad)
+        return time.perf_counter() - t0, out[:3]
 
 
-def cpu_reference_rate(batch, reps):
-    ref = CpuReference(batch)
-    best = min(ref.step()[0] for _ in range(reps))
-    return batch / best, ref.threads
+class CpuPost:
+    """The oracle's post-process chain (bench.py:12-76, anchors.py:95-172) on a fixed synthetic sample."""
+
+    def __init__(self, model, batch, soft, ood):
+        import synth
+        from oracle import oracle as orc
+        self.orc, self.batch, self.soft, self.ood = orc, batch, soft, ood
+        self.threads = orc.use_all_cores()
+        size, scale = synth.MODEL_SHAPES[model]
+        self.anchors = orc.anchor_boxes(3, 7, 3, synth.ASPECTS, scale, (size, size))
+        self.co, self.bo = synth.head_outputs(9, batch, size, NUM_CLASSES, tie_free=False)
+
+    def step(self):
+        orc = self.orc
+        t0 = time.perf_counter()
+        cls_k, box_k, idx, klass = orc.post_process(self.co, self.bo, 5, NUM_CLASSES, K_TOP)
+        for i in range(self.batch):
+            det, src = orc.generate_detections(cls_k[i], box_k[i], self.anchors, idx[i], klass[i], None, None, D_MAX, self.soft,
+                                               return_src=True)
+            if self.ood:
+                rows = orc.gather_logit_rows(self.co, idx[i][src][None].repeat(self.batch, 0), NUM_CLASSES)[i]
+                orc.ood_scores(rows, 1.0)
+        return time.perf_counter() - t0
+
+
+def cpu_record(kind, model, batch, reps, what, **kw):
+    ref = CpuTrain(model, batch, kw['num_gt']) if kind == 'train' else CpuPost(model, batch, kw.get('soft', False), kw.get('ood', False))
+    best = min((ref.step()[0] if kind == 'train' else ref.step()) for _ in range(reps))
+    return {'value': batch / best, 'unit': 'images/s', 'cores': ref.threads, 'kind': 'port',
+            'sample': f'{what}, B={batch} images per step, best of {reps} (oracle/, C + OpenMP on all host cores)'}
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the headline path on the box's host cores."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     sample_b = 8
-    ref = CpuReference(sample_b)
+    ref = CpuTrain('d0', sample_b, 10)
     for _ in range(max(args.warmup, 1)):
         ref.step()
     dt = sum(ref.step()[0] for _ in range(args.steps)) / max(args.steps, 1)
-    threads = ref.threads
     value = sample_b / dt
-    sample = f'D0-512 C=90 M=10 labeler+loss fwd on B={sample_b} images per step (of the B=64 workload)'
+    sample = f'D0-512 C=90 M=10 labeler + loss fwd+grad on B={sample_b} images per step (of the B=64 workload)'
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'reference_sample': sample},
-        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'config': {'workload': TrainWorkload.describe('d0', 64, 10), 'reference_sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': ref.threads, 'kind': 'port', 'sample': sample,
+                         'torch_reference_survey': TORCH_REFERENCE_SURVEY},
         'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
@@ -141,290 +194,550 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
 
 
-# --------------------------------------------------------------------------------- GPU arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+# --------------------------------------------------------------------------------- GPU harness
+class Ctx:
+    """Per-process state shared by the workloads: device, ranks, timing helpers."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise RuntimeError('bench.py needs a CUDA device: the hot path only exists as sm_100a kernels')
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
+        from ood_object_detection_b200 import _lib
+        _lib.lib()
+        self.peak, self.peak_src = peaks()
+
+    def sync_all(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        t = self.torch.tensor([ms], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def capture(self, fn):
+        """fn as a CUDA graph (warmed up on the capture stream first); (graph, outputs) or (None, None)."""
+        torch = self.torch
+        if self.args.no_graph:
+            return None, None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    fn()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side):
+                    out = fn()
+            torch.cuda.current_stream().wait_stream(side)
+            for _ in range(3):
+                gr.replay()
+            torch.cuda.synchronize()
+            return gr, out
+        except Exception as exc:   # capture is an optimisation, never a requirement
+            torch.cuda.synchronize()
+            self.capture_error = f'{type(exc).__name__}: {exc}'
+            return None, None
+
+    def timed(self, launch, steps, after=None):
+        """EXACTLY `steps` calls of launch() between two events, barrier + synchronize on both sides, max over
+        ranks -> ms per step."""
+        torch = self.torch
+        self.sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            launch()
+        if after is not None:
+            after()
+        b.record()
+        self.sync_all()
+        return self.max_over_ranks(a.elapsed_time(b)) / steps
+
+
+def device_outputs(torch, dev, seed, B, size, C):
     import synth
-    from ood_object_detection_b200 import _lib
-    from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
-    from ood_object_detection_b200.loss import loss_fn_fused
-    from ood_object_detection_b200.distributed import (PeerMailbox, all_reduce_partial_sums,
-                                                       forward_losses_one_collective, local_partial_sums)
-
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise RuntimeError('bench.py needs a CUDA device: the hot path only exists as sm_100a kernels')
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    _lib.lib()
-
-    # ---- synthetic inputs of the named shape, generated on the device (SURVEY 8d recipe) ----
     g = torch.Generator(device=dev)
-    g.manual_seed(1 + rank)
-    anchors = Anchors(3, 7, 3, synth.ASPECTS, SCALE, (SIZE, SIZE)).to(dev)
-    labeler = AnchorLabeler(anchors, NUM_CLASSES, match_threshold=0.5)
-    feat = synth.feat_hw(SIZE)
-    cls_out = [torch.randn((BATCH, 9 * NUM_CLASSES, h, w), generator=g, device=dev) * 1.5 - 4.6 for h, w in feat]
-    box_out = [torch.randn((BATCH, 36, h, w), generator=g, device=dev) * 0.2 for h, w in feat]
-    gb_np, gc_np = synth.gt_boxes(100 + rank, BATCH, SIZE, NUM_GT, NUM_CLASSES)
-    gt_boxes, gt_cls = torch.from_numpy(gb_np).to(dev), torch.from_numpy(gc_np).to(dev)
-    A = anchors.boxes.shape[0]
-    bytes_loss = BATCH * A * (4 * NUM_CLASSES + 16)          # A*(4C+16) bytes per image, forward
+    g.manual_seed(seed)
+    feat = synth.feat_hw(size)
+    cls = [torch.randn((B, 9 * C, h, w), generator=g, device=dev) * 1.5 - 4.6 for h, w in feat]
+    box = [torch.randn((B, 36, h, w), generator=g, device=dev) * 0.2 for h, w in feat]
+    return cls, box
 
-    unit = torch.ones((1,), dtype=torch.float32, device=dev)
 
-    def compute():
-        """Our kernels for one batch: labeler -> fused loss.  N > 1: partial sums against a unit normaliser,
-        both kernels writing into one 4-float buffer; with peer mailboxes the loss kernel's finishing CTA also
-        trades them with the other ranks, so the launch sequence is the same as on one GPU."""
-        if world > 1:
-            return local_partial_sums(labeler, cls_out, box_out, gt_boxes, gt_cls, unit, mailbox=mailbox, **LOSS_KW), None
-        lb = labeler.assign(gt_boxes, gt_cls)
-        return loss_fn_fused(cls_out, box_out, lb, **LOSS_KW), lb.num_positives
+class TrainWorkload:
+    """AnchorLabeler assignment + fused focal/Huber loss, forward and gradient, B images per rank."""
 
-    # N > 1: the only exchange is 4 floats per rank and step.  Preferred: remote stores into peer mailboxes
-    # over NVLink (no collective kernel, ranks not in lockstep); fallback: one NCCL all-reduce.
-    mailbox, exchange = None, 'none'
-    if world > 1:
+    @staticmethod
+    def describe(model, B, M):
+        import synth
+        size, _ = synth.MODEL_SHAPES[model]
+        return (f'{model.upper()}-{size} A={synth.num_anchors(size)} C={NUM_CLASSES} B={B}/GPU M={M}: AnchorLabeler + fused '
+                f'focal/huber loss, forward + gradient')
+
+    def __init__(self, ctx, model, batch, num_gt, seed=1):
+        import synth
+        from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
+        torch = ctx.torch
+        self.ctx, self.model, self.B, self.M = ctx, model, batch, num_gt
+        size, scale = synth.MODEL_SHAPES[model]
+        self.size = size
+        self.anchors = Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size)).to(ctx.dev)
+        self.labeler = AnchorLabeler(self.anchors, NUM_CLASSES, match_threshold=0.5)
+        self.cls, self.box = device_outputs(torch, ctx.dev, seed + ctx.rank, batch, size, NUM_CLASSES)
+        for t in self.cls + self.box:
+            t.requires_grad_(True)
+        gb, gc_ = synth.gt_boxes(100 + seed + ctx.rank, batch, size, num_gt, NUM_CLASSES)
+        self.gb_np, self.gc_np = gb, gc_
+        self.gt_boxes, self.gt_cls = torch.from_numpy(gb).to(ctx.dev), torch.from_numpy(gc_).to(ctx.dev)
+        self.A = self.anchors.boxes.shape[0]
+        self.bytes_fwd = batch * self.A * (4 * NUM_CLASSES + 16)      # SURVEY 8d: A*(4C+16) bytes per image, forward
+        self.buf = torch.zeros((4,), dtype=torch.float32, device=ctx.dev)   # [total, cls, box, sum(num_pos)+1]
+        self.mailbox, self.exchange = None, 'none'
+
+    def setup_exchange(self):
+        """N > 1: the loss sums of the global batch for logging (the reference's reduce_dict): NVLink peer mailboxes
+        written by the loss kernel itself, else one NCCL all-reduce."""
+        from ood_object_detection_b200.distributed import PeerMailbox
+        ctx, torch = self.ctx, self.ctx.torch
+        if ctx.world == 1:
+            return
         ok, why = 1, ''
-        if args.no_peer:
+        if ctx.args.no_peer:
             ok, why = 0, 'disabled by --no-peer'
         else:
             try:
-                mailbox = PeerMailbox(dev)
+                self.mailbox = PeerMailbox(ctx.dev)
             except Exception as exc:
                 ok, why = 0, f'{type(exc).__name__}: {exc}'
-        flag = torch.tensor([ok], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        flag = torch.tensor([ok], device=ctx.dev)
+        ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
-            mailbox = None
-        exchange = ('peer mailboxes over NVLink, written by the loss kernel (odk_loss_params.exchange)' if mailbox is not None
-                    else f'nccl all-reduce of 4 floats ({why or "a peer could not map the mailboxes"})')
-    def step():
-        """One eager step through the public API (warm-up and the untimed clock-sampling load)."""
-        out, _ = compute()
-        if world == 1:
-            return out
-        if mailbox is not None:
-            return mailbox.previous()     # global sums of the step before (this step's are on the wire)
-        return all_reduce_partial_sums(out)
+            self.mailbox = None
+        self.exchange = ('peer mailboxes over NVLink, written by the loss kernel (odk_loss_params.exchange)' if self.mailbox is not None
+                         else f'nccl all-reduce of 4 floats ({why or "a peer could not map the mailboxes"})')
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
-            step()
-        sync_all()
-        # The compute part of a step is a fixed launch sequence (memsets, our kernels, tiny torch kernels):
-        # it is captured once into a CUDA graph and replayed, so the timed region measures the GPU, not the
-        # python launch path.  The NCCL all-reduce (N > 1) stays outside the graph.
-        # N > 1: the exchange is captured too, software-pipelined -- a replay collects the PREVIOUS step's
-        # global sums while this step's kernels run, so a step costs the host one graph launch:
-        #   mailboxes: one graph  = [labeler -> loss], whose last CTA collects(previous) and publishes(current);
-        #   nccl     : two graphs = [all-reduce bufs[1-k]] || [labeler], join, [loss -> bufs[k]].
-        graphs, graph_outs, mode = [], [], 'eager'
-        bufs = [torch.zeros((4,), dtype=torch.float32, device=dev) for _ in range(2)]
-        if not args.no_graph:
-            try:
-                side, aux = torch.cuda.Stream(), torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    compute()
-                    for k in range(2 if (world > 1 and mailbox is None) else 1):
-                        gr = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(gr, stream=side):
-                            if world == 1 or mailbox is not None:
-                                graph_outs.append(compute()[0])
-                            else:
-                                aux.wait_stream(side)                      # fork
-                                with torch.cuda.stream(aux):
-                                    reduced = all_reduce_partial_sums(bufs[1 - k], copy=False)
-                                lb = labeler.assign(gt_boxes, gt_cls, normalizer_out=bufs[k][3:4])
-                                # join BEFORE the loss: its persistent grid fills every SM, so a collective
-                                # kernel still resident would hold one of its CTAs back for the whole pass
-                                side.wait_stream(aux)
-                                loss_fn_fused(cls_out, box_out, lb, normalizer=unit, out=bufs[k], **LOSS_KW)
-                                graph_outs.append(reduced)
-                        graphs.append(gr)
-                torch.cuda.current_stream().wait_stream(side)
-                for _ in range(3):
-                    for gr in graphs:
-                        gr.replay()
-                torch.cuda.synchronize()
-                mode = 'cuda_graph' if world == 1 else 'cuda_graph (kernels + pipelined exchange)'
-            except Exception as exc:  # capture is an optimisation, never a requirement
-                graphs, mode = [], f'eager (graph capture failed: {type(exc).__name__})'
-                torch.cuda.synchronize()
-        if sampler:
-            sampler.start()
-        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_start.record()
-        last = None
-        if graphs:
-            for i in range(args.steps):
-                graphs[i % len(graphs)].replay()
-            if world == 1:
-                last = graph_outs[0]
-            elif mailbox is not None:   # the last step's record is still in the mailboxes: inside the timed region
-                last = mailbox.collect()[0]
-            else:
-                last = all_reduce_partial_sums(bufs[(args.steps - 1) % 2])
+    def step(self, grad=True):
+        """One training step's worth of the path through the public API: labeler -> fused loss (+ backward)."""
+        from ood_object_detection_b200.loss import loss_fn_fused
+        lb = self.labeler.assign(self.gt_boxes, self.gt_cls, normalizer_out=self.buf[3:4], transient=True)
+        ex = None if self.mailbox is None else self.mailbox.attach(self.buf[3:4], normalized=True)
+        if grad:
+            self.drop_grads()   # backward() then hands its buffers over as .grad instead of accumulating into old ones
+            tot, _, _ = loss_fn_fused(self.cls, self.box, lb, out=self.buf, exchange=ex, **LOSS_KW)
+            tot.backward()
         else:
-            for i in range(args.steps):
-                last = step()
-            if mailbox is not None:         # eager steps return the previous step's sums: drain the last one
-                last = mailbox.collect()[0]
-        t_end.record()
-        sync_all()
-        total_ms = t_start.elapsed_time(t_end)
-        if world > 1:
-            if mailbox is not None and int(mailbox.status.item()) != 0:
-                raise RuntimeError('peer mailbox exchange timed out: a rank did not publish its partial sums')
-            # graphs that hold NCCL kernels must be gone before the process group is torn down
-            last = [float(x) for x in last]
-            graphs.clear()
-            graph_outs.clear()
-            gc.collect()
-            torch.cuda.synchronize()
-        # the dominant kernel alone: K back-to-back launches of the loss on the same inputs (its 4-byte
-        # counter memset included), one event pair around them -- the queue stays full, so this is device
-        # time per launch, not python time
-        lb_fixed = labeler.assign(gt_boxes, gt_cls)
-        for _ in range(3):
-            loss_fn_fused(cls_out, box_out, lb_fixed, **LOSS_KW)
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        k0.record()
-        for _ in range(args.steps):
-            loss_fn_fused(cls_out, box_out, lb_fixed, **LOSS_KW)
-        k1.record()
-        sync_all()
-        # keep the same load running (untimed) for ~60 ms so the clock sampler sees the GPU under it;
-        # every rank runs the SAME number of extra steps (the step contains collectives)
-        shared = torch.tensor([total_ms], device=dev)
-        if world > 1:
-            dist.all_reduce(shared, op=dist.ReduceOp.MAX)
-        n_extra = int(min(400, max(0, np.ceil((60.0 - shared.item()) / max(shared.item() / args.steps, 1e-3)))))
-        for _ in range(n_extra):
-            step()
-        torch.cuda.synchronize()
-        clocks = sampler.stop() if sampler else None
-        loss_ms = k0.elapsed_time(k1) / args.steps
+            with self.ctx.torch.no_grad():
+                loss_fn_fused([c.detach() for c in self.cls], [b.detach() for b in self.box], lb, out=self.buf, exchange=ex, **LOSS_KW)
+        if self.ctx.world > 1 and self.mailbox is None:   # fallback exchange: one NCCL all-reduce of the un-normalised sums
+            with self.ctx.torch.no_grad():
+                part = self.buf.detach().clone()
+                part[:3] *= part[3]
+                self.ctx.dist.all_reduce(part, op=self.ctx.dist.ReduceOp.SUM)
+                self.global_loss = part[:3] / (part[3] - float(self.ctx.world - 1))
+        return self.buf
 
-        # ---- forward + gradient in the same pass (what a training step needs), untimed extra ----
-        co_g = [c.requires_grad_(True) for c in cls_out]
-        bo_g = [b.requires_grad_(True) for b in box_out]
-    torch.cuda.synchronize()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nfb = max(3, min(args.steps, 10))
-    for i in range(2 + nfb):
-        if i == 2:
-            g0.record()
-        lb = labeler.assign(gt_boxes, gt_cls)
-        tot, _, _ = loss_fn_fused(co_g, bo_g, lb, **LOSS_KW)
-        tot.backward()
-        for t in co_g + bo_g:
+    def drop_grads(self):
+        for t in self.cls + self.box:
             t.grad = None
-    g1.record()
-    torch.cuda.synchronize()
-    fwd_bwd_ms = g0.elapsed_time(g1) / nfb
-    for t in cls_out + box_out:
-        t.requires_grad_(False)
 
-    tmax = torch.tensor([total_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms = float(tmax.item())
-    ms_per_step = total_ms / args.steps
-    value = world * BATCH / (ms_per_step * 1e-3)
+    def measure(self, steps, warmup, grad=True):
+        """-> (ms per step, launch mode)."""
+        ctx = self.ctx
+        for _ in range(max(warmup, 3)):
+            self.step(grad)
+        self.drop_grads()
+        ctx.sync_all()
+        gr = None
+        if not (ctx.world > 1 and self.mailbox is None):   # (the NCCL fallback exchange stays outside graphs)
+            gr, _ = ctx.capture(lambda: self.step(grad))
+        mode = 'cuda_graph' if gr is not None else 'eager'
+        drain = None
+        if self.mailbox is not None:     # the last step's record is still in the mailboxes: inside the timed region
+            drain = lambda: self.mailbox.collect()   # noqa: E731
+        ms = ctx.timed(gr.replay if gr is not None else (lambda: self.step(grad)), steps, after=drain)
+        self.graph = gr   # keep the graph's pool alive while its outputs (.grad) are in use
+        return ms, mode
 
-    # ---- e2e: same step through the public API from pinned HOST buffers, loss read back ----
-    with torch.no_grad():
-        h_cls = [c.cpu().pin_memory() for c in cls_out]
-        h_box = [b.cpu().pin_memory() for b in box_out]
-        h_gb, h_gc = gt_boxes.cpu().pin_memory(), gt_cls.cpu().pin_memory()
+    def kernel_ms(self, steps):
+        """The dominant kernel alone: back-to-back launches of the fused loss (forward + gradient) on a fixed
+        assignment, its 4-byte counter memset included; the queue stays full, so this is device time per launch."""
+        from ood_object_detection_b200.loss import loss_fn_fused
+        torch = self.ctx.torch
+        lb = self.labeler.assign(self.gt_boxes, self.gt_cls)
+        outs = []
+
+        def once():
+            tot, _, _ = loss_fn_fused(self.cls, self.box, lb, **LOSS_KW)   # gradients are written in the same pass
+            outs.append(tot)
+            if len(outs) > 2:
+                outs.pop(0)
+        for _ in range(3):
+            once()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            once()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+
+    def e2e(self, steps):
+        """The same step from pinned HOST buffers: H2D of logits / boxes / gt each step, D2H of the 3 loss scalars."""
+        from ood_object_detection_b200.loss import loss_fn_fused
+        ctx, torch = self.ctx, self.ctx.torch
+        with torch.no_grad():
+            h_cls = [c.detach().cpu().pin_memory() for c in self.cls]
+            h_box = [b.detach().cpu().pin_memory() for b in self.box]
+        h_gb, h_gc = self.gt_boxes.cpu().pin_memory(), self.gt_cls.cpu().pin_memory()
         h_out = torch.empty((3,), dtype=torch.float32).pin_memory()
         h2d = sum(t.numel() * t.element_size() for t in h_cls + h_box + [h_gb, h_gc])
 
-        def e2e_step():
-            d_cls = [t.to(dev, non_blocking=True) for t in h_cls]
-            d_box = [t.to(dev, non_blocking=True) for t in h_box]
-            lb = labeler.assign(h_gb.to(dev, non_blocking=True), h_gc.to(dev, non_blocking=True))
-            out = loss_fn_fused(d_cls, d_box, lb, normalizer=unit if world > 1 else None, **LOSS_KW)
-            if world > 1:
-                out = forward_losses_one_collective(out[1], out[2], lb.num_positives, LOSS_KW['box_loss_weight'])
-            h_out.copy_(torch.stack(list(out)), non_blocking=True)
+        def once():
+            d_cls = [t.to(ctx.dev, non_blocking=True).requires_grad_(True) for t in h_cls]
+            d_box = [t.to(ctx.dev, non_blocking=True).requires_grad_(True) for t in h_box]
+            lb = self.labeler.assign(h_gb.to(ctx.dev, non_blocking=True), h_gc.to(ctx.dev, non_blocking=True), transient=True)
+            out = loss_fn_fused(d_cls, d_box, lb, **LOSS_KW)
+            out[0].backward()          # gradients stay on the device: they feed the head's backward pass there
+            h_out.copy_(torch.stack([o.detach() for o in out]), non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return h_out
-
-        e2e_steps = max(2, min(args.steps, 10))
         for _ in range(2):
-            e2e_step()
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(e2e_steps):
-            e2e_step()
-        e1.record()
-        sync_all()
-        e2e_ms = torch.tensor([e0.elapsed_time(e1) / e2e_steps], device=dev)
-        if world > 1:
-            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        e2e_value = world * BATCH / (float(e2e_ms.item()) * 1e-3)
+            once()
+        ms = ctx.timed(once, steps)
         del h_cls, h_box
+        return {'value': ctx.world * self.B / (ms * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
+                'steps': steps, 'ms_per_step': ms}
 
-    extra = {}
-    if rank == 0 and not args.no_extra:
-        try:
-            extra = postprocess_extra(torch, dev, synth)
-        except Exception as exc:  # the extra block must never take the headline down
-            extra = {'error': repr(exc)}
+    def oracle_check(self):
+        """This rank's loss against the CPU oracle on the same inputs (rel. error of total / cls / box)."""
+        from oracle import oracle as orc
+        import synth
+        torch = self.ctx.torch
+        with torch.no_grad():
+            got = [float(x) for x in self.step(grad=False)[:3].cpu()]
+        oc, ob, onp, _, _ = orc.batch_label_anchors(self.anchors.boxes.cpu().numpy(), list(self.gb_np), list(self.gc_np))
+        fhw = synth.feat_hw(self.size)
+        ref = orc.loss_fn([c.detach().cpu().numpy() for c in self.cls], [b.detach().cpu().numpy() for b in self.box],
+                          orc.split_levels(oc, fhw), orc.split_levels(ob, fhw), onp, NUM_CLASSES, LOSS_KW['alpha'], LOSS_KW['gamma'],
+                          LOSS_KW['delta'], LOSS_KW['box_loss_weight'])
+        return max(abs(g - r) / max(abs(r), 1e-30) for g, r in zip(got, ref[:3]))
+
+
+class PostWorkload:
+    """DetBenchPredict's post-process: top-k -> decode -> NMS / soft-NMS (-> OOD scores) for B images per rank."""
+
+    def __init__(self, ctx, model, batch_global, soft, ood, seed=3):
+        import synth
+        from ood_object_detection_b200.anchors import Anchors
+        from ood_object_detection_b200.distributed import shard_range
+        torch = ctx.torch
+        self.ctx, self.model, self.soft, self.ood = ctx, model, soft, ood
+        lo, hi = shard_range(batch_global, ctx.rank, ctx.world)
+        self.Bg, self.B = batch_global, hi - lo
+        size, scale = synth.MODEL_SHAPES[model]
+        self.anchors = Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size)).to(ctx.dev)
+        self.cls, self.box = device_outputs(torch, ctx.dev, seed + ctx.rank, self.B, size, NUM_CLASSES)
+        self.A = self.anchors.boxes.shape[0]
+        self.bytes = self.B * self.A * 4 * NUM_CLASSES               # SURVEY 8d: A*4C bytes per image
+        self.size = size
+
+    def describe(self):
+        return (f'{self.model.upper()}-{self.size} A={self.A} C={NUM_CLASSES} B={self.Bg} top-{K_TOP} + decode + '
+                f'{"soft-" if self.soft else ""}NMS-{D_MAX}{" + OOD energy/max-logit" if self.ood else ""}')
+
+    def step(self, cls=None, box=None, pipeline='staged'):
+        from ood_object_detection_b200.bench import post_process_detect
+        from ood_object_detection_b200.distributed import gather_detections
+        out = post_process_detect(cls or self.cls, box or self.box, self.anchors.boxes, 5, NUM_CLASSES, K_TOP, D_MAX, self.soft,
+                                  with_ood=self.ood, pipeline=pipeline)
+        if self.ctx.world > 1:   # evaluator.py:38-39: every rank sees every image's detections
+            extras = [out['energy'], out['max_logit']] if self.ood else None
+            return gather_detections(out['detections'], out['count'], extras)
+        return out
+
+    def measure(self, steps, warmup, pipeline='staged'):
+        ctx = self.ctx
+        with ctx.torch.no_grad():
+            for _ in range(max(warmup, 3)):
+                self.step(pipeline=pipeline)
+            ctx.sync_all()
+            gr = None
+            if ctx.world == 1:           # NCCL collectives stay outside graphs here
+                gr, _ = ctx.capture(lambda: self.step(pipeline=pipeline))
+            ms = ctx.timed(gr.replay if gr is not None else (lambda: self.step(pipeline=pipeline)), steps)
+            worst = 0.0
+            if ctx.world == 1:           # the slowest single call (allocator stalls, clock ramps show up here)
+                torch = ctx.torch
+                for _ in range(min(steps, 10)):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    (gr.replay if gr is not None else self.step)()
+                    b.record()
+                    torch.cuda.synchronize()
+                    worst = max(worst, a.elapsed_time(b))
+        return ms, ('cuda_graph' if gr is not None else 'eager'), worst
+
+    def e2e(self, steps):
+        ctx, torch = self.ctx, self.ctx.torch
+        with torch.no_grad():
+            h_cls = [c.cpu().pin_memory() for c in self.cls]
+            h_box = [b.cpu().pin_memory() for b in self.box]
+            h_det = torch.empty((self.B, D_MAX, 6), dtype=torch.float32).pin_memory()
+            h_cnt = torch.empty((self.B,), dtype=torch.int32).pin_memory()
+            h2d = sum(t.numel() * t.element_size() for t in h_cls + h_box)
+
+            def once():
+                from ood_object_detection_b200.bench import post_process_detect
+                d_cls = [t.to(ctx.dev, non_blocking=True) for t in h_cls]
+                d_box = [t.to(ctx.dev, non_blocking=True) for t in h_box]
+                out = post_process_detect(d_cls, d_box, self.anchors.boxes, 5, NUM_CLASSES, K_TOP, D_MAX, self.soft, with_ood=self.ood)
+                h_det.copy_(out['detections'], non_blocking=True)
+                h_cnt.copy_(out['count'], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            for _ in range(2):
+                once()
+            ms = ctx.timed(once, steps)
+        return {'value': self.Bg / (ms * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': h_det.numel() * 4 + h_cnt.numel() * 4, 'steps': steps, 'ms_per_step': ms}
+
+
+def roofline(ctx, kernel, algorithmic_bytes, ms, traffic=None):
+    achieved = algorithmic_bytes / (ms * 1e-3) / 1e9
+    return {'bound': 'hbm', 'kernel': kernel, 'achieved': achieved, 'peak': ctx.peak, 'unit': 'GB/s', 'frac': achieved / ctx.peak,
+            'traffic': traffic, 'peak_source': ctx.peak_src, 'algorithmic_bytes_per_launch': algorithmic_bytes, 'kernel_ms': ms}
+
+
+def traffic_of(key):
+    tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tp):
+        with open(tp) as f:
+            return json.load(f).get(key)
+    return None
+
+
+# --------------------------------------------------------------------------------- workload records
+def record_train(ctx, model, batch, num_gt, steps, warmup, with_cpu, scaling, e2e_batch=None):
+    """A full record for one labeler+loss configuration (global batch `batch` when scaling == 'strong')."""
+    from ood_object_detection_b200.distributed import shard_range
+    if scaling == 'strong':
+        lo, hi = shard_range(batch, ctx.rank, ctx.world)
+        local, total = hi - lo, batch
+    else:
+        local, total = batch, batch * ctx.world
+    w = TrainWorkload(ctx, model, local, num_gt)
+    ms, mode = w.measure(steps, warmup, grad=True)
+    ms_fwd, _ = w.measure(steps, warmup, grad=False)
+    rec = {'workload': TrainWorkload.describe(model, local, num_gt), 'value': total / (ms * 1e-3), 'unit': 'images/s', 'ms_per_step': ms,
+           'scaling': scaling, 'global_batch': total, 'launch': mode,
+           'forward_only': {'ms_per_step': ms_fwd, 'images_per_s': total / (ms_fwd * 1e-3),
+                            'frac_of_peak': w.bytes_fwd / (ms_fwd * 1e-3) / 1e9 / ctx.peak},
+           'step_frac_of_peak': 2 * w.bytes_fwd / (ms * 1e-3) / 1e9 / ctx.peak}
+    if ctx.rank == 0:
+        k_ms = w.kernel_ms(max(5, min(steps, 20)))
+        rec['roofline'] = roofline(ctx, 'odk::loss_kernel_ring<new,grad,fused>', 2 * w.bytes_fwd, k_ms, traffic_of('loss_grad_kernel_dram_bytes_per_launch'))
+    w.drop_grads()
+    if e2e_batch is None:
+        rec['e2e'] = w.e2e(max(2, min(steps, 6)))
+    del w
+    gc.collect()
+    ctx.torch.cuda.empty_cache()
+    if e2e_batch is not None:   # a bounded slice: the full batch does not fit a sensible pinned host buffer
+        w2 = TrainWorkload(ctx, model, e2e_batch, num_gt)
+        rec['e2e'] = w2.e2e(3)
+        rec['e2e']['note'] = f'measured on B={e2e_batch} images per step per rank (the full batch is {local})'
+        del w2
+        gc.collect()
+        ctx.torch.cuda.empty_cache()
+    if with_cpu and ctx.rank == 0:
+        rec['cpu_baseline'] = cpu_record('train', model, 8 if model == 'd0' else 2, 2, f'{model.upper()} C=90 M={num_gt} labeler + loss fwd+grad', num_gt=num_gt)
+    return rec
+
+
+def record_post(ctx, model, batch, soft, ood, steps, warmup, with_cpu, pipelines=('staged',)):
+    w = PostWorkload(ctx, model, batch, soft, ood)
+    ms, mode, worst = w.measure(steps, warmup, pipelines[0])
+    rec = {'workload': w.describe(), 'value': batch / (ms * 1e-3), 'unit': 'images/s', 'ms_per_step': ms, 'ms_per_step_max': worst,
+           'scaling': 'strong', 'global_batch': batch, 'launch': mode, 'pipeline': pipelines[0],
+           'gather': 'nccl all_gather of [B/N, D, 6] + counts' if ctx.world > 1 else 'none'}
+    if ctx.world == 1:
+        rec['roofline'] = roofline(ctx, 'odk::topk_collect_kernel (+ sample, tail kernels: the whole odk_postprocess call)', w.bytes, ms,
+                                   traffic_of('topk_collect_kernel_dram_bytes_per_launch'))
+        for p in pipelines[1:]:
+            ms2, _, _ = w.measure(steps, warmup, p)
+            rec[f'pipeline_{p}'] = {'ms_per_step': ms2, 'images_per_s': batch / (ms2 * 1e-3), 'frac_of_peak': w.bytes / (ms2 * 1e-3) / 1e9 / ctx.peak}
+        rec['e2e'] = w.e2e(max(2, min(steps, 5)))
+    del w
+    gc.collect()
+    ctx.torch.cuda.empty_cache()
+    if with_cpu and ctx.rank == 0 and ctx.world == 1:
+        rec['cpu_baseline'] = cpu_record('post', model, 2, 1, f'{model.upper()} C=90 top-{K_TOP} + decode + {"soft-" if soft else ""}NMS-{D_MAX}' +
+                                         (' + OOD' if ood else ''), soft=soft, ood=ood)
+    return rec
+
+
+def record_chain(ctx, steps, warmup, with_cpu):
+    """configs[0], the reference's CPU-runnable case: D0 batch 8, labeler + loss (fwd+grad) + top-5000 + NMS-100."""
+    from ood_object_detection_b200.bench import post_process_detect
+    t = TrainWorkload(ctx, 'd0', 8, 10, seed=11)
+    torch = ctx.torch
+
+    def step():
+        t.step(grad=True)
+        with torch.no_grad():
+            return post_process_detect([c.detach() for c in t.cls], [b.detach() for b in t.box], t.anchors.boxes, 5, NUM_CLASSES, K_TOP, D_MAX, False)
+    for _ in range(max(warmup, 3)):
+        step()
+    t.drop_grads()
+    gr, _ = ctx.capture(step)
+    ms = ctx.timed(gr.replay if gr is not None else step, steps)
+    rec = {'workload': 'D0-512 A=49104 C=90 B=8 M=10: labeler + loss fwd+grad + top-5000 + decode + NMS-100 (BASELINE.json configs[0])',
+           'value': 8 / (ms * 1e-3), 'unit': 'images/s', 'ms_per_step': ms, 'launch': 'cuda_graph' if gr is not None else 'eager'}
+    if with_cpu:
+        ct, cp = CpuTrain('d0', 8, 10), CpuPost('d0', 8, False, False)
+        best = min(ct.step(grad=True)[0] + cp.step() for _ in range(2))
+        rec['cpu_baseline'] = {'value': 8 / best, 'unit': 'images/s', 'cores': ct.threads, 'kind': 'port',
+                               'sample': 'the same chain, B=8, best of 2 (oracle/, C + OpenMP on all host cores)',
+                               'torch_reference_survey_images_per_s': TORCH_REFERENCE_SURVEY['d0_b8_m10']['images_per_s']}
+    return rec
+
+
+# --------------------------------------------------------------------------------- GPU arm
+def exchange_check(ctx, w):
+    """N > 1, after the timed run: (a) the mailbox's global loss equals, bit for bit, the same fp32 sum in rank order
+    over partials moved by an NCCL all-gather; (b) it agrees with an NCCL all-reduce of the partials; (c) this
+    rank's own loss agrees with the CPU oracle on its shard."""
+    torch, dist = ctx.torch, ctx.dist
+    out = {}
+    with torch.no_grad():
+        w.step(grad=False)                    # publishes this step's record, w.buf = local {total, cls, box, n}
+        local = w.buf.clone()
+        got = None
+        if w.mailbox is not None:
+            got = torch.stack(list(w.mailbox.collect()[0])).clone()
+            w.mailbox.check()
+        part = local.clone()
+        part[:3] *= part[3]                   # un-normalised sums, exactly what the kernel publishes
+        parts = [torch.empty_like(part) for _ in range(ctx.world)]
+        dist.all_gather(parts, part)
+        acc = torch.zeros((4,), dtype=torch.float32, device=ctx.dev)
+        for p in parts:                       # rank order, fp32: the mailbox's arithmetic
+            acc = acc + p
+        ref = acc[:3] / (acc[3] - float(ctx.world - 1))
+        red = part.clone()
+        dist.all_reduce(red, op=dist.ReduceOp.SUM)
+        red3 = red[:3] / (red[3] - float(ctx.world - 1))
+        if got is not None:
+            out['mailbox_equals_rank_ordered_nccl_gather_bitwise'] = bool(torch.equal(got, ref))
+            out['mailbox_vs_nccl_allreduce_max_rel'] = float(((got - red3).abs() / red3.abs().clamp(min=1e-30)).max())
+            out['global_loss'] = [float(x) for x in got]
+        else:
+            out['global_loss'] = [float(x) for x in red3]
+    rel = torch.tensor([w.oracle_check() if ctx.rank == 0 else 0.0], device=ctx.dev)
+    out['rank0_local_loss_vs_cpu_oracle_max_rel'] = float(rel.item())
+    ok = out.get('mailbox_equals_rank_ordered_nccl_gather_bitwise', True) and out.get('mailbox_vs_nccl_allreduce_max_rel', 0.0) < 1e-5 \
+        and out['rank0_local_loss_vs_cpu_oracle_max_rel'] < 1e-5
+    out['ok'] = bool(ok)
+    return out
+
+
+def run_ours(args):
+    ctx = Ctx(args)
+    torch, dist = ctx.torch, ctx.dist
+    rank, world = ctx.rank, ctx.world
+    with_cpu = world == 1 and not args.no_cpu_baseline
+    sampler = ClockSampler(ctx.local) if rank == 0 else None
+
+    # ---- headline: configs[1], labeler + loss forward + gradient, B = 64 per GPU (weak scaling) ----
+    head = TrainWorkload(ctx, 'd0', 64, 10)
+    head.setup_exchange()
+    for _ in range(max(args.warmup, 3)):
+        head.step(True)
+    head.drop_grads()
+    ctx.sync_all()
+    if sampler:
+        sampler.start()
+    ms_per_step, mode = head.measure(args.steps, args.warmup, grad=True)
+    # keep the same load running (untimed) for ~60 ms so the clock sampler sees the GPU under it; every rank runs
+    # the SAME number of extra steps
+    n_extra = int(min(400, max(0, np.ceil((60.0 - ms_per_step * args.steps) / max(ms_per_step, 1e-3)))))
+    for _ in range(n_extra):
+        head.graph.replay() if head.graph is not None else head.step(True)
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    if head.mailbox is not None:
+        head.mailbox.check()
+    loss_out = [float(x) for x in head.buf[:3].detach().cpu()]
+    value = world * head.B / (ms_per_step * 1e-3)
+    ms_fwd, _ = head.measure(args.steps, args.warmup, grad=False)
+    xcheck = exchange_check(ctx, head) if world > 1 else None
+    k_ms = head.kernel_ms(max(5, min(args.steps, 50))) if rank == 0 else None
+    head.drop_grads()
+    head.graph = None
+    e2e = head.e2e(max(2, min(args.steps, 10)))
+    bytes_fwd, workload, exchange = head.bytes_fwd, TrainWorkload.describe('d0', 64, 10), head.exchange
+    if world > 1:   # graphs / mailboxes that hold peer mappings go before the other workloads allocate
+        torch.cuda.synchronize()
+    del head
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configurations, same run ----
+    workloads = {}
+    if not args.only:
+        steps2 = max(5, min(args.steps, 20))
+        plan = [('post_d3_hard', lambda: record_post(ctx, 'd3', 32, False, False, steps2, args.warmup, with_cpu, ('staged', 'persistent'))),
+                ('post_d3_soft', lambda: record_post(ctx, 'd3', 32, True, False, steps2, args.warmup, with_cpu, ('staged', 'persistent'))),
+                ('post_d5_ood', lambda: record_post(ctx, 'd5', 32, False, True, steps2, args.warmup, with_cpu)),
+                ('train_d7', lambda: record_train(ctx, 'd7', 128, 100, max(3, min(args.steps, 10)), args.warmup, with_cpu, 'strong', e2e_batch=8))]
+        if world == 1:
+            plan.append(('chain_d0_b8', lambda: record_chain(ctx, steps2, args.warmup, with_cpu)))
+        for name, fn in plan:
+            try:
+                workloads[name] = fn()
+            except Exception as exc:   # a secondary workload must never take the headline down
+                workloads[name] = {'error': f'{type(exc).__name__}: {exc}'}
+                gc.collect()
+                torch.cuda.empty_cache()
+            if world > 1:
+                dist.barrier()
 
     if rank == 0:
-        peak, peak_src = peaks()
-        achieved = bytes_loss / (loss_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get('loss_kernel_dram_bytes_per_launch')
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            rate, threads = cpu_reference_rate(16, 2)
-            cpu = {'value': rate, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
-                   'sample': 'D0-512 C=90 M=10 labeler+loss fwd, B=16 of the B=64 workload, best of 2 (oracle/, OpenMP)'}
+        if with_cpu:
+            cpu = cpu_record('train', 'd0', 16, 2, 'D0-512 C=90 M=10 labeler + loss fwd+grad (of the B=64 workload)', num_gt=10)
+            cpu['torch_reference_survey'] = TORCH_REFERENCE_SURVEY
         line = {
             'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'global_batch': world * BATCH, 'parallelism': f'images sharded x{world}',
+            'config': {'workload': workload, 'global_batch': world * 64, 'parallelism': f'images sharded x{world}',
                        'launch': mode, 'exchange': exchange,
-                       'l2': 'inputs (1.18 GB/step) larger than the 126 MB L2; no flush needed',
-                       'loss_out': [float(x) for x in last]},
-            'roofline': {'bound': 'hbm', 'kernel': 'odk::loss_kernel_ring<new,fwd,fused>', 'achieved': achieved, 'peak': peak,
-                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                         'algorithmic_bytes_per_launch': bytes_loss, 'kernel_ms': loss_ms},
+                       'l2': 'inputs (1.18 GB read + 1.18 GB of gradients written per step) larger than the 126 MB L2; no flush needed',
+                       'loss_out': loss_out, 'exchange_check': xcheck},
+            'roofline': roofline(ctx, 'odk::loss_kernel_ring<new,grad,fused>', 2 * bytes_fwd, k_ms, traffic_of('loss_grad_kernel_dram_bytes_per_launch')),
+            'step_frac_of_peak': 2 * bytes_fwd / (ms_per_step * 1e-3) / 1e9 / ctx.peak,
             'cpu_baseline': cpu,
-            'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
-                    'steps': e2e_steps},
-            'gpu_launches': 2 * args.steps,
-            'launches_per_step': {'odk::assign_gt_kernel': 1, 'odk::loss_kernel_ring': 1,
-                                  'cudaMemsetAsync': 2},
+            'e2e': e2e,
+            'gpu_launches': 5 * args.steps,
+            'launches_per_step': {'odk::assign_gt_kernel': 1, 'odk::loss_kernel_ring': 1, 'odk::clear_keys_kernel': 1,
+                                  'odk::scale_multi_kernel (exits on device)': 2, 'cudaMemsetAsync (4-byte counter)': 1},
             'clocks': clocks,
-            'fwd_plus_grad': {'ms_per_step': fwd_bwd_ms, 'images_per_s': BATCH / (fwd_bwd_ms * 1e-3),
-                              'achieved_GBps': 2 * bytes_loss / (fwd_bwd_ms * 1e-3) / 1e9,
-                              'note': 'labeler + loss fwd + d total/d outputs written in the same pass + backward()'},
-            'extra': extra,
+            'forward_only': {'ms_per_step': ms_fwd, 'images_per_s': world * 64 / (ms_fwd * 1e-3),
+                             'frac_of_peak': bytes_fwd / (ms_fwd * 1e-3) / 1e9 / ctx.peak},
+            'workloads': workloads,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -438,58 +751,15 @@ def run_ours(args):
         guard.cancel()
 
 
-def postprocess_extra(torch, dev, synth):
-    """BASELINE.json configs[2] on one GPU (not the headline): D3 896^2 B=32 post-process."""
-    from ood_object_detection_b200.anchors import Anchors, detect_batch
-    from ood_object_detection_b200.bench import _post_process
-    size, scale = synth.MODEL_SHAPES['d3']
-    B, C, K, D = 32, 90, 5000, 100
-    g = torch.Generator(device=dev)
-    g.manual_seed(3)
-    feat = synth.feat_hw(size)
-    cls_out = [torch.randn((B, 9 * C, h, w), generator=g, device=dev) * 1.5 - 4.6 for h, w in feat]
-    box_out = [torch.randn((B, 36, h, w), generator=g, device=dev) * 0.2 for h, w in feat]
-    anchors = Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size)).to(dev)
-    A = anchors.boxes.shape[0]
-    out = {}
-    for soft in (False, True):
-        def step():
-            cls_k, box_k, idx, klass = _post_process(cls_out, box_out, 5, C, K)
-            return detect_batch(cls_k, box_k, anchors.boxes, idx, klass, None, None, D, soft), (cls_k, box_k, idx, klass)
-        for _ in range(3):
-            step()
-        torch.cuda.synchronize()
-        n = 10
-        tk, tot = [], []
-        for _ in range(n):
-            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            a.record()
-            pp = _post_process(cls_out, box_out, 5, C, K)
-            b.record()
-            detect_batch(pp[0], pp[1], anchors.boxes, pp[2], pp[3], None, None, D, soft)
-            c.record()
-            torch.cuda.synchronize()
-            tk.append(a.elapsed_time(b))
-            tot.append(a.elapsed_time(c))
-        ms, tk_ms = float(np.median(tot)), float(np.median(tk))   # median: robust to one-off allocator stalls
-        peak, _ = peaks()
-        by = B * A * 4 * C
-        out['soft_nms' if soft else 'hard_nms'] = {
-            'workload': f'D3-896 A={A} C=90 B=32 top-{K} + decode + {"soft-" if soft else ""}NMS-{D}',
-            'ms_per_step': ms, 'images_per_s': B / (ms * 1e-3), 'topk_ms': tk_ms, 'ms_per_step_max': float(max(tot)),
-            'topk_achieved_GBps': by / (tk_ms * 1e-3) / 1e9, 'topk_frac_of_peak': by / (tk_ms * 1e-3) / 1e9 / peak}
-    return out
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--no-extra', action='store_true', help='skip the D3 post-process extra block')
+    ap.add_argument('--only', action='store_true', help='headline workload only (skip the other BASELINE.json configurations)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-peer', action='store_true', help='N > 1: exchange the loss partial sums with an NCCL all-reduce instead of peer mailboxes')
+    ap.add_argument('--no-peer', action='store_true', help='N > 1: exchange the loss sums with an NCCL all-reduce instead of peer mailboxes')
     ap.add_argument('--no-graph', action='store_true', help='launch the timed steps eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -73,10 +73,11 @@ int odk_assign(const float *anchors, const float *gt_boxes, const int32_t *gt_la
  *               W, H, off_l, shape, level
  * match_thr must be > 0.  Workspace: odk_assign_grid_workspace_bytes(B, A). */
 size_t odk_assign_grid_workspace_bytes(int B, int64_t A);
+#define ODK_ASSIGN_WS_CLEAN 1   /* flags: the workspace is all zero (fresh, or left so by odk_loss' clear_keys): no memset */
 int odk_assign_grid(const float *anchors, const float *plane_desc, int num_planes, const float *gt_boxes,
                     const int32_t *gt_labels, const int32_t *gt_count, int B, int Mmax, const int32_t *level_hw,
                     int num_levels, int na, float match_thr, int filter_valid, int32_t *match, float *num_pos,
-                    float *normalizer, void *workspace, size_t workspace_bytes, void *stream);
+                    float *normalizer, int flags, void *workspace, size_t workspace_bytes, void *stream);
 /* `match` may be NULL: the assignment then stays in the workspace as 64-bit keys
  * ([B, odk_planar_stride(A)] uint64 at offset 0; 0 = unmatched, else low 32 bits = ~gt_row), which
  * odk_loss consumes directly (odk_loss_params.match_is_key64) and odk_keys_to_match converts on
@@ -119,7 +120,11 @@ typedef struct odk_exchange {
     int32_t world, rank;
     const float *num_pos_plus_1;  /* device: this rank's sum(num_positives) + 1 (odk_assign_grid's `normalizer`) */
     float *global_out3;           /* device: {total, cls_loss, box_loss} of the previous step's GLOBAL batch */
-    int32_t *status;              /* device: 0, or 1 if a peer's record did not arrive in time */
+    int32_t *status;              /* device, STICKY: 0, or 1 + the first sequence number whose record set did not arrive in
+                                     time (never cleared by the library; global_out3 is NaN for that step) */
+    int32_t normalized;           /* out[0..2] of this launch are already divided by *num_pos_plus_1 (local normaliser,
+                                     what a gradient step uses): the published sums are multiplied back */
+    uint32_t timeout_ms;          /* how long a collect waits for the peers' records; 0 = 30 000 ms */
 } odk_exchange;
 
 typedef struct odk_loss_params {
@@ -130,6 +135,8 @@ typedef struct odk_loss_params {
     float label_smoothing;
     int32_t legacy_focal;
     int32_t match_is_key64;   /* `match` points at odk_assign_grid's 64-bit keys instead of int32 rows */
+    int32_t clear_keys;       /* with match_is_key64 (`match` = the labeler's workspace): after the last read, zero the keys the
+                                 labeler set and its counters, so the next odk_assign_grid can run with ODK_ASSIGN_WS_CLEAN */
     const odk_exchange *exchange;   /* NULL = no exchange (HOST pointer, read during the call) */
 } odk_loss_params;
 
@@ -159,16 +166,18 @@ int odk_scale_inplace_multi(void *const *bufs, const int64_t *sizes, int count, 
  *     of `world` device pointers (entry `rank` is the local mailbox).  No waiting.
  *   odk_partials_collect: waits (bounded spin) until all `world` records of the next sequence
  *     number are in the LOCAL mailbox, sums them in rank order (deterministic) and writes
- *     out3 = {total, cls_loss, box_loss} of the global batch (sums / (sum(num_pos) + 1), loss.py:261,297);
- *     *status = 0, or 1 if a peer's record did not arrive in time (about a second of polling; out3 is
- *     then unspecified, later steps are unaffected because records carry their step number).
+ *     out3 = {total, cls_loss, box_loss} of the global batch (sums / (sum(num_pos) + 1), loss.py:261,297).
+ *     If a peer's record does not arrive within timeout_ms (wall clock, %globaltimer; 0 = 30 s) the step's
+ *     out3 is NaN, *status becomes 1 + its sequence number and STAYS set (sticky: the caller decides when
+ *     to look), and the collected counter is NOT advanced, so the same record set is waited for again by
+ *     the next collect instead of summing whatever stale record is in the slot.
  * Every rank must alternate collect(j-1) ... publish(j) in stream order (that ordering is the flow
  * control that makes two slots enough) and publish once before its first collect.
  * odk_loss with odk_loss_params.exchange does both inside the loss kernel (collect(j-1) when a record
  * is outstanding, then publish(j)); odk_partials_collect then only drains the last step. */
 size_t odk_mailbox_bytes(int world);
 int odk_partials_publish(const float *partials4, void *const *mailboxes, int world, int rank, void *stream);
-int odk_partials_collect(void *mailbox_local, int world, float *out3, int32_t *status, void *stream);
+int odk_partials_collect(void *mailbox_local, int world, float *out3, int32_t *status, uint32_t timeout_ms, void *stream);
 
 /* ---- post-process: top-k -------------------------------------------------------------------
  * Replaces _post_process (bench.py:12-56): concat/permute of the levels, torch.topk over

@@ -22,13 +22,14 @@ MAILBOX_MAX_WORLD = 32
 class Exchange(ctypes.Structure):
     """odk_exchange (include/odk.h): fused peer-mailbox exchange of the loss partial sums."""
     _fields_ = [('mailboxes', c_void_p * MAILBOX_MAX_WORLD), ('world', ctypes.c_int32), ('rank', ctypes.c_int32),
-                ('num_pos_plus_1', c_void_p), ('global_out3', c_void_p), ('status', c_void_p)]
+                ('num_pos_plus_1', c_void_p), ('global_out3', c_void_p), ('status', c_void_p),
+                ('normalized', ctypes.c_int32), ('timeout_ms', ctypes.c_uint32)]
 
 
 class LossParams(ctypes.Structure):
     _fields_ = [('alpha', c_float), ('gamma', c_float), ('delta', c_float), ('box_loss_weight', c_float),
                 ('label_smoothing', c_float), ('legacy_focal', ctypes.c_int32), ('match_is_key64', ctypes.c_int32),
-                ('exchange', ctypes.POINTER(Exchange))]
+                ('clear_keys', ctypes.c_int32), ('exchange', ctypes.POINTER(Exchange))]
 
 
 class DetectParams(ctypes.Structure):
@@ -46,7 +47,8 @@ SIGNATURES = {
     'odk_assign_workspace_bytes': (c_size_t, [c_int, c_int]),
     'odk_assign': (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P]),
     'odk_assign_grid_workspace_bytes': (c_size_t, [c_int, c_int64]),
-    'odk_assign_grid': (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    'odk_assign_grid': (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, c_int, _P, c_size_t,
+                                _P]),
     'odk_keys_to_match': (c_int, [_P, c_int, c_int64, _P, _P]),
     'odk_iou_matrix': (c_int, [_P, c_int, _P, c_int, _P, _P]),
     'odk_targets': (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, _P, _P, _P, _P]),
@@ -57,7 +59,7 @@ SIGNATURES = {
     'odk_scale_inplace_multi': (c_int, [_P, _P, c_int, _P, _P]),
     'odk_mailbox_bytes': (c_size_t, [c_int]),
     'odk_partials_publish': (c_int, [_P, _P, c_int, c_int, _P]),
-    'odk_partials_collect': (c_int, [_P, c_int, _P, _P, _P]),
+    'odk_partials_collect': (c_int, [_P, c_int, _P, _P, ctypes.c_uint32, _P]),
     'odk_topk_workspace_bytes': (c_size_t, [c_int, c_int, _P, c_int, c_int, c_int]),
     'odk_topk': (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     'odk_detect': (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int64, _P, _P, ctypes.POINTER(DetectParams), _P, _P, _P,

@@ -56,7 +56,8 @@ class Anchors(nn.Module):
         self.feat_sizes = get_feat_sizes(image_size, max_level)
         self.config = self._generate_configs()
         self.register_buffer('boxes', self._generate_boxes())
-        self.register_buffer('plane_desc', self._generate_plane_desc())
+        # not persistent: the reference's Anchors has only `boxes` in its state_dict, and checkpoints must stay interchangeable
+        self.register_buffer('plane_desc', self._generate_plane_desc(), persistent=False)
 
     @classmethod
     def from_config(cls, config, img_size=None, min_level=0):
@@ -138,8 +139,12 @@ class LabelBatch:
     ``match`` ([B, Apad] int32, planar order) is all the fused loss needs; the reference-layout
     target tensors are only materialised on demand (``targets()``)."""
 
-    def __init__(self, labeler, gt_boxes, gt_labels, match, num_positives, keys=None, normalizer=None):
+    def __init__(self, labeler, gt_boxes, gt_labels, match, num_positives, keys=None, normalizer=None, workspace=None,
+                 transient=False):
         self.labeler = labeler
+        self.workspace = workspace        # the labeler's workspace the keys live in (gt-centric kernel)
+        self.transient = transient        # consumed by ONE fused loss, which zeroes the keys again (no memset next time)
+        self.consumed = False
         self.gt_boxes = gt_boxes
         self.gt_labels = gt_labels
         self._match = match
@@ -152,6 +157,8 @@ class LabelBatch:
     def match(self):
         """[B, Apad] int32 gt row per anchor (planar order), converted from the keys on first use."""
         if self._match is None:
+            if self.consumed:
+                raise RuntimeError('this LabelBatch was created with transient=True and its keys were consumed by the loss')
             lib = _lib.lib()
             B, apad = self.keys.shape
             self._match = torch.empty((B, apad), dtype=torch.int32, device=self.keys.device)
@@ -183,6 +190,7 @@ class AnchorLabeler(object):
         self.match_threshold = match_threshold
         self.num_classes = num_classes
         self.indices_cache = {}
+        self._clean_ws = {}   # (device, bytes) -> workspaces the fused loss has left all-zero again (transient batches)
         # gt-centric kernel (odk_assign_grid) for the regular pyramid grids; the dense kernel
         # (odk_assign) is kept for arbitrary anchor sets and non-positive thresholds
         self.use_grid_kernel = True
@@ -227,9 +235,16 @@ class AnchorLabeler(object):
                 overlapping, _ = (sims > 0.9).max(0) if sims.shape[0] > 0 else (torch.zeros_like(task_mask), None)
                 gt_classes[i][overlapping] = task_cls
 
-    def assign(self, gt_boxes, gt_classes, filter_valid=True, task_cls=None, normalizer_out=None) -> LabelBatch:
+    def _recycle(self, ws):
+        """Called by the fused loss for a transient batch: its kernel has zeroed the keys it read."""
+        self._clean_ws.setdefault((ws.device, ws.numel()), []).append(ws)
+
+    def assign(self, gt_boxes, gt_classes, filter_valid=True, task_cls=None, normalizer_out=None, transient=False) -> LabelBatch:
         """Run the assignment kernels; the result feeds either ``targets()`` or the fused loss.
-        ``normalizer_out`` (float32 [1], same device) receives sum(num_positives) + 1 in place."""
+        ``normalizer_out`` (float32 [1], same device) receives sum(num_positives) + 1 in place.
+        ``transient``: the batch will be consumed by exactly one fused loss call (what ``DetBenchTrain`` does); that
+        kernel then zeroes the assignment keys it read, and the next ``assign`` reuses the workspace without the
+        8-bytes-per-anchor memset."""
         if task_cls is not None:
             self._relabel_task_cls(gt_boxes, gt_classes, task_cls)
         boxes, labels, count = self._pack(gt_boxes, gt_classes, filter_valid)
@@ -249,16 +264,20 @@ class AnchorLabeler(object):
                 # the assignment stays in the workspace as 64-bit keys: the fused loss reads them directly,
                 # int32 `match` is only materialised if somebody asks for it (LabelBatch.match / targets())
                 ws_bytes = lib.odk_assign_grid_workspace_bytes(B, A)
-                ws = torch.empty((ws_bytes + 15) // 16 * 2, dtype=torch.int64, device=dev)
+                n64 = (ws_bytes + 15) // 16 * 2
+                pool = self._clean_ws.get((dev, n64))
+                ws, flags = (pool.pop(), 1) if pool else (torch.empty(n64, dtype=torch.int64, device=dev), 0)
                 normalizer = torch.empty((1,), dtype=torch.float32, device=dev) if normalizer_out is None else normalizer_out
                 if normalizer.dtype != torch.float32 or normalizer.numel() != 1 or normalizer.device != dev:
                     raise ValueError('normalizer_out must be one float32 element on the gt device')
                 _lib.check(lib.odk_assign_grid(_lib.ptr(anc), _lib.ptr(desc), desc.shape[0], _lib.ptr(boxes),
                                                _lib.ptr(labels), _lib.ptr(count), B, M, _lib.int_array(hw), len(hw), na,
                                                thr, int(bool(filter_valid)), None, _lib.ptr(num_pos),
-                                               _lib.ptr(normalizer), _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr(dev)))
+                                               _lib.ptr(normalizer), flags, _lib.ptr(ws), ws.numel() * 8,
+                                               _lib.stream_ptr(dev)))
                 keys = ws[:B * apad].view(B, apad)
-                return LabelBatch(self, boxes, labels, None, num_pos, keys=keys, normalizer=normalizer)
+                return LabelBatch(self, boxes, labels, None, num_pos, keys=keys, normalizer=normalizer, workspace=ws,
+                                  transient=bool(transient))
             else:
                 match = torch.empty((B, apad), dtype=torch.int32, device=dev)
                 ws_bytes = lib.odk_assign_workspace_bytes(B, M)

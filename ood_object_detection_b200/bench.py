@@ -230,7 +230,7 @@ class DetBenchTrain(_Bench):
     def _losses(self, cls_levels, box_levels, target):
         if self.anchor_labeler is not None:
             return self.loss_fn.forward_fused(cls_levels, box_levels,
-                                              self.anchor_labeler.assign(target['bbox'], target['cls']))
+                                              self.anchor_labeler.assign(target['bbox'], target['cls'], transient=True))
         if 'label_num_positives' not in target:
             raise AssertionError('a bench without a labeler needs the pre-computed label_* targets (bench.py:124-128)')
         levels = range(self.num_levels)

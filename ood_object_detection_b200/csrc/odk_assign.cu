@@ -21,7 +21,7 @@ constexpr int kAssignThreads = 256;
 constexpr int kPerThread = 4;                    // consecutive planar anchors per thread (one int4 store)
 constexpr int kGtTile = 256;
 constexpr int kDirectMax = 48;
-constexpr int kCtrStride = 32;                   // ints between per-image counters: one 128 B line each                   // gt rows per image up to which the direct path is used
+// gt rows per image up to which the direct path is used
 
 // Forced matches for one image, run by the LAST CTA of that image: gt row i claims its arg-max
 // anchor (anchor 0 if its IoU is 0 everywhere); the lowest gt row wins a contested anchor
@@ -334,7 +334,7 @@ __device__ __forceinline__ void assign_one_gt(const Geo &g, const float4 *__rest
                                               int nplanes, const float4 *__restrict__ gt_boxes,
                                               const int32_t *__restrict__ gt_labels, const int32_t *__restrict__ gt_count,
                                               int Mmax, float thr, int filter_valid, unsigned long long *keys,
-                                              int32_t *pos_count) {
+                                              int32_t *pos_count, unsigned *touched, int touched_cap) {
     __shared__ int s_off[kMaxPlanes + 1], s_x0[kMaxPlanes], s_nx[kMaxPlanes], s_y0[kMaxPlanes];
     __shared__ int s_w[kMaxPlanes], s_base[kMaxPlanes], s_sh[kMaxPlanes], s_hw[kMaxPlanes];
     __shared__ unsigned char s_done[kMaxPlanes];
@@ -439,7 +439,10 @@ __device__ __forceinline__ void assign_one_gt(const Geo &g, const float4 *__rest
                         if (!(thr > v)) {   // a candidate match for this anchor (argmax_matcher.py:126-137)
                             const unsigned long long kg =
                                 ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
-                            if (atomicMax(krow + p, kg) == 0ull) atomicAdd(pos_count + (size_t)b * kCtrStride, 1);
+                            if (atomicMax(krow + p, kg) == 0ull) {   // first key of this anchor: count it, list it
+                                const int slot = atomicAdd(pos_count + (size_t)b * kCtrStride, 1);
+                                if (slot < touched_cap) touched[(size_t)b * touched_cap + slot] = (unsigned)p;
+                            }
                         }
                     }
                 }
@@ -478,7 +481,10 @@ __device__ __forceinline__ void assign_one_gt(const Geo &g, const float4 *__rest
         int l;
         const int p = ref_to_planar(g, r, l);
         const unsigned long long kf = (0xFFFFFFFFull << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
-        if (atomicMax(krow + p, kf) == 0ull) atomicAdd(pos_count + (size_t)b * kCtrStride, 1);
+        if (atomicMax(krow + p, kf) == 0ull) {
+            const int slot = atomicAdd(pos_count + (size_t)b * kCtrStride, 1);
+            if (slot < touched_cap) touched[(size_t)b * touched_cap + slot] = (unsigned)p;
+        }
     }
 }
 
@@ -509,9 +515,11 @@ __global__ void __launch_bounds__(kGtcThreads)
 assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *__restrict__ desc, int nplanes,
                  const float4 *__restrict__ gt_boxes, const int32_t *__restrict__ gt_labels,
                  const int32_t *__restrict__ gt_count, int Mmax, float thr, int filter_valid,
-                 unsigned long long *keys, int32_t *pos_count, unsigned *done, int B, float *num_pos, float *normalizer) {
+                 unsigned long long *keys, int32_t *pos_count, unsigned *touched, int touched_cap, unsigned *done, int B,
+                 float *num_pos, float *normalizer) {
     __shared__ bool s_last;
-    assign_one_gt(g, anchors, desc, nplanes, gt_boxes, gt_labels, gt_count, Mmax, thr, filter_valid, keys, pos_count);
+    assign_one_gt(g, anchors, desc, nplanes, gt_boxes, gt_labels, gt_count, Mmax, thr, filter_valid, keys, pos_count, touched,
+                  touched_cap);
     __threadfence();   // this thread's counter updates are visible before the CTA reports in
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x * gridDim.y - 1u;
@@ -631,7 +639,7 @@ int odk_assign(const float *anchors, const float *gt_boxes, const int32_t *gt_la
 
 size_t odk_assign_grid_workspace_bytes(int B, int64_t A) {
     if (B < 0 || A < 0) return 0;
-    return (size_t)B * (size_t)odk_planar_stride(A) * sizeof(unsigned long long) + (size_t)B * odk::kCtrStride * sizeof(int32_t) + 16;
+    return odk::assign_grid_layout(B, odk_planar_stride(A)).total;
 }
 
 int odk_keys_to_match(const void *keys, int B, int64_t A, int32_t *match, void *stream) {
@@ -650,7 +658,7 @@ int odk_keys_to_match(const void *keys, int B, int64_t A, int32_t *match, void *
 int odk_assign_grid(const float *anchors, const float *plane_desc, int num_planes, const float *gt_boxes,
                     const int32_t *gt_labels, const int32_t *gt_count, int B, int Mmax, const int32_t *level_hw,
                     int num_levels, int na, float match_thr, int filter_valid, int32_t *match, float *num_pos,
-                    float *normalizer, void *workspace, size_t workspace_bytes, void *stream) {
+                    float *normalizer, int flags, void *workspace, size_t workspace_bytes, void *stream) {
     using namespace odk;
     Geo g;
     int rc = make_geo(&g, level_hw, num_levels, na);
@@ -669,16 +677,21 @@ int odk_assign_grid(const float *anchors, const float *plane_desc, int num_plane
     if (((uintptr_t)anchors | (uintptr_t)gt_boxes | (uintptr_t)workspace | (uintptr_t)match) & 15)
         return set_error(ODK_EINVAL, "odk_assign_grid: anchors / gt_boxes / match / workspace must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    const AssignGridWs w = assign_grid_layout(B, g.Apad);
     unsigned long long *keys = (unsigned long long *)workspace;
-    int32_t *pos = (int32_t *)((char *)workspace + (size_t)B * g.Apad * sizeof(unsigned long long));
-    unsigned *done = (unsigned *)((char *)workspace + odk_assign_grid_workspace_bytes(B, g.A) - 16);
-    cudaError_t e = cudaMemsetAsync(workspace, 0, odk_assign_grid_workspace_bytes(B, g.A), st);
-    if (e != cudaSuccess) return set_error((int)e, "odk_assign_grid memset: %s", cudaGetErrorString(e));
+    int32_t *pos = (int32_t *)((char *)workspace + w.pos);
+    unsigned *touched = (unsigned *)((char *)workspace + w.touched);
+    unsigned *done = (unsigned *)((char *)workspace + w.done);
+    if (!(flags & ODK_ASSIGN_WS_CLEAN)) {   // else: keys, counters and `done` are zero already (odk_loss cleared them)
+        cudaError_t e = cudaMemsetAsync(workspace, 0, w.total, st);
+        if (e != cudaSuccess) return set_error((int)e, "odk_assign_grid memset: %s", cudaGetErrorString(e));
+    }
     if (Mmax > 0) {
         dim3 grid(Mmax, B);
         assign_gt_kernel<<<grid, kGtcThreads, 0, st>>>(g, (const float4 *)anchors, plane_desc, num_planes,
                                                        (const float4 *)gt_boxes, gt_labels, gt_count, Mmax, match_thr,
-                                                       filter_valid, keys, pos, done, B, num_pos, normalizer);
+                                                       filter_valid, keys, pos, touched, w.touched_cap, done, B, num_pos,
+                                                       normalizer);
         rc = check_launch("odk_assign_grid/assign_gt_kernel");
     } else {
         finish_counts_kernel<<<1, kGtcThreads, 0, st>>>(B, pos, num_pos, normalizer);

@@ -23,6 +23,25 @@ int set_error(int code, const char *fmt, ...);
 int check_launch(const char *what);
 int make_geo(Geo *g, const int32_t *level_hw, int num_levels, int na);
 
+// Workspace of odk_assign_grid (also read by odk_loss when it clears the assignment keys):
+//   keys [B][Apad] u64 | pos_count [B][kCtrStride] i32 | touched [B][touched_cap] u32 | done u32 (16 bytes)
+// `touched` lists the planar positions whose key is non-zero, in the order the positive counter handed out
+// slots; an image with more than touched_cap positives simply is not listed completely (the cleaner then clears
+// its whole row).
+constexpr int kCtrStride = 32;                   // ints between per-image counters: one 128 B line each
+constexpr int kTouchedCapMax = 16384;
+struct AssignGridWs { size_t keys, pos, touched, done, total; int touched_cap; };
+inline AssignGridWs assign_grid_layout(int B, long long Apad) {
+    AssignGridWs w;
+    w.touched_cap = (int)(Apad < kTouchedCapMax ? Apad : kTouchedCapMax);
+    w.keys = 0;
+    w.pos = (size_t)B * (size_t)Apad * sizeof(unsigned long long);
+    w.touched = w.pos + (size_t)B * kCtrStride * sizeof(int32_t);
+    w.done = w.touched + (((size_t)B * w.touched_cap * sizeof(unsigned)) + 15) / 16 * 16;
+    w.total = w.done + 16;
+    return w;
+}
+
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__
 

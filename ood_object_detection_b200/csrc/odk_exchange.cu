@@ -15,9 +15,9 @@ __global__ void __launch_bounds__(32) publish_kernel(const float4 *__restrict__ 
 }
 
 __global__ void __launch_bounds__(32) collect_kernel(unsigned char *local, int world, float *__restrict__ out3,
-                                                     int *__restrict__ status) {
+                                                     int *status, unsigned timeout_ms) {
     __shared__ float4 s_v[ODK_MAILBOX_MAX_WORLD];
-    collect_records(local, world, s_v, out3, status);
+    collect_records(local, world, s_v, out3, status, timeout_ms);
 }
 
 }  // namespace odk
@@ -45,12 +45,12 @@ int odk_partials_publish(const float *partials4, void *const *mailboxes, int wor
     return check_launch("odk_partials_publish");
 }
 
-int odk_partials_collect(void *mailbox_local, int world, float *out3, int32_t *status, void *stream) {
+int odk_partials_collect(void *mailbox_local, int world, float *out3, int32_t *status, uint32_t timeout_ms, void *stream) {
     using namespace odk;
     if (world < 1 || world > ODK_MAILBOX_MAX_WORLD) return set_error(ODK_EINVAL, "odk_partials_collect: bad world size");
     if (!mailbox_local || !out3 || !status || ((uintptr_t)mailbox_local & 15))
         return set_error(ODK_EINVAL, "odk_partials_collect: null or misaligned pointer");
-    collect_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned char *)mailbox_local, world, out3, status);
+    collect_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned char *)mailbox_local, world, out3, status, timeout_ms);
     return check_launch("odk_partials_collect");
 }
 

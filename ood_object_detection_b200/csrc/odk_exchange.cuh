@@ -41,19 +41,32 @@ __device__ __forceinline__ void publish_record(const Mailboxes &mb, int world, i
     __syncwarp();
 }
 
-// Called by one full warp: waits (bounded) for the next record set in the local mailbox, sums it in rank
-// order and writes the normalised global losses.  s_v: shared scratch of ODK_MAILBOX_MAX_WORLD float4.
-__device__ __forceinline__ void collect_records(unsigned char *local, int world, float4 *s_v, float *out3, int *status) {
+__device__ __forceinline__ unsigned long long exchange_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Called by one full warp: waits for the next record set in the local mailbox (up to timeout_ms of wall clock;
+// 0 = 30 s -- like a collective, a step only completes when every rank has contributed, so the bound exists to
+// turn a dead peer into an error instead of a hung GPU, not to ride out a slow one), sums it in rank order and
+// writes the normalised global losses.  On timeout the losses are NaN, *status = 1 + seq (sticky: only ever
+// written on failure) and the collected counter is NOT advanced: the next collect waits for the same set, so a
+// stale record is never summed.  s_v: shared scratch of ODK_MAILBOX_MAX_WORLD float4.
+__device__ __forceinline__ void collect_records(unsigned char *local, int world, float4 *s_v, float *out3, int *status,
+                                                unsigned timeout_ms) {
     unsigned *ctr = mailbox_counters(local, world);
     const int lane = threadIdx.x & 31;
     const unsigned seq = ctr[1] + 1u;
+    const unsigned long long budget = (unsigned long long)(timeout_ms ? timeout_ms : 30000u) * 1000000ull;
     bool ok = true;
     if (lane < world) {
         const unsigned char *rec = local + ((size_t)(seq & 1u) * world + lane) * kRecBytes;
         const unsigned *flag = reinterpret_cast<const unsigned *>(rec + 16);
+        const unsigned long long t0 = exchange_now_ns();
         unsigned spins = 0;
         while (ld_acquire_sys(flag) != seq) {
-            if (++spins > (1u << 20)) { ok = false; break; }   // about a second: a peer is gone, do not hang the GPU
+            if ((++spins & 63u) == 0u && exchange_now_ns() - t0 > budget) { ok = false; break; }
             __nanosleep(200);
         }
         s_v[lane] = __ldcg(reinterpret_cast<const float4 *>(rec));   // L2: never a stale L1 line of an older step
@@ -61,12 +74,17 @@ __device__ __forceinline__ void collect_records(unsigned char *local, int world,
     const bool all_ok = __all_sync(0xffffffffu, ok);
     __syncwarp();
     if (lane == 0) {
-        float t = 0.f, c = 0.f, b = 0.f, n = 0.f;
-        for (int r = 0; r < world; ++r) { t += s_v[r].x; c += s_v[r].y; b += s_v[r].z; n += s_v[r].w; }
-        n -= (float)(world - 1);   // every rank contributed sum(num_positives) + 1
-        out3[0] = t / n; out3[1] = c / n; out3[2] = b / n;
-        *status = all_ok ? 0 : 1;
-        ctr[1] = seq;
+        if (all_ok) {
+            float t = 0.f, c = 0.f, b = 0.f, n = 0.f;
+            for (int r = 0; r < world; ++r) { t += s_v[r].x; c += s_v[r].y; b += s_v[r].z; n += s_v[r].w; }
+            n -= (float)(world - 1);   // every rank contributed sum(num_positives) + 1
+            out3[0] = t / n; out3[1] = c / n; out3[2] = b / n;
+            ctr[1] = seq;
+        } else {
+            const float nan = __int_as_float(0x7fc00000);
+            out3[0] = nan; out3[1] = nan; out3[2] = nan;
+            if (*status == 0) *status = (int)(1u + seq);
+        }
     }
     __syncwarp();
 }

@@ -71,6 +71,14 @@ struct LossArgs {
     const float *xnpos;
     float *xout;
     int *xstatus;
+    int xnormalized;
+    unsigned xtimeout_ms;
+    // optional: leave odk_assign_grid's workspace zero again after the last read of the keys (clear_cap > 0)
+    unsigned long long *clr_keys;
+    int32_t *clr_pos;
+    const unsigned *clr_touched;
+    unsigned *clr_done;
+    int clr_cap;
 };
 
 // ---- element math ----------------------------------------------------------------------------
@@ -428,9 +436,10 @@ __device__ __forceinline__ void finish_block(const LossArgs &A, float csum, floa
             __syncthreads();
             if (threadIdx.x < 32) {
                 unsigned *ctr = mailbox_counters(A.xmb.p[A.xrank], A.xworld);
-                if (ctr[0] > ctr[1]) collect_records(A.xmb.p[A.xrank], A.xworld, s_recv, A.xout, A.xstatus);
+                if (ctr[0] > ctr[1]) collect_records(A.xmb.p[A.xrank], A.xworld, s_recv, A.xout, A.xstatus, A.xtimeout_ms);
                 float4 v = s_mine;
                 v.w = __ldg(A.xnpos);
+                if (A.xnormalized) { v.x *= v.w; v.y *= v.w; v.z *= v.w; }   // back to the un-normalised sums the records carry
                 publish_record(A.xmb, A.xworld, A.xrank, v);
             }
         }
@@ -574,6 +583,25 @@ loss_kernel_ring(const __grid_constant__ LossArgs A) {
     finish_block(A, csum, bsum, nrm);
 }
 
+// After the loss: zero the assignment keys the labeler set (it listed them), its positive counters and its CTA
+// counter, so the next odk_assign_grid needs no 8-bytes-per-anchor memset (ODK_ASSIGN_WS_CLEAN).  One CTA per image.
+__global__ void __launch_bounds__(256)
+clear_keys_kernel(unsigned long long *keys, int32_t *pos, const unsigned *__restrict__ touched, unsigned *done, int Apad, int cap) {
+    const int b = blockIdx.x;
+    const int n = pos[(size_t)b * kCtrStride];
+    unsigned long long *row = keys + (size_t)b * Apad;
+    if (n <= cap) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) row[__ldg(touched + (size_t)b * cap + i)] = 0ull;
+    } else {   // more positives than the list holds: the whole row
+        for (int i = threadIdx.x; i < Apad; i += blockDim.x) row[i] = 0ull;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pos[(size_t)b * kCtrStride] = 0;
+        if (b == 0) *done = 0u;
+    }
+}
+
 static int g_sms = 0;
 static int sm_count() {
     if (!g_sms) {
@@ -695,6 +723,16 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
             a.xmb.p[r] = (unsigned char *)x->mailboxes[r];
         }
         a.xworld = x->world; a.xrank = x->rank; a.xnpos = x->num_pos_plus_1; a.xout = x->global_out3; a.xstatus = x->status;
+        a.xnormalized = x->normalized; a.xtimeout_ms = x->timeout_ms;
+    }
+    a.clr_cap = 0;
+    if (params->clear_keys) {
+        if (!fused || !params->match_is_key64) return set_error(ODK_EINVAL, "odk_loss: clear_keys needs odk_assign_grid's 64-bit keys");
+        const AssignGridWs w = assign_grid_layout(B, a.g.Apad);
+        char *aws = (char *)match;   // the keys are the head of the labeler's workspace
+        a.clr_keys = (unsigned long long *)aws; a.clr_pos = (int32_t *)(aws + w.pos);
+        a.clr_touched = (const unsigned *)(aws + w.touched); a.clr_done = (unsigned *)(aws + w.done);
+        a.clr_cap = w.touched_cap;
     }
     a.partials = (double *)workspace;
     a.counter = (unsigned *)((char *)workspace + (size_t)kMaxPartials * 2 * sizeof(double));
@@ -720,16 +758,22 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
     cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned), st);
     if (e != cudaSuccess) return set_error((int)e, "odk_loss memset: %s", cudaGetErrorString(e));
     const int mode = params->legacy_focal ? kLegacy : (params->label_smoothing > 0.0f ? kNewSmooth : kNew);
+    rc = -1;
 #define ODK_LOSS_CASE(M)                                                                                       \
     if (mode == M) {                                                                                           \
-        if (grad) return fused ? launch_loss<M, true, true>(ring, plain, st) : launch_loss<M, true, false>(ring, plain, st);   \
-        return fused ? launch_loss<M, false, true>(ring, plain, st) : launch_loss<M, false, false>(ring, plain, st);           \
+        if (grad) rc = fused ? launch_loss<M, true, true>(ring, plain, st) : launch_loss<M, true, false>(ring, plain, st);   \
+        else rc = fused ? launch_loss<M, false, true>(ring, plain, st) : launch_loss<M, false, false>(ring, plain, st);      \
     }
     ODK_LOSS_CASE(kNew)
     ODK_LOSS_CASE(kNewSmooth)
     ODK_LOSS_CASE(kLegacy)
 #undef ODK_LOSS_CASE
-    return set_error(ODK_EINVAL, "odk_loss: bad mode");
+    if (rc < 0) return set_error(ODK_EINVAL, "odk_loss: bad mode");
+    if (rc == ODK_OK && a.clr_cap > 0) {
+        clear_keys_kernel<<<B, 256, 0, st>>>(a.clr_keys, a.clr_pos, a.clr_touched, a.clr_done, a.g.Apad, a.clr_cap);
+        rc = check_launch("odk_loss/clear_keys_kernel");
+    }
+    return rc;
 }
 
 }  // extern "C"

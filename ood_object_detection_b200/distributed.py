@@ -102,7 +102,7 @@ def local_partial_sums(labeler, cls_outputs, box_outputs, gt_boxes, gt_classes, 
     from .loss import loss_fn_fused
     if buf is None:
         buf = torch.empty((4,), dtype=torch.float32, device=gt_boxes.device)
-    lb = labeler.assign(gt_boxes, gt_classes, normalizer_out=buf[3:4])
+    lb = labeler.assign(gt_boxes, gt_classes, normalizer_out=buf[3:4], transient=True)
     loss_fn_fused(cls_outputs, box_outputs, lb, normalizer=unit, out=buf,
                   exchange=None if mailbox is None else mailbox.attach(buf[3:4]), **loss_kw)
     return buf
@@ -136,7 +136,7 @@ class PeerMailbox:
     store); ``world == 1`` (or ``local_only``) uses plain device memory.  Raises when symmetric memory
     cannot be set up -- callers fall back to ``all_reduce_partial_sums`` (NCCL)."""
 
-    def __init__(self, device, group=None, local_only=False):
+    def __init__(self, device, group=None, local_only=False, timeout_ms=30000):
         from . import _lib
         self._lib = _lib
         lib = _lib.lib()
@@ -172,10 +172,11 @@ class PeerMailbox:
         self._ptrs = (_lib.ctypes.c_void_p * self.world)(*ptrs)
         self._ptr_list = ptrs
         self.published = self.collected = 0
+        self.timeout_ms = int(timeout_ms)   # how long a collect waits for the peers (wall clock); the status flag is sticky
         self.out3 = torch.zeros((3,), dtype=torch.float32, device=self.device)
         self.status = torch.zeros((1,), dtype=torch.int32, device=self.device)
 
-    def attach(self, num_pos_plus_1):
+    def attach(self, num_pos_plus_1, normalized=False):
         """Descriptor for ``loss_fn_fused(..., exchange=...)``: the loss kernel's finishing CTA collects the
         previous step's records into ``self.out3`` / ``self.status`` (when one is outstanding) and publishes
         its own sums together with ``num_pos_plus_1`` (float32 [1], what the labeler wrote)."""
@@ -188,12 +189,22 @@ class PeerMailbox:
         x.world, x.rank = self.world, self.rank
         x.num_pos_plus_1 = num_pos_plus_1.data_ptr()
         x.global_out3, x.status = self.out3.data_ptr(), self.status.data_ptr()
+        x.normalized, x.timeout_ms = int(bool(normalized)), int(self.timeout_ms)
         self._keep = (x, num_pos_plus_1)
         return x
 
     def previous(self):
-        """(total, cls, box) of the last step a fused launch or ``collect()`` has collected."""
+        """(total, cls, box) of the last step a fused launch or ``collect()`` has collected (NaN if that step's
+        records did not arrive in time; ``check()`` raises then)."""
         return self.out3[0], self.out3[1], self.out3[2]
+
+    def check(self):
+        """Raise if any collect so far timed out (the device flag is sticky: 1 + the first failing sequence number).
+        Reads one int from the device: call it where a sync is acceptable (end of an epoch, logging step)."""
+        st = int(self.status.item())
+        if st != 0:
+            raise RuntimeError(f'peer mailbox exchange: the records of step {st - 1} did not arrive within '
+                               f'{self.timeout_ms} ms (a rank is gone or stalled); loss values since then are NaN')
 
     def publish(self, buf4):
         if buf4.dtype != torch.float32 or buf4.numel() < 4 or not buf4.is_contiguous() or buf4.device != self.device:
@@ -211,7 +222,7 @@ class PeerMailbox:
         status = self.status if status is None else status
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().odk_partials_collect(_lib.ptr(self.buf), self.world, _lib.ptr(out), _lib.ptr(status),
-                                                       _lib.stream_ptr(self.device)))
+                                                       self.timeout_ms, _lib.stream_ptr(self.device)))
         self.collected += 1
         return (out[0], out[1], out[2]), status
 

@@ -79,10 +79,13 @@ class _DetectionLossFn(torch.autograd.Function):
             gbox = [torch.empty_like(t) for t in box_out]
             gcls_p, gbox_p = _lib.ptr_array(gcls), _lib.ptr_array(gbox)
         fused = meta.get('label_batch')
+        if fused is not None and fused.consumed:
+            raise RuntimeError('this LabelBatch was created with transient=True and has already been consumed by a loss call')
         use_keys = fused is not None and fused.keys is not None
+        clear = use_keys and fused.transient and fused.workspace is not None
         exchange = meta.get('exchange')   # distributed.PeerMailbox.attach(...) descriptor, or None
         params = _lib.LossParams(meta['alpha'], meta['gamma'], meta['delta'], meta['box_loss_weight'],
-                                 meta['label_smoothing'], int(bool(meta['legacy_focal'])), int(use_keys),
+                                 meta['label_smoothing'], int(bool(meta['legacy_focal'])), int(use_keys), int(clear),
                                  _lib.ctypes.pointer(exchange) if exchange is not None else None)
         if fused is not None:
             match = fused.keys if use_keys else fused.match
@@ -97,8 +100,11 @@ class _DetectionLossFn(torch.autograd.Function):
                                     _lib.ptr(match), _lib.ptr(anchors), _lib.ptr(gtb), _lib.ptr(gtl), mmax,
                                     _lib.ptr(cls_t), _lib.ptr(box_t), _lib.ptr(meta['normalizer']), params,
                                     _lib.ptr(out), gcls_p, gbox_p, _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr(dev)))
-        if need_grad:
-            ctx.gcls, ctx.gbox = gcls, gbox
+        if clear:   # the kernel's last CTA zeroed the keys: the workspace goes back to the labeler, the batch is spent
+            fused.consumed = True
+            fused.labeler._recycle(fused.workspace)
+            fused.keys = fused.workspace = None
+        ctx.gcls, ctx.gbox = (gcls, gbox) if need_grad else (None, None)
         ctx.box_loss_weight = meta['box_loss_weight']
         ctx.levels = n
         ctx.in_dtypes = [t.dtype for t in outputs]
@@ -108,10 +114,19 @@ class _DetectionLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_total, g_cls, g_box):
         lib = _lib.lib()
+        if ctx.gcls is None:
+            # the buffers were scaled in place and handed to autograd by the first backward (no copy, no second
+            # 1.2 GB pass); a second walk over the graph would need them back
+            raise RuntimeError('the fused detection loss supports ONE backward pass per forward (its gradient buffers are '
+                               'handed to autograd as .grad): call loss_fn again instead of retain_graph=True, and '
+                               'backpropagate a single combination of (loss, class_loss, box_loss)')
         dev = ctx.gcls[0].device
         # stored: d total / d logits (= d cls_loss / d logits) and d total / d box (= w * d box_loss / d box);
         # in the usual total.backward() both factors ARE g_total and no torch kernel runs here
         w = ctx.box_loss_weight
+        if w == 0 and g_box is not None:
+            raise RuntimeError('box_loss_weight == 0: the stored box gradient is w * d box_loss / d box = 0, so a gradient '
+                               'through box_loss alone cannot be recovered; use a non-zero weight or detach box_loss')
 
         def factor(a, b):
             if a is None and b is None:
@@ -120,7 +135,7 @@ class _DetectionLossFn(torch.autograd.Function):
             return t.float().reshape(1).contiguous()
 
         s_cls = factor(g_total, g_cls)
-        s_box = factor(g_total, None if (g_box is None or w == 0) else g_box.float() / w)
+        s_box = factor(g_total, None if g_box is None else g_box.float() / w)
         with torch.cuda.device(dev):
             for bufs, sc in ((ctx.gcls, s_cls), (ctx.gbox, s_box)):
                 for lo in range(0, len(bufs), 16):

@@ -62,8 +62,8 @@ def test_abi_argument_errors_without_gpu():
     assert lib.odk_partials_publish(None, None, 0, 0, None) == -1 and b'world' in lib.odk_last_error()
     assert lib.odk_partials_publish(None, None, 2, 2, None) == -1
     assert lib.odk_partials_publish(None, None, 2, 1, None) == -1 and b'partials4' in lib.odk_last_error()
-    assert lib.odk_partials_collect(None, 2, None, None, None) == -1
-    assert lib.odk_partials_collect(None, 99, None, None, None) == -1 and b'world' in lib.odk_last_error()
+    assert lib.odk_partials_collect(None, 2, None, None, 0, None) == -1
+    assert lib.odk_partials_collect(None, 99, None, None, 0, None) == -1 and b'world' in lib.odk_last_error()
     # odk_detect / odk_loss validate their parameter structs before touching the device
     assert lib.odk_detect(None, None, None, None, 1, 10, None, 100, None, None, None, None, None, None, None) == -1
     assert b'params' in lib.odk_last_error()
@@ -168,15 +168,18 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     from ood_object_detection_b200 import _lib
     src = tmp_path / 'layout.c'
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "odk.h"\n'
-                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(odk_loss_params), '
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(odk_loss_params), '
                    'offsetof(odk_loss_params, exchange), sizeof(odk_exchange), offsetof(odk_exchange, world), '
-                   'offsetof(odk_exchange, num_pos_plus_1), offsetof(odk_exchange, status), sizeof(odk_detect_params)); return 0; }\n')
+                   'offsetof(odk_exchange, num_pos_plus_1), offsetof(odk_exchange, status), sizeof(odk_detect_params), '
+                   'offsetof(odk_loss_params, clear_keys), offsetof(odk_exchange, normalized), '
+                   'offsetof(odk_exchange, timeout_ms), offsetof(odk_detect_params, pipeline)); return 0; }\n')
     exe = tmp_path / 'layout'
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), '-o', str(exe), str(src)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(_lib.LossParams), _lib.LossParams.exchange.offset, ctypes.sizeof(_lib.Exchange),
             _lib.Exchange.world.offset, _lib.Exchange.num_pos_plus_1.offset, _lib.Exchange.status.offset,
-            ctypes.sizeof(_lib.DetectParams)]
+            ctypes.sizeof(_lib.DetectParams), _lib.LossParams.clear_keys.offset, _lib.Exchange.normalized.offset,
+            _lib.Exchange.timeout_ms.offset, _lib.DetectParams.pipeline.offset]
     assert got == want
 
 
@@ -276,7 +279,7 @@ def test_bench_wrappers_with_stubbed_kernels(monkeypatch):
 
     with_labeler = B.DetBenchTrain(Model())   # default: own labeler, fused path
     assert with_labeler.anchor_labeler is not None and with_labeler.anchor_labeler.num_classes == 7
-    monkeypatch.setattr(with_labeler.anchor_labeler, 'assign', lambda boxes, cls: ('label_batch', boxes, cls))
+    monkeypatch.setattr(with_labeler.anchor_labeler, 'assign', lambda boxes, cls, transient=False: ('label_batch', boxes, cls))
     with_labeler.loss_fn = FakeLoss()
     with_labeler.train()
     assert with_labeler(x, {'bbox': 'gtb', 'cls': 'gtc'}) == {'loss': 't', 'class_loss': 'c', 'box_loss': 'b'}

@@ -146,6 +146,39 @@ def test_config3_4_postprocess_properties(name, B):
     assert torch.equal(out['max_logit'][:4][ok], rows.amax(2)[ok])
 
 
+@pytest.mark.parametrize('regime', ['dense', 'planted'])
+@pytest.mark.parametrize('pipeline', ['staged', 'persistent'])
+def test_config3_d3_b32_soft_nms_full_rows(regime, pipeline):
+    """configs[2] as BASELINE.json names it: D3 896^2, B=32, SOFT-NMS.  Full detection rows (boxes, rescored values,
+    classes, source ranks) of six images against the oracle chain, hard NMS of the same batch too, both pipelines
+    of odk_postprocess; in the planted (trained-net-like) regime also: how many images left the sampled-threshold
+    path (flags) -- none may, for either regime."""
+    from ood_object_detection_b200.bench import post_process_detect
+    from test_gpu_postprocess import assert_dets_close
+    size, scale = synth.MODEL_SHAPES['d3']
+    B, C, K, D = 32, 90, 5000, 100
+    if regime == 'dense':
+        cls, box = device_outputs(21, B, size, C)
+    else:
+        co, bo = synth.planted_outputs(22, 6, size, C)        # six planted images, tiled to the batch
+        reps = (B + 5) // 6
+        cls = [torch.from_numpy(np.concatenate([c] * reps)[:B]).to(DEV) for c in co]
+        box = [torch.from_numpy(np.concatenate([b] * reps)[:B]).to(DEV) for b in bo]
+    anc = orc.anchor_boxes(3, 7, 3, synth.ASPECTS, scale, (size, size))
+    check = [0, 1, 2, 3, 4, 5]
+    ref = orc.post_process([c[check].cpu().numpy() for c in cls], [b[check].cpu().numpy() for b in box], 5, C, K)
+    for soft in (True, False):
+        out = post_process_detect(cls, box, torch.from_numpy(anc).to(DEV), 5, C, K, D, soft, return_flags=True, pipeline=pipeline)
+        assert int(out['flags'].sum()) == 0, f'{int(out["flags"].sum())} of {B} images took the exact path'
+        for j, i in enumerate(check):
+            det, src = orc.generate_detections(ref[0][j], ref[1][j], anc, ref[2][j], ref[3][j], None, None, D, soft, return_src=True)
+            n = int(out['count'][i])
+            assert n == det.shape[0]
+            np.testing.assert_array_equal(out['src'][i, :n].cpu().numpy(), src)
+            np.testing.assert_array_equal(out['anchor'][i, :n].cpu().numpy(), ref[2][j][src])
+            assert_dets_close(out['detections'][i, :n].cpu().numpy(), det)
+
+
 def test_non_square_images_whole_chain():
     """H != W (384x640) and a different anchor scale: exercises the (y, x) index maps, the plane
     descriptors of the gt-centric kernel and every per-level stride with H_l != W_l."""

@@ -93,9 +93,55 @@ def test_peer_mailbox_single_rank_sequences():
         assert int(status) == 0
         n = 7.0 + step
         np.testing.assert_allclose([float(tot), float(cl), float(bx)], [(10.0 + step) / n, (4.0 + step) / n, 0.12 / n], rtol=1e-6)
-    # a collect with nothing published gives up (bounded spin) and says so instead of hanging the GPU
-    _, status = mb.collect()
-    assert int(status) == 1
+    # a collect with nothing published gives up after timeout_ms of wall clock and says so instead of hanging the GPU:
+    # NaN losses, a STICKY status (1 + the sequence number that failed), and the record set is waited for again
+    mb.timeout_ms = 20
+    (tot, _, _), status = mb.collect()
+    assert int(status) == 1 + 6 and torch.isnan(tot)
+    with pytest.raises(RuntimeError, match='did not arrive'):
+        mb.check()
+    mb.publish(torch.tensor([3.0, 2.0, 1.0, 2.0], device=DEV))
+    (tot, cl, bx), status = mb.collect()          # the same sequence number, now present
+    np.testing.assert_allclose([float(tot), float(cl), float(bx)], [1.5, 1.0, 0.5], rtol=1e-6)
+    assert int(status) == 1 + 6                   # sticky: the caller decides when to look and clear
+
+
+def test_peer_mailbox_late_rank_is_never_summed_stale():
+    """Two ranks emulated on one GPU (rank 1 publishes into rank 0's mailbox from its own counters): when rank 1 is
+    late, rank 0's collect times out WITHOUT consuming the step -- it must not sum whatever older record sits in
+    rank 1's slot -- and picks the step up once the record has arrived."""
+    from ood_object_detection_b200 import _lib
+    lib = _lib.lib()
+    nbytes = int(lib.odk_mailbox_bytes(2))
+    mb0 = torch.zeros((nbytes,), dtype=torch.uint8, device=DEV)
+    mb1 = torch.zeros((nbytes,), dtype=torch.uint8, device=DEV)
+    ptrs = (_lib.ctypes.c_void_p * 2)(mb0.data_ptr(), mb1.data_ptr())
+    out, status = torch.zeros(3, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+    st = _lib.stream_ptr(torch.device(DEV))
+
+    def publish(rank, vals):
+        v = torch.tensor(vals, dtype=torch.float32, device=DEV)
+        _lib.check(lib.odk_partials_publish(_lib.ptr(v), ptrs, 2, rank, st))
+        torch.cuda.synchronize()
+
+    def collect(timeout_ms):
+        _lib.check(lib.odk_partials_collect(_lib.ptr(mb0), 2, _lib.ptr(out), _lib.ptr(status), timeout_ms, st))
+        torch.cuda.synchronize()
+        return out.cpu().numpy().copy(), int(status)
+
+    publish(0, [4.0, 2.0, 1.0, 3.0]); publish(1, [6.0, 2.0, 3.0, 4.0])       # step 1, both ranks: n = 3 + 4 - 1 = 6
+    got, stt = collect(1000)
+    np.testing.assert_allclose(got, [10.0 / 6, 4.0 / 6, 4.0 / 6], rtol=1e-6)
+    assert stt == 0
+    publish(0, [1.0, 1.0, 1.0, 2.0]); publish(1, [1.0, 1.0, 1.0, 2.0])       # step 2
+    collect(1000)
+    publish(0, [8.0, 4.0, 2.0, 2.0])                                          # step 3: rank 1 is late ...
+    got, stt = collect(20)                                                    # ... its slot still holds step 1's record
+    assert np.isnan(got).all() and stt == 1 + 3
+    publish(1, [4.0, 2.0, 1.0, 3.0])                                          # ... now it arrives
+    got, stt = collect(1000)
+    np.testing.assert_allclose(got, [12.0 / 4, 6.0 / 4, 3.0 / 4], rtol=1e-6)  # step 3's own records, n = 2 + 3 - 1
+    assert stt == 1 + 3
 
 
 def test_peer_mailbox_in_cuda_graph():

@@ -37,6 +37,34 @@ def test_anchor_table(golden):
     np.testing.assert_allclose(d0[1], [-7.2, -18.4, 15.2, 26.4], rtol=1e-6)
 
 
+def test_repo_anchors_match_the_reference_table(golden):
+    """The package's own Anchors (the table the kernels and every GPU test use) against the reference's table for
+    d0 / d3 / d5 / d7: count, first and last rows bit for bit, and the float64 checksums; plus bit equality with
+    the oracle's table and the plane descriptors the gt-centric labeler derives from it."""
+    from ood_object_detection_b200.anchors import Anchors
+    g = golden('anchors')
+    for name, (size, scale) in synth.MODEL_SHAPES.items():
+        anc = Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size))
+        b = anc.boxes.numpy()
+        assert b.dtype == np.float32 and b.shape == (int(g[f'{name}_count']), 4)
+        np.testing.assert_array_equal(b[:32], g[f'{name}_head'])
+        np.testing.assert_array_equal(b[-32:], g[f'{name}_tail'])
+        np.testing.assert_allclose(b.astype(np.float64).sum(0), g[f'{name}_sum64'], rtol=1e-13)
+        wgt = (np.arange(b.shape[0], dtype=np.float64) % 1009 + 1)[:, None]
+        np.testing.assert_allclose((b.astype(np.float64) * wgt).sum(0), g[f'{name}_wsum64'], rtol=1e-13)
+        np.testing.assert_array_equal(b, anchors_for(size, scale))
+        # plane descriptors: cell (0, 0) of every (level, shape) grid is the table's own first row of that plane
+        desc = anc.plane_desc.numpy()
+        assert desc.shape == (5 * 9, 12)
+        for k in (0, 8, 9, 44):
+            off, a = int(desc[k, 9]), int(desc[k, 10])
+            row = b[off + a].astype(np.float64)
+            np.testing.assert_allclose([desc[k, 0] - desc[k, 4], desc[k, 1] - desc[k, 5], desc[k, 0] + desc[k, 4], desc[k, 1] + desc[k, 5]],
+                                       row, rtol=1e-6, atol=1e-4)
+    assert 'anchors.plane_desc' not in Anchors(3, 7, 3, synth.ASPECTS, 4.0, (128, 128)).state_dict() \
+        and 'plane_desc' not in Anchors(3, 7, 3, synth.ASPECTS, 4.0, (128, 128)).state_dict()
+
+
 # ------------------------------------------------------------------ labeler
 @pytest.mark.parametrize('tag,kw', [('empty', {}), ('zero_iou', {}), ('identical', {}), ('tiny', {}),
                                     ('padded_float', {}), ('collide', {}), ('nofilter', {'filter_valid': False})])
