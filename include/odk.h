@@ -261,6 +261,23 @@ int odk_nms(const float *boxes, const float *scores, int n, double iou_thr, int6
 int odk_ood(const void *const *cls_levels, int B, int C, const int32_t *level_hw, int num_levels, int na,
             const int64_t *anchor_idx, int D, float temperature, float *energy, float *max_logit, void *stream);
 
+/* ---- evaluation: per-image true/false positives and CorLoc ------------------------------------
+ * Replaces PerImageEvaluation.compute_object_detection_metrics (effdet/evaluation/per_image_evaluation.py:29-92;
+ * _compute_tp_fp :177-240, _compute_tp_fp_for_single_class :305-470, _compute_cor_loc :93-175,
+ * _remove_invalid_boxes :512-536; np_box_list.py iou / ioa / non_max_suppression), the numpy loop the reference's
+ * evaluators run per image on the host (detection_evaluator.py:268-305), for a whole batch on the device.
+ *   dets [B,D,6] rows x0,y0,x1,y1,score,class as odk_detect writes them; count [B] rows in use or NULL (= D);
+ *   gt_boxes [B,M,4] yxyx fp32; gt_labels [B,M] int32 in the same numbering as dets' class column, < 0 = padding;
+ *   gt_difficult / gt_group_of [B,M] uint8 or NULL; class index = label - label_offset must be in [0, num_classes);
+ *   match_iou 0.5, nms_iou 1.0 (= off) and nms_max 10000 are the ObjectDetectionEvaluation defaults.
+ * Outputs: label [B,D] int8 per detection slot: 1 true positive, 0 false positive, -1 ignored (matched a difficult
+ * or group-of box; group_of_weight 0), -2 not evaluated (padding, invalid box, removed by the NMS);
+ * corloc [B,num_classes] uint8.  Decisions are bit-exact (numpy's mixed fp32 / float64 arithmetic is reproduced);
+ * equal scores are taken later-detection-first (numpy's argsort()[::-1] leaves that order unspecified). */
+int odk_match_detections(const float *dets, const int32_t *count, int B, int D, const float *gt_boxes, const int32_t *gt_labels,
+                         const uint8_t *gt_difficult, const uint8_t *gt_group_of, int M, int num_classes, int label_offset,
+                         double match_iou, double nms_iou, int nms_max, int8_t *label, uint8_t *corloc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,7 @@ SIGNATURES = {
     'odk_soft_nms': (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, c_int, _P, _P, _P, _P]),
     'odk_nms_workspace_bytes': (c_size_t, [c_int]),
     'odk_nms': (c_int, [_P, _P, c_int, c_double, _P, _P, _P, c_size_t, _P]),
+    'odk_match_detections': (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_double, c_double, c_int, _P, _P, _P]),
     'odk_ood': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_float, _P, _P, _P]),
 }
 

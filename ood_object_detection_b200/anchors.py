@@ -190,6 +190,8 @@ class AnchorLabeler(object):
         self.match_threshold = match_threshold
         self.num_classes = num_classes
         self.indices_cache = {}
+        self._dev_tables = {}
+        self.host_results = False
         self._clean_ws = {}   # (device, bytes) -> workspaces the fused loss has left all-zero again (transient batches)
         # gt-centric kernel (odk_assign_grid) for the regular pyramid grids; the dense kernel
         # (odk_assign) is kept for arbitrary anchor sets and non-positive thresholds
@@ -197,14 +199,36 @@ class AnchorLabeler(object):
 
     # ---- helpers ---------------------------------------------------------------------------
     def _device(self):
+        """The CUDA device the kernels run on.  With ``anchors`` on a CUDA device: that one, and results stay
+        there.  With ``anchors`` still on the host -- how the reference's datasets build their labeler
+        (preloader.py:60-62, dataloader.py:60-66) -- the current CUDA device is used with cached device copies of
+        the anchor table, and the targets are copied back to the host so the calling script sees what the
+        reference gave it (``host_results``).  There is no CPU implementation."""
         dev = self.anchors.boxes.device
-        if dev.type != 'cuda':
-            raise RuntimeError('AnchorLabeler: anchors.boxes must be on a CUDA device (call anchors.cuda()); '
-                               'there is no CPU fallback')
-        return dev
+        if dev.type == 'cuda':
+            self.host_results = False
+            return dev
+        if not torch.cuda.is_available():
+            raise RuntimeError('AnchorLabeler needs a CUDA device: the assignment only exists as sm_100a kernels (no CPU '
+                               'fallback).  In a forked DataLoader worker label in the main process instead '
+                               '(ood_object_detection_b200.pipeline.label_batch_targets)')
+        self.host_results = True
+        return torch.device('cuda', torch.cuda.current_device())
+
+    def _anchor_tables(self, dev):
+        """(boxes, plane_desc) on ``dev`` (cached copies when the module itself lives on the host)."""
+        if self.anchors.boxes.device == dev:
+            return self.anchors.boxes, getattr(self.anchors, 'plane_desc', None)
+        key = (dev, self.anchors.boxes.data_ptr())
+        if self._dev_tables.get('key') != key:
+            desc = getattr(self.anchors, 'plane_desc', None)
+            self._dev_tables = {'key': key, 'boxes': self.anchors.boxes.to(dev), 'desc': None if desc is None else desc.to(dev)}
+        return self._dev_tables['boxes'], self._dev_tables['desc']
 
     def _pack(self, gt_boxes, gt_classes, filter_valid):
-        """-> gt_boxes [B,M,4] fp32, labels [B,M] int32, count [B] int32 or None, on device."""
+        """-> gt_boxes [B,M,4] fp32, labels [B,M] int32, count [B] int32 or None, on device.  Ragged lists (the
+        reference scripts' call form, preloader.py:146, dataloader.py:207-210) are padded with ONE vectorised
+        scatter and reach the device in one copy per array -- no per-image launches or copies."""
         dev = self._device()
         if isinstance(gt_boxes, torch.Tensor) and gt_boxes.dim() == 3:
             boxes = gt_boxes.to(dev, torch.float32).contiguous()
@@ -213,27 +237,65 @@ class AnchorLabeler(object):
             return boxes, labels, None
         lens = [int(b.shape[0]) for b in gt_boxes]
         B, M = len(lens), max([1] + lens)
+        for b, n in zip(gt_boxes, lens):
+            if n and b.dtype != torch.float32:
+                raise ValueError('Invalid tensor type: should be tf.float32')  # BoxList contract
+        total = sum(lens)
+        rows = np.repeat(np.arange(B), lens)
+        cols = np.arange(total) - np.repeat(np.cumsum([0] + lens[:-1]), lens)
+        count = torch.tensor(lens, dtype=torch.int32).to(dev, non_blocking=True)
+        if total == 0:
+            return (torch.zeros((B, M, 4), dtype=torch.float32, device=dev),
+                    torch.full((B, M), -1, dtype=torch.int32, device=dev), count)
+        flat_b = torch.cat([b.reshape(-1, 4) for b, n in zip(gt_boxes, lens) if n])
+        flat_c = torch.cat([c.reshape(-1) for c, n in zip(gt_classes, lens) if n]).to(torch.int32)
+        if flat_b.device.type == 'cpu':     # pad on the host (pinned), one H2D per array
+            boxes_h = torch.zeros((B, M, 4), dtype=torch.float32).pin_memory()
+            labels_h = torch.full((B, M), -1, dtype=torch.int32).pin_memory()
+            boxes_h[rows, cols] = flat_b
+            labels_h[rows, cols] = flat_c
+            return boxes_h.to(dev, non_blocking=True), labels_h.to(dev, non_blocking=True), count
+        r, c = torch.from_numpy(rows).to(dev, non_blocking=True), torch.from_numpy(cols).to(dev, non_blocking=True)
         boxes = torch.zeros((B, M, 4), dtype=torch.float32, device=dev)
         labels = torch.full((B, M), -1, dtype=torch.int32, device=dev)
-        for i, n in enumerate(lens):
-            if n:
-                if gt_boxes[i].dtype != torch.float32:
-                    raise ValueError('Invalid tensor type: should be tf.float32')  # BoxList contract
-                boxes[i, :n] = gt_boxes[i].to(dev)
-                labels[i, :n] = gt_classes[i].to(dev).to(torch.int32)
-        count = torch.tensor(lens, dtype=torch.int32, device=dev)
+        boxes[r, c] = flat_b.to(dev)
+        labels[r, c] = flat_c.to(dev)
         return boxes, labels, count
 
-    def _relabel_task_cls(self, gt_boxes, gt_classes, task_cls):
-        # reference anchors.py:396-403: every gt overlapping a task-class gt by IoU > 0.9 takes
-        # the task class; the caller's class tensors are modified in place.
-        from .object_detection import BoxList
-        for i in range(len(gt_boxes)):
-            task_mask = gt_classes[i] == task_cls
-            if (~task_mask).sum() > 0:
-                sims = self.target_assigner._similarity_calc.compare(BoxList(gt_boxes[i][task_mask]), BoxList(gt_boxes[i]))
-                overlapping, _ = (sims > 0.9).max(0) if sims.shape[0] > 0 else (torch.zeros_like(task_mask), None)
-                gt_classes[i][overlapping] = task_cls
+    @staticmethod
+    def _relabel_task_cls(boxes, labels, count, task_cls):
+        """Reference anchors.py:396-403 for the whole batch at once, on the device: every gt box that a box of the
+        task class overlaps with IoU > 0.9 takes the task class.  boxes [B,M,4], labels [B,M] (padded), count [B]
+        or None.  Same fp32 operation order as IouSimilarity (region_similarity_calculator.py:48-73), one
+        [B,M,M] pass, no host synchronisation.  (An image with other boxes but none of the task class makes the
+        reference raise from ``max`` over an empty dimension; here it is simply left unchanged.)"""
+        B, M = labels.shape
+        valid = torch.ones_like(labels, dtype=torch.bool) if count is None else \
+            torch.arange(M, device=labels.device)[None, :] < count[:, None]
+        task = (labels == int(task_cls)) & valid
+        ymin, xmin, ymax, xmax = boxes.unbind(-1)
+        area = (ymax - ymin) * (xmax - xmin)
+        h = (torch.min(ymax[:, :, None], ymax[:, None, :]) - torch.max(ymin[:, :, None], ymin[:, None, :])).clamp(min=0)
+        w = (torch.min(xmax[:, :, None], xmax[:, None, :]) - torch.max(xmin[:, :, None], xmin[:, None, :])).clamp(min=0)
+        inter = h * w
+        union = area[:, :, None] + area[:, None, :] - inter
+        iou = torch.where(inter == 0.0, torch.zeros_like(inter), inter / union)
+        hit = ((iou > 0.9) & task[:, :, None]).any(1) & valid
+        return torch.where(hit, torch.full_like(labels, int(task_cls)), labels)
+
+    @staticmethod
+    def _write_back_classes(gt_classes, new_labels, count):
+        """The reference relabels the CALLER's class tensors in place (anchors.py:403); so do we: one device->host
+        copy for host inputs, one slice copy per tensor otherwise (no per-image synchronisation)."""
+        if isinstance(gt_classes, torch.Tensor):
+            gt_classes.copy_(new_labels.reshape(gt_classes.shape).to(gt_classes.dtype))
+            return
+        lens = [int(c.shape[0]) for c in gt_classes]
+        host = new_labels.cpu() if any(c.device.type == 'cpu' for c in gt_classes) else None
+        for i, (c, n) in enumerate(zip(gt_classes, lens)):
+            if n:
+                src = host[i, :n] if c.device.type == 'cpu' else new_labels[i, :n]
+                c.copy_(src.reshape(c.shape).to(c.dtype))
 
     def _recycle(self, ws):
         """Called by the fused loss for a transient batch: its kernel has zeroed the keys it read."""
@@ -245,20 +307,20 @@ class AnchorLabeler(object):
         ``transient``: the batch will be consumed by exactly one fused loss call (what ``DetBenchTrain`` does); that
         kernel then zeroes the assignment keys it read, and the next ``assign`` reuses the workspace without the
         8-bytes-per-anchor memset."""
-        if task_cls is not None:
-            self._relabel_task_cls(gt_boxes, gt_classes, task_cls)
         boxes, labels, count = self._pack(gt_boxes, gt_classes, filter_valid)
+        if task_cls is not None:
+            labels = self._relabel_task_cls(boxes, labels, count, task_cls)
+            self._write_back_classes(gt_classes, labels, count)
         dev = boxes.device
         B, M = boxes.shape[0], boxes.shape[1]
         lib = _lib.lib()
-        anc = self.anchors.boxes
+        anc, desc = self._anchor_tables(dev)
         A = anc.shape[0]
         apad = lib.odk_planar_stride(A)
         num_pos = torch.empty((B,), dtype=torch.float32, device=dev)
         hw = self.anchors.level_hw()
         na = self.anchors.get_anchors_per_location()
         thr = float(np.float32(self.match_threshold))
-        desc = getattr(self.anchors, 'plane_desc', None)
         with torch.cuda.device(dev):
             if self.use_grid_kernel and desc is not None and thr > 0.0:
                 # the assignment stays in the workspace as 64-bit keys: the fused loss reads them directly,
@@ -299,10 +361,13 @@ class AnchorLabeler(object):
         cls_flat = torch.empty((B * A,), dtype=torch.int64, device=dev)
         box_flat = torch.empty((B * A * 4,), dtype=torch.float32, device=dev)
         hw = self.anchors.level_hw()
+        anc, _ = self._anchor_tables(dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.odk_targets(_lib.ptr(self.anchors.boxes), _lib.ptr(lb.gt_boxes), _lib.ptr(lb.gt_labels), B, M,
+            _lib.check(lib.odk_targets(_lib.ptr(anc), _lib.ptr(lb.gt_boxes), _lib.ptr(lb.gt_labels), B, M,
                                        _lib.int_array(hw), len(hw), na, _lib.ptr(lb.match), _lib.ptr(cls_flat),
                                        _lib.ptr(box_flat), _lib.stream_ptr(dev)))
+        if self.host_results:   # anchors live on the host: the caller gets host tensors back, like from the reference
+            cls_flat, box_flat = cls_flat.cpu(), box_flat.cpu()
         cls_out, box_out = [], []
         offs = self.anchors.level_offsets()
         for i, level in enumerate(range(self.anchors.min_level, self.anchors.max_level + 1)):
@@ -317,14 +382,15 @@ class AnchorLabeler(object):
         """One image: ([H_l, W_l, na] int64 per level, [H_l, W_l, na*4] fp32 per level, num_positives)."""
         lb = self.assign([gt_boxes], [gt_classes.reshape(-1)], filter_valid=filter_valid)
         cls_t, box_t = lb.targets()
-        return [c[0] for c in cls_t], [b[0] for b in box_t], lb.num_positives[0]
+        npos = lb.num_positives.cpu() if self.host_results else lb.num_positives
+        return [c[0] for c in cls_t], [b[0] for b in box_t], npos[0]
 
     def batch_label_anchors(self, gt_boxes, gt_classes, filter_valid=True, task_cls=None):
         """([B, H_l, W_l, na] int64 per level, [B, H_l, W_l, na*4] fp32 per level, num_positives [B])."""
         assert len(gt_boxes) == len(gt_classes)
         lb = self.assign(gt_boxes, gt_classes, filter_valid=filter_valid, task_cls=task_cls)
         cls_t, box_t = lb.targets()
-        return cls_t, box_t, lb.num_positives
+        return cls_t, box_t, (lb.num_positives.cpu() if self.host_results else lb.num_positives)
 
 
 # ------------------------------------------------------------------------------- detections

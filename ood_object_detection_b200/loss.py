@@ -89,7 +89,7 @@ class _DetectionLossFn(torch.autograd.Function):
                                  _lib.ctypes.pointer(exchange) if exchange is not None else None)
         if fused is not None:
             match = fused.keys if use_keys else fused.match
-            anchors, gtb, gtl = fused.labeler.anchors.boxes, fused.gt_boxes, fused.gt_labels
+            anchors, gtb, gtl = fused.labeler._anchor_tables(dev)[0], fused.gt_boxes, fused.gt_labels
             cls_t = box_t = None
             mmax = gtb.shape[1]
         else:

@@ -47,3 +47,36 @@ def detections_for_evaluator(dets: torch.Tensor, count: torch.Tensor, yxyx: bool
         rows = arr[i, :D * 6].reshape(D, 6)[:n]
         out.append({'bbox': rows[:, :4].copy(), 'scores': rows[:, 4].copy(), 'cls': rows[:, 5].copy()})
     return out
+
+
+def match_detections(dets: torch.Tensor, count, gt_boxes: torch.Tensor, gt_classes: torch.Tensor, num_classes: int,
+                     gt_difficult=None, gt_group_of=None, label_offset: int = 1, matching_iou_threshold: float = 0.5,
+                     nms_iou_threshold: float = 1.0, nms_max_output_boxes: int = 10000):
+    """Per-image true/false-positive labels and CorLoc flags for a whole batch on the device:
+    what ``ObjectDetectionEvaluator.add_single_detected_image_info`` ->
+    ``PerImageEvaluation.compute_object_detection_metrics`` computes with numpy image by image on the host
+    (effdet/evaluation/detection_evaluator.py:268-305, per_image_evaluation.py:29-92).
+
+    dets [B, D, 6] (x0, y0, x1, y1, score, class; as ``detect_batch`` / ``post_process_detect`` return them),
+    count [B] or None; gt_boxes [B, M, 4] yxyx, gt_classes [B, M] in the detections' class numbering (< 0 = padding).
+    Returns (label [B, D] int8: 1 tp / 0 fp / -1 ignored / -2 not evaluated, corloc [B, num_classes] uint8); the AP /
+    CorLoc accumulation over the dataset (a sort by score and two cumulative sums) stays with the caller."""
+    from . import _lib
+    lib = _lib.lib()
+    dets = _lib.require_cuda(dets, 'detections').float().contiguous()
+    dev = dets.device
+    B, D = dets.shape[0], dets.shape[1]
+    gtb = gt_boxes.to(dev, torch.float32).reshape(B, -1, 4).contiguous()
+    M = gtb.shape[1]
+    gtl = gt_classes.to(dev).reshape(B, M).to(torch.int32).contiguous()
+    cnt = None if count is None else count.to(dev, torch.int32).contiguous()
+    dif = None if gt_difficult is None else gt_difficult.to(dev).reshape(B, M).to(torch.uint8).contiguous()
+    gof = None if gt_group_of is None else gt_group_of.to(dev).reshape(B, M).to(torch.uint8).contiguous()
+    label = torch.empty((B, D), dtype=torch.int8, device=dev)
+    corloc = torch.empty((B, int(num_classes)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.odk_match_detections(_lib.ptr(dets), _lib.ptr(cnt), B, D, _lib.ptr(gtb), _lib.ptr(gtl), _lib.ptr(dif),
+                                            _lib.ptr(gof), M, int(num_classes), int(label_offset), float(matching_iou_threshold),
+                                            float(nms_iou_threshold), int(nms_max_output_boxes), _lib.ptr(label), _lib.ptr(corloc),
+                                            _lib.stream_ptr(dev)))
+    return label, corloc

@@ -525,3 +525,114 @@ ORC_API int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------ F4: per-image TP/FP matching and CorLoc
+ * effdet/evaluation/per_image_evaluation.py:29-92 (compute_object_detection_metrics), :93-175 (CorLoc),
+ * :177-240 (_compute_tp_fp, per class), :276-303 (_get_overlaps_and_scores_box_mode), :305-470
+ * (_compute_tp_fp_for_single_class: compute_match_iou / compute_match_ioa), :512-536 (_remove_invalid_boxes);
+ * effdet/evaluation/np_box_list.py:128-205 (area / intersection / iou / ioa), :297-396 (sort_by_field,
+ * non_max_suppression).  numpy arithmetic as the reference runs it on float32 boxes: areas and the coordinate
+ * differences are rounded in fp32, but np.maximum(np.zeros(...), diff) promotes the intersection sides to
+ * float64, so intersection, union (= (float)(area1 + area2) - inter) and the ratios are float64.
+ * Classes are 0-based here (the evaluator has already removed its label offset).  Outputs per detection slot:
+ * 1 true positive, 0 false positive, -1 ignored (matched a difficult or a group-of box), -2 removed (invalid box,
+ * score filter, NMS); corloc[c] as _compute_cor_loc.  group_of_weight = 0 (the reference's default): detections
+ * matched to group-of boxes are only ignored.  Ties between equal scores: numpy's argsort()[::-1] order is
+ * unspecified; this restatement takes the later detection first (a stable ascending sort, reversed). */
+static double eval_inter(const float *p, const float *q) {
+    const float h32 = fminf(p[2], q[2]) - fmaxf(p[0], q[0]);
+    const float w32 = fminf(p[3], q[3]) - fmaxf(p[1], q[1]);
+    const double h = h32 > 0.0f ? (double)h32 : 0.0, w = w32 > 0.0f ? (double)w32 : 0.0;
+    return h * w;
+}
+static double eval_iou(const float *p, const float *q) {
+    const double inter = eval_inter(p, q);
+    const float a1 = area_yxyx(p), a2 = area_yxyx(q);
+    return inter / ((double)(a1 + a2) - inter);
+}
+typedef struct { float s; int64_t i; } si64_t;
+static int si64_cmp_desc_later_first(const void *pa, const void *pb) {
+    const si64_t *a = (const si64_t *)pa, *b = (const si64_t *)pb;
+    if (a->s != b->s) return a->s > b->s ? -1 : 1;
+    return a->i > b->i ? -1 : (a->i < b->i ? 1 : 0);
+}
+
+ORC_API void orc_match_detections(const float *det_boxes, const float *det_scores, const int64_t *det_classes, int64_t N,
+                                  const float *gt_boxes, const int64_t *gt_classes, const uint8_t *gt_difficult,
+                                  const uint8_t *gt_group_of, int64_t M, int64_t num_classes, double match_iou,
+                                  double nms_iou, int64_t nms_max, int8_t *label, uint8_t *corloc) {
+    si64_t *order = (si64_t *)malloc(sizeof(si64_t) * (size_t)(N > 0 ? N : 1));
+    int64_t *sel = (int64_t *)malloc(sizeof(int64_t) * (size_t)(N > 0 ? N : 1));
+    uint8_t *gt_done = (uint8_t *)malloc((size_t)(M > 0 ? M : 1));
+    for (int64_t i = 0; i < N; ++i) label[i] = -2;
+    for (int64_t c = 0; c < num_classes; ++c) {
+        corloc[c] = 0;
+        /* _remove_invalid_boxes + _get_ith_class_arrays */
+        int64_t n = 0, best = -1;
+        for (int64_t i = 0; i < N; ++i) {
+            const float *b = det_boxes + 4 * i;
+            if (det_classes[i] != c || !(b[0] < b[2] && b[1] < b[3])) continue;
+            if (best < 0 || det_scores[i] > det_scores[best]) best = i;          /* np.argmax: first maximum */
+            if (det_scores[i] > -10.0f) { order[n].s = det_scores[i]; order[n].i = i; ++n; }   /* filter_scores_greater_than */
+        }
+        int64_t mc = 0;
+        for (int64_t m = 0; m < M; ++m) mc += gt_classes[m] == c;
+        /* CorLoc (:143-175): the best-scoring detection against every gt box of the class */
+        if (best >= 0 && mc > 0) {
+            double mx = -1.0;
+            for (int64_t m = 0; m < M; ++m)
+                if (gt_classes[m] == c) { const double v = eval_iou(det_boxes + 4 * best, gt_boxes + 4 * m); if (v > mx) mx = v; }
+            corloc[c] = mx >= match_iou;
+        }
+        if (n == 0) continue;
+        qsort(order, (size_t)n, sizeof(si64_t), si64_cmp_desc_later_first);
+        /* non_max_suppression (np_box_list.py:328-396) */
+        int64_t k = 0;
+        if (nms_iou >= 1.0) {
+            for (int64_t j = 0; j < n && k < nms_max; ++j) sel[k++] = order[j].i;
+        } else {
+            for (int64_t j = 0; j < n && k < nms_max; ++j) {
+                int keep = 1;
+                for (int64_t q = 0; q < k && keep; ++q)
+                    if (eval_iou(det_boxes + 4 * sel[q], det_boxes + 4 * order[j].i) > nms_iou) keep = 0;
+                if (keep) sel[k++] = order[j].i;
+            }
+        }
+        for (int64_t j = 0; j < k; ++j) label[sel[j]] = 0;
+        if (mc == 0) continue;                      /* :365-366: no gt of the class, every detection is a false positive */
+        memset(gt_done, 0, (size_t)(M > 0 ? M : 1));
+        /* compute_match_iou (:379-407) over the non-group-of boxes, then compute_match_ioa (:409-441) */
+        for (int64_t j = 0; j < k; ++j) {
+            const float *d = det_boxes + 4 * sel[j];
+            int64_t gid = -1;
+            double gv = -1.0;
+            for (int64_t m = 0; m < M; ++m) {
+                if (gt_classes[m] != c || (gt_group_of && gt_group_of[m])) continue;
+                const double v = eval_iou(d, gt_boxes + 4 * m);
+                if (v > gv) { gv = v; gid = m; }                                  /* np.argmax: first maximum */
+            }
+            if (gid >= 0 && gv >= match_iou) {
+                if (!(gt_difficult && gt_difficult[gid])) {
+                    if (!gt_done[gid]) { label[sel[j]] = 1; gt_done[gid] = 1; }
+                } else {
+                    label[sel[j]] = -1;
+                }
+            }
+        }
+        if (gt_group_of) {
+            for (int64_t j = 0; j < k; ++j) {
+                if (label[sel[j]] != 0) continue;   /* not a true positive, not matched to a difficult box */
+                const float *d = det_boxes + 4 * sel[j];
+                int64_t gid = -1;
+                double gv = -1.0;
+                for (int64_t m = 0; m < M; ++m) {
+                    if (gt_classes[m] != c || !gt_group_of[m]) continue;
+                    const double v = eval_inter(gt_boxes + 4 * m, d) / (double)area_yxyx(d);   /* ioa(gt, det) */
+                    if (v > gv) { gv = v; gid = m; }
+                }
+                if (gid >= 0 && gv >= match_iou) label[sel[j]] = -1;
+            }
+        }
+    }
+    free(order); free(sel); free(gt_done);
+}

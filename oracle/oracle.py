@@ -320,3 +320,23 @@ def gather_logit_rows(cls_outputs, anchor_idx, num_classes, na=9):
     B = cls_outputs[0].shape[0]
     allc = np.concatenate([np.transpose(c, (0, 2, 3, 1)).reshape(B, -1, num_classes) for c in cls_outputs], 1)
     return np.take_along_axis(allc, np.asarray(anchor_idx)[:, :, None].astype(np.int64), 1)
+
+
+# ------------------------------------------------------------------------------------ evaluation
+def match_detections(det_boxes, det_scores, det_classes, gt_boxes, gt_classes, num_classes, gt_difficult=None,
+                     gt_group_of=None, match_iou=0.5, nms_iou=1.0, nms_max=10000):
+    """effdet/evaluation/per_image_evaluation.py:29-92 for one image (boxes yxyx, classes 0-based) ->
+    (label [N] int8: 1 tp / 0 fp / -1 ignored / -2 removed, corloc [num_classes] uint8)."""
+    db, ds, dc = _f32(det_boxes).reshape(-1, 4), _f32(det_scores).reshape(-1), _i64(det_classes).reshape(-1)
+    gb, gc = _f32(gt_boxes).reshape(-1, 4), _i64(gt_classes).reshape(-1)
+    N, M = db.shape[0], gb.shape[0]
+    u8p = ctypes.POINTER(ctypes.c_uint8)
+    dif = None if gt_difficult is None else np.ascontiguousarray(gt_difficult, np.uint8)
+    gof = None if gt_group_of is None else np.ascontiguousarray(gt_group_of, np.uint8)
+    label = np.empty((max(N, 1),), np.int8)
+    corloc = np.zeros((num_classes,), np.uint8)
+    lib().orc_match_detections(_p(db, _f32p), _p(ds, _f32p), _p(dc, _i64p), ctypes.c_int64(N), _p(gb, _f32p), _p(gc, _i64p),
+                               None if dif is None else _p(dif, u8p), None if gof is None else _p(gof, u8p), ctypes.c_int64(M),
+                               ctypes.c_int64(num_classes), ctypes.c_double(match_iou), ctypes.c_double(nms_iou),
+                               ctypes.c_int64(nms_max), label.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)), _p(corloc, u8p))
+    return label[:N], corloc

@@ -276,7 +276,25 @@ def gold_softnms():
     save('softnms', **out)
 
 
+# ----------------------------------------------------------------------------- evaluation
+def gold_evaluation():
+    from effdet.evaluation.per_image_evaluation import PerImageEvaluation
+    out = {}
+    for tag, seed, n_det, n_gt, C, nms_iou, nms_max, flags in synth.EVAL_CASES:
+        det, scores, cls, gtb, gtc, dif, gof = synth.eval_case(seed, n_det, n_gt, C)
+        if not flags:
+            dif[:] = False
+            gof[:] = False
+        ev = PerImageEvaluation(C, matching_iou_threshold=0.5, nms_iou_threshold=nms_iou, nms_max_output_boxes=nms_max)
+        sc, tp, corloc = ev.compute_object_detection_metrics(det.copy(), scores.copy(), cls.copy(), gtb.copy(), gtc.copy(), dif.copy(), gof.copy())
+        out[f'{tag}_corloc'] = np.asarray(corloc).astype(np.uint8)
+        for c in range(C):
+            out[f'{tag}_scores_{c}'] = np.asarray(sc[c], np.float32)
+            out[f'{tag}_tp_{c}'] = np.asarray(tp[c]).astype(np.float32)
+    save('evaluation', **out)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['anchors', 'labeler', 'loss', 'postprocess', 'softnms']
+    which = sys.argv[1:] or ['anchors', 'labeler', 'loss', 'postprocess', 'softnms', 'evaluation']
     for w in which:
         globals()['gold_' + w]()

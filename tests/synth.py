@@ -124,3 +124,27 @@ def nms_candidates(seed, n, image_size, num_classes, n_clusters=40):
     scores = rs.uniform(0.02, 1.0, n).astype(np.float32)
     classes = np.where(rs.uniform(size=n) < 0.8, kcls[which], rs.randint(0, num_classes, n)).astype(np.int64)
     return boxes, scores, classes
+
+
+# (tag, seed, detections, gt boxes, classes, nms_iou, nms_max, difficult / group-of flags): per-image evaluation cases
+EVAL_CASES = [('plain', 71, 100, 12, 8, 1.0, 10000, False), ('flags', 72, 100, 30, 5, 1.0, 10000, True),
+              ('nms', 73, 100, 10, 4, 0.3, 50, True), ('one_class', 74, 60, 6, 1, 1.0, 10000, False),
+              ('no_gt_of_class', 75, 40, 3, 20, 1.0, 10000, False)]
+
+
+def eval_case(seed, n_det, n_gt, num_classes, size=512.0):
+    """Detections scattered around (and away from) the gt boxes, unique scores, a few invalid boxes."""
+    rs = np.random.RandomState(seed)
+    gb, gc = gt_boxes(seed, 1, int(size), n_gt, num_classes)
+    gtb, gt_classes = gb[0], (gc[0] - 1).astype(np.int64)               # 0-based like the evaluator sees them
+    src = rs.randint(0, max(n_gt, 1), n_det)
+    det = gtb[src] + rs.standard_normal((n_det, 4)).astype(np.float32) * rs.choice([2.0, 12.0, 60.0], (n_det, 1)).astype(np.float32)
+    det = det.astype(np.float32)
+    det[::17, 2] = det[::17, 0]                                               # invalid: ymax == ymin
+    cls = np.where(rs.uniform(size=n_det) < 0.8, gt_classes[src], rs.randint(0, num_classes, n_det)).astype(np.int64)
+    scores = rs.permutation(n_det).astype(np.float32) / np.float32(n_det) * np.float32(0.98) + np.float32(0.01)
+    difficult = rs.uniform(size=n_gt) < 0.15
+    group_of = rs.uniform(size=n_gt) < 0.15
+    return det, scores, cls, gtb, gt_classes, difficult, group_of
+
+

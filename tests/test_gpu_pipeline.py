@@ -196,3 +196,74 @@ def test_loss_kernel_fused_exchange_single_rank():
     got, status = mb.collect()     # drain: the last step's record
     assert int(status) == 0
     np.testing.assert_allclose([float(v) for v in got], refs[-1], rtol=1e-5)
+
+
+def test_match_detections_vs_reference_goldens_and_oracle(golden):
+    """odk_match_detections on a batch made of the five evaluation cases whose results the
+    reference's PerImageEvaluation produced (tests/golden/evaluation.npz): per-class (score, tp/fp) sequences and
+    CorLoc flags bit-identical, and per-slot labels identical to the oracle's."""
+    from ood_object_detection_b200.pipeline import match_detections
+    from test_oracle_golden import assert_eval_matches_golden
+    g = golden('evaluation')
+    for nms_iou, nms_max in ((1.0, 10000), (0.3, 50)):
+        cases = [c for c in synth.EVAL_CASES if (c[5], c[6]) == (nms_iou, nms_max)]
+        D, M, C = max(c[2] for c in cases), max(c[3] for c in cases), max(c[4] for c in cases)
+        B = len(cases)
+        dets = np.zeros((B, D, 6), np.float32)
+        count = np.zeros((B,), np.int32)
+        gtb = np.zeros((B, M, 4), np.float32)
+        gtl = np.full((B, M), -1, np.int32)
+        dif, gof = np.zeros((B, M), np.uint8), np.zeros((B, M), np.uint8)
+        raw = []
+        for i, (tag, seed, n_det, n_gt, Ci, _, _, flags) in enumerate(cases):
+            det, scores, cls, gb, gc, d_, g_ = synth.eval_case(seed, n_det, n_gt, Ci)
+            if not flags:
+                d_[:] = False
+                g_[:] = False
+            dets[i, :n_det, 0], dets[i, :n_det, 1], dets[i, :n_det, 2], dets[i, :n_det, 3] = det[:, 1], det[:, 0], det[:, 3], det[:, 2]
+            dets[i, :n_det, 4], dets[i, :n_det, 5] = scores, cls + 1            # class column is 1-based (anchors.py:157)
+            count[i] = n_det
+            gtb[i, :n_gt], gtl[i, :n_gt], dif[i, :n_gt], gof[i, :n_gt] = gb, gc + 1, d_, g_
+            raw.append((tag, Ci, det, scores, cls, gb, gc, d_, g_))
+        label, corloc = match_detections(torch.from_numpy(dets).to(DEV), torch.from_numpy(count).to(DEV), torch.from_numpy(gtb).to(DEV),
+                                         torch.from_numpy(gtl).to(DEV), C, torch.from_numpy(dif).to(DEV), torch.from_numpy(gof).to(DEV),
+                                         label_offset=1, nms_iou_threshold=nms_iou, nms_max_output_boxes=nms_max)
+        label, corloc = label.cpu().numpy(), corloc.cpu().numpy()
+        for i, (tag, Ci, det, scores, cls, gb, gc, d_, g_) in enumerate(raw):
+            n = det.shape[0]
+            assert (label[i, n:] == -2).all() and (corloc[i, Ci:] == 0).all()
+            assert_eval_matches_golden(g, tag, Ci, scores, cls, label[i, :n], corloc[i, :Ci])
+            o_label, o_corloc = orc.match_detections(det, scores, cls, gb, gc, Ci, d_, g_, 0.5, nms_iou, nms_max)
+            np.testing.assert_array_equal(label[i, :n], o_label)
+            np.testing.assert_array_equal(corloc[i, :Ci], o_corloc)
+
+
+def test_match_detections_on_pipeline_output():
+    """Detections straight from odk_postprocess (planted objects) against gt boxes placed on some of them: the
+    device labels equal the oracle's for every image, without any per-image device->host hop."""
+    from ood_object_detection_b200.bench import post_process_detect
+    from ood_object_detection_b200.pipeline import match_detections
+    size, B, C, K, D = 256, 4, 12, 1500, 40
+    co, bo = synth.planted_outputs(95, B, size, C, n_obj=25)
+    anc = torch.from_numpy(orc.anchor_boxes(3, 7, 3, synth.ASPECTS, 4.0, (size, size))).to(DEV)
+    out = post_process_detect([torch.from_numpy(x).to(DEV) for x in co], [torch.from_numpy(x).to(DEV) for x in bo], anc, 5, C, K, D, False)
+    dets, count = out['detections'], out['count']
+    d = dets.cpu().numpy()
+    M = 8
+    gtb = np.zeros((B, M, 4), np.float32)
+    gtl = np.full((B, M), -1, np.int32)
+    rs = np.random.RandomState(3)
+    for i in range(B):
+        n = int(count[i])
+        pick = rs.choice(n, size=min(M - 2, n), replace=False)
+        gtb[i, :len(pick)] = d[i, pick][:, [1, 0, 3, 2]] + rs.standard_normal((len(pick), 4)).astype(np.float32) * 1.5
+        gtl[i, :len(pick)] = d[i, pick, 5].astype(np.int32)
+    label, corloc = match_detections(dets, count, torch.from_numpy(gtb).to(DEV), torch.from_numpy(gtl).to(DEV), C)
+    assert int((label == 1).sum()) > 0
+    for i in range(B):
+        n = int(count[i])
+        valid = gtl[i] >= 0
+        o_label, o_corloc = orc.match_detections(d[i, :n][:, [1, 0, 3, 2]], d[i, :n, 4], d[i, :n, 5].astype(np.int64) - 1,
+                                                 gtb[i][valid], gtl[i][valid].astype(np.int64) - 1, C)
+        np.testing.assert_array_equal(label[i, :n].cpu().numpy(), o_label)
+        np.testing.assert_array_equal(corloc[i].cpu().numpy(), o_corloc)

@@ -239,3 +239,31 @@ def test_ood_definition():
     ref = -np.log(np.exp(rows.astype(np.float64)).sum(1))
     np.testing.assert_allclose(e, ref, rtol=1e-6)
     np.testing.assert_array_equal(m, rows.max(1))
+
+
+# ------------------------------------------------------------------ per-image evaluation
+def assert_eval_matches_golden(g, tag, C, scores, cls, label, corloc):
+    """Per-slot labels (1 tp / 0 fp / -1 ignored / -2 removed) against the reference's per-class (scores,
+    tp_fp_labels) arrays -- same (score, label) sequence per class -- and its CorLoc flags."""
+    np.testing.assert_array_equal(np.asarray(corloc), g[f'{tag}_corloc'])
+    for c in range(C):
+        sel = (cls == c) & (label >= 0)
+        order = np.argsort(-scores[sel], kind='stable')
+        np.testing.assert_array_equal(scores[sel][order], g[f'{tag}_scores_{c}'])
+        np.testing.assert_array_equal(label[sel][order].astype(np.float32), g[f'{tag}_tp_{c}'])
+
+
+@pytest.mark.parametrize('case', synth.EVAL_CASES, ids=[c[0] for c in synth.EVAL_CASES])
+def test_match_detections_golden(golden, case):
+    """oracle.match_detections vs PerImageEvaluation.compute_object_detection_metrics of the reference
+    (per_image_evaluation.py:29-92) on detections scattered around the gt boxes: plain, with difficult /
+    group-of boxes, with the class's own NMS (0.3 / 50), a single class, classes without gt."""
+    tag, seed, n_det, n_gt, C, nms_iou, nms_max, flags = case
+    g = golden('evaluation')
+    det, scores, cls, gtb, gtc, dif, gof = synth.eval_case(seed, n_det, n_gt, C)
+    if not flags:
+        dif[:] = False
+        gof[:] = False
+    label, corloc = orc.match_detections(det, scores, cls, gtb, gtc, C, dif, gof, 0.5, nms_iou, nms_max)
+    assert_eval_matches_golden(g, tag, C, scores, cls, label, corloc)
+    assert (label == 1).sum() > 0 and (label == 0).sum() > 0
