@@ -20,6 +20,9 @@
  *     odk_planar_stride(A) (A rounded up to 4).
  *   - `cls_levels` / `box_levels`: HOST arrays of num_levels DEVICE pointers to contiguous
  *     NCHW fp32 tensors [B, na*C, H_l, W_l] / [B, na*4, H_l, W_l] (efficientdet.py:410-414).
+ *   - `layout` (post-process entry points): bit l set = class level l is stored channels_last, i.e.
+ *     [B, H_l, W_l, na*C] in memory (what a channels_last / AMP head writes); bit 8 + l the same for
+ *     box level l ([B, H_l, W_l, na*4], 16-byte aligned).  0 = everything NCHW.  Both are read in place.
  *   - return 0 on success, <0 for argument errors, >0 = cudaError_t of a failed launch;
  *     odk_last_error() returns a thread-local message.  No exceptions cross the ABI.
  */
@@ -137,6 +140,8 @@ typedef struct odk_loss_params {
     int32_t match_is_key64;   /* `match` points at odk_assign_grid's 64-bit keys instead of int32 rows */
     int32_t clear_keys;       /* with match_is_key64 (`match` = the labeler's workspace): after the last read, zero the keys the
                                  labeler set and its counters, so the next odk_assign_grid can run with ODK_ASSIGN_WS_CLEAN */
+    int32_t layout;           /* bit l: class level l is channels_last ([B,H,W,na*C] in memory), bit 8 + l: box level l; 0 = NCHW.
+                                 channels_last levels need `match` (fused targets) */
     const odk_exchange *exchange;   /* NULL = no exchange (HOST pointer, read during the call) */
 } odk_loss_params;
 
@@ -188,7 +193,7 @@ int odk_partials_collect(void *mailbox_local, int world, float *out3, int32_t *s
  */
 size_t odk_topk_workspace_bytes(int B, int C, const int32_t *level_hw, int num_levels, int na, int K);
 int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B, int C, const int32_t *level_hw,
-             int num_levels, int na, int K, float *cls_topk, float *box_topk, int64_t *indices, int64_t *classes,
+             int num_levels, int na, int K, int layout, float *cls_topk, float *box_topk, int64_t *indices, int64_t *classes,
              void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- post-process: detections ---------------------------------------------------------------
@@ -238,7 +243,7 @@ size_t odk_postprocess_flags_offset(int B, int C, const int32_t *level_hw, int n
  * done, suppression done}; then the start and the end of the kernel. */
 size_t odk_postprocess_timeline_offset(int B, int C, const int32_t *level_hw, int num_levels, int na, int K);
 int odk_postprocess(const void *const *cls_levels, const void *const *box_levels, int B, int C, const int32_t *level_hw,
-                    int num_levels, int na, int K, const float *anchors, const float *img_scale, const float *img_size,
+                    int num_levels, int na, int K, int layout, const float *anchors, const float *img_scale, const float *img_size,
                     const odk_detect_params *params, float temperature, float *dets, int32_t *count, int32_t *src,
                     int64_t *det_anchor, float *energy, float *max_logit, float *cls_topk, float *box_topk,
                     int64_t *indices, int64_t *classes, void *workspace, size_t workspace_bytes, void *stream);
@@ -258,7 +263,7 @@ int odk_nms(const float *boxes, const float *scores, int n, double iou_thr, int6
  * Not in the reference.  For anchor_idx [B,D] int64 (entries < 0 skipped ->
  * outputs 0): energy = -T*logsumexp(logits[anchor,:]/T), max_logit = max_c logits[anchor,c],
  * read in place from the NCHW levels (the row the reference gathers at bench.py:51-52). */
-int odk_ood(const void *const *cls_levels, int B, int C, const int32_t *level_hw, int num_levels, int na,
+int odk_ood(const void *const *cls_levels, int B, int C, const int32_t *level_hw, int num_levels, int na, int layout,
             const int64_t *anchor_idx, int D, float temperature, float *energy, float *max_logit, void *stream);
 
 /* ---- evaluation: per-image true/false positives and CorLoc ------------------------------------

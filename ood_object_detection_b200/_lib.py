@@ -29,7 +29,7 @@ class Exchange(ctypes.Structure):
 class LossParams(ctypes.Structure):
     _fields_ = [('alpha', c_float), ('gamma', c_float), ('delta', c_float), ('box_loss_weight', c_float),
                 ('label_smoothing', c_float), ('legacy_focal', ctypes.c_int32), ('match_is_key64', ctypes.c_int32),
-                ('clear_keys', ctypes.c_int32), ('exchange', ctypes.POINTER(Exchange))]
+                ('clear_keys', ctypes.c_int32), ('layout', ctypes.c_int32), ('exchange', ctypes.POINTER(Exchange))]
 
 
 class DetectParams(ctypes.Structure):
@@ -61,19 +61,19 @@ SIGNATURES = {
     'odk_partials_publish': (c_int, [_P, _P, c_int, c_int, _P]),
     'odk_partials_collect': (c_int, [_P, c_int, _P, _P, ctypes.c_uint32, _P]),
     'odk_topk_workspace_bytes': (c_size_t, [c_int, c_int, _P, c_int, c_int, c_int]),
-    'odk_topk': (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    'odk_topk': (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     'odk_detect': (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int64, _P, _P, ctypes.POINTER(DetectParams), _P, _P, _P,
                            _P]),
     'odk_postprocess_workspace_bytes': (c_size_t, [c_int, c_int, _P, c_int, c_int, c_int]),
     'odk_postprocess_flags_offset': (c_size_t, [c_int, c_int, _P, c_int, c_int, c_int]),
     'odk_postprocess_timeline_offset': (c_size_t, [c_int, c_int, _P, c_int, c_int, c_int]),
-    'odk_postprocess': (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, c_int, _P, _P, _P, ctypes.POINTER(DetectParams), c_float,
+    'odk_postprocess': (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, _P, ctypes.POINTER(DetectParams), c_float,
                                 _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     'odk_soft_nms': (c_int, [_P, _P, c_int, c_int, c_float, c_float, c_float, c_int, _P, _P, _P, _P]),
     'odk_nms_workspace_bytes': (c_size_t, [c_int]),
     'odk_nms': (c_int, [_P, _P, c_int, c_double, _P, _P, _P, c_size_t, _P]),
     'odk_match_detections': (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_double, c_double, c_int, _P, _P, _P]),
-    'odk_ood': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P, c_int, c_float, _P, _P, _P]),
+    'odk_ood': (c_int, [_P, c_int, c_int, _P, c_int, c_int, c_int, _P, c_int, c_float, _P, _P, _P]),
 }
 
 
@@ -123,3 +123,22 @@ def int_array(values):
 
 def ptr_array(tensors):
     return (c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def prep_levels(outputs, num_levels, what='head output'):
+    """Head outputs as the kernels read them, IN PLACE: fp32 CUDA tensors that are either contiguous NCHW or
+    channels_last ([B, H, W, C] in memory -- what a channels_last / AMP head writes, efficientdet.py:405-414).
+    Returns (tensors, mask) with bit l of mask set for a channels_last level; only other dtypes / stridings are
+    copied."""
+    outs, mask = [], 0
+    for l, t in enumerate(outputs[:num_levels]):
+        require_cuda(t, what)
+        if t.dtype != torch.float32:
+            t = t.float()
+        if not t.is_contiguous():
+            if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+                mask |= 1 << l
+            else:
+                t = t.contiguous()
+        outs.append(t)
+    return outs, mask

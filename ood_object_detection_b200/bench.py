@@ -19,16 +19,6 @@ from .loss import DetectionLoss
 from .ood import ood_scores
 
 
-def _prep_levels(outputs, num_levels):
-    outs = []
-    for t in outputs[:num_levels]:
-        _lib.require_cuda(t, 'head output')
-        if t.dtype != torch.float32:
-            t = t.float()
-        outs.append(t if t.is_contiguous() else t.contiguous())
-    return outs
-
-
 def _post_process(
         cls_outputs: List[torch.Tensor],
         box_outputs: List[torch.Tensor],
@@ -44,8 +34,9 @@ def _post_process(
     ascending flat index (the reference leaves their order unspecified).
     """
     lib = _lib.lib()
-    cls_l = _prep_levels(cls_outputs, num_levels)
-    box_l = _prep_levels(box_outputs, num_levels)
+    cls_l, cmask = _lib.prep_levels(cls_outputs, num_levels)
+    box_l, bmask = _lib.prep_levels(box_outputs, num_levels)
+    layout = cmask | (bmask << 8)     # channels_last levels are read in place (no NHWC -> NCHW copy)
     dev = cls_l[0].device
     B = cls_l[0].shape[0]
     na = box_l[0].shape[1] // 4
@@ -62,7 +53,7 @@ def _post_process(
     ws = torch.empty(((ws_bytes + 15) // 16 * 2,), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.odk_topk(_lib.ptr_array(cls_l), _lib.ptr_array(box_l), B, int(num_classes), _lib.int_array(hw),
-                                num_levels, na, K, _lib.ptr(cls_k), _lib.ptr(box_k), _lib.ptr(idx), _lib.ptr(klass),
+                                num_levels, na, K, layout, _lib.ptr(cls_k), _lib.ptr(box_k), _lib.ptr(idx), _lib.ptr(klass),
                                 _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr(dev)))
     return cls_k, box_k, idx, klass
 
@@ -82,8 +73,9 @@ def post_process_detect(cls_outputs, box_outputs, anchor_boxes, num_levels, num_
     indices, classes [B,K]).  ``pipeline``: 'staged' (sample -> one-wave collect -> one tail CTA per image) or
     'persistent' (one persistent kernel, the tails overlap the stream of the later images); same results."""
     lib = _lib.lib()
-    cls_l = _prep_levels(cls_outputs, num_levels)
-    box_l = _prep_levels(box_outputs, num_levels)
+    cls_l, cmask = _lib.prep_levels(cls_outputs, num_levels)
+    box_l, bmask = _lib.prep_levels(box_outputs, num_levels)
+    layout = cmask | (bmask << 8)     # channels_last levels are read in place
     dev = cls_l[0].device
     B = cls_l[0].shape[0]
     na = box_l[0].shape[1] // 4
@@ -126,7 +118,7 @@ def post_process_detect(cls_outputs, box_outputs, anchor_boxes, num_levels, num_
     ws = torch.empty(((ws_bytes + 15) // 16 * 2,), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.odk_postprocess(_lib.ptr_array(cls_l), _lib.ptr_array(box_l), B, int(num_classes), hw_arr, num_levels,
-                                       na, K, _lib.ptr(anchor_boxes), _lib.ptr(scale), _lib.ptr(size), params,
+                                       na, K, layout, _lib.ptr(anchor_boxes), _lib.ptr(scale), _lib.ptr(size), params,
                                        float(temperature), _lib.ptr(dets), _lib.ptr(count), _lib.ptr(src), _lib.ptr(anchor),
                                        _lib.ptr(energy), _lib.ptr(max_logit), _lib.ptr(cls_k), _lib.ptr(box_k), _lib.ptr(idx),
                                        _lib.ptr(klass), _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr(dev)))

@@ -233,7 +233,7 @@ nms_kernel(const float4 *__restrict__ boxes, const float *__restrict__ scores, i
 
 // ---- OOD scores --------------------------------------------------------------------------------
 // one warp per detection: energy = -T * logsumexp(row / T), max_logit = max(row)
-struct LevelPtrs { const float *p[ODK_MAX_LEVELS]; };
+struct LevelPtrs { const float *p[ODK_MAX_LEVELS]; unsigned char nhwc[ODK_MAX_LEVELS]; };
 
 __global__ void __launch_bounds__(256)
 ood_kernel(const __grid_constant__ Geo g, const __grid_constant__ LevelPtrs lv, int B, int C, const long long *__restrict__ anchor_idx, int D, float T,
@@ -243,7 +243,7 @@ ood_kernel(const __grid_constant__ Geo g, const __grid_constant__ LevelPtrs lv, 
     const int b = wid / D;
     if (only_flag && __ldg(only_flag + b) == 0u) return;
     float e, m;
-    ood_row(g, lv.p, b, C, __ldg(anchor_idx + wid), T, lane, e, m);
+    ood_row(g, lv.p, lv.nhwc, b, C, __ldg(anchor_idx + wid), T, lane, e, m);
     if (lane == 0) { energy[wid] = e; max_logit[wid] = m; }
 }
 
@@ -275,12 +275,13 @@ int launch_detect_flagged(const float *cls_topk, const float *box_topk, const in
     return check_launch("odk_detect");
 }
 
-int launch_ood_flagged(const Geo &g, const void *const *cls_levels, int B, int C, const int64_t *anchor_idx, int D, float T,
+int launch_ood_flagged(const Geo &g, const void *const *cls_levels, int layout, int B, int C, const int64_t *anchor_idx, int D, float T,
                        float *energy, float *max_logit, const unsigned *only_flag, cudaStream_t st) {
     LevelPtrs lv;
     memset(&lv, 0, sizeof(lv));
     for (int l = 0; l < g.nlev; ++l) {
         lv.p[l] = (const float *)cls_levels[l];
+        lv.nhwc[l] = (layout >> l) & 1;
         if (!lv.p[l]) return set_error(ODK_EINVAL, "odk_ood: null level pointer (level %d)", l);
     }
     const long long warps = (long long)B * D;
@@ -343,7 +344,7 @@ int odk_nms(const float *boxes, const float *scores, int n, double iou_thr, int6
     return check_launch("odk_nms");
 }
 
-int odk_ood(const void *const *cls_levels, int B, int C, const int32_t *level_hw, int num_levels, int na,
+int odk_ood(const void *const *cls_levels, int B, int C, const int32_t *level_hw, int num_levels, int na, int layout,
             const int64_t *anchor_idx, int D, float temperature, float *energy, float *max_logit, void *stream) {
     using namespace odk;
     Geo g;
@@ -353,7 +354,7 @@ int odk_ood(const void *const *cls_levels, int B, int C, const int32_t *level_hw
     if (B == 0 || D == 0) return ODK_OK;
     if (!cls_levels || !anchor_idx || !energy || !max_logit) return set_error(ODK_EINVAL, "odk_ood: null pointer");
     if (!(temperature > 0.0f)) return set_error(ODK_EINVAL, "odk_ood: temperature must be positive");
-    return launch_ood_flagged(g, cls_levels, B, C, anchor_idx, D, temperature, energy, max_logit, nullptr, (cudaStream_t)stream);
+    return launch_ood_flagged(g, cls_levels, layout, B, C, anchor_idx, D, temperature, energy, max_logit, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -338,20 +338,23 @@ static __device__ int soft_nms_rounds(const DetSmem &S, int n, bool gaussian, fl
 
 // OOD scores of one anchor by one warp: energy = -T * logsumexp(row / T), max_logit = max(row) over the C raw
 // class logits of the anchor, read in place from the NCHW level (stride hw between classes).
-__device__ __forceinline__ void ood_row(const Geo &g, const float *const *levels, int b, int C, long long anc, float T, int lane,
-                                        float &e, float &m) {
+__device__ __forceinline__ void ood_row(const Geo &g, const float *const *levels, const unsigned char *nhwc, int b, int C, long long anc,
+                                        float T, int lane, float &e, float &m) {
     e = 0.f; m = 0.f;
     if (anc < 0 || anc >= g.A) return;
     const int l = geo_level(g, (int)anc);
     const int loc = (int)anc - g.off[l];
     const int sp = loc / g.na, a = loc - sp * g.na;
-    const float *row = levels[l] + ((size_t)(b * g.na + a) * C) * g.hw[l] + sp;
+    // NCHW: the row's classes are hw apart; channels_last: they are contiguous
+    const size_t cstride = nhwc[l] ? 1 : (size_t)g.hw[l];
+    const float *row = nhwc[l] ? levels[l] + ((size_t)b * g.hw[l] + sp) * (size_t)(g.na * C) + (size_t)a * C
+                               : levels[l] + ((size_t)(b * g.na + a) * C) * g.hw[l] + sp;
     float mx = -INFINITY;
-    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, __ldg(row + (size_t)c * g.hw[l]));
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, __ldg(row + (size_t)c * cstride));
     mx = warp_max(mx);
     float s = 0.f;
     const float invT = 1.0f / T;
-    for (int c = lane; c < C; c += 32) s += expf((__ldg(row + (size_t)c * g.hw[l]) - mx) * invT);
+    for (int c = lane; c < C; c += 32) s += expf((__ldg(row + (size_t)c * cstride) - mx) * invT);
     s = warp_sum(s);
     e = -T * (mx * invT + logf(s));
     m = mx;

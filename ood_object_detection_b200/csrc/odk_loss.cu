@@ -48,6 +48,7 @@ struct LossArgs {
     unsigned item_off[ODK_MAX_LEVELS + 1];   // items of the levels THIS launch covers
     FastDiv div_nq[ODK_MAX_LEVELS];
     FastDiv div_nchunk, div_na;
+    unsigned char cls_nhwc[ODK_MAX_LEVELS], box_nhwc[ODK_MAX_LEVELS];   // channels_last levels ([B, H, W, channels] in memory)
     int vec[ODK_MAX_LEVELS];   // 4 if the level's planes are 16-byte aligned rows of 4, else 1
     int nq[ODK_MAX_LEVELS];    // position groups per plane
     int B, C, cchunk, nchunk, Mmax;
@@ -390,22 +391,23 @@ __device__ __forceinline__ void loss_item(const LossArgs &A, int l, unsigned loc
 }
 
 // ---- deterministic two-stage reduction shared by both kernels --------------------------------
-__device__ __forceinline__ void finish_block(const LossArgs &A, float csum, float bsum, float nrm) {
+__device__ __forceinline__ void finish_block(const LossArgs &A, float csum, float bsum, float nrm, double cextra = 0.0) {
     __shared__ double s_c[kLossThreads / 32], s_b[kLossThreads / 32];
     __shared__ bool s_last;
     __shared__ float4 s_mine, s_recv[ODK_MAILBOX_MAX_WORLD];
-    double dc = warp_sum((double)csum), db = warp_sum((double)bsum);
+    double dc = warp_sum((double)csum + cextra), db = warp_sum((double)bsum);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) { s_c[warp] = dc; s_b[warp] = db; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double c = 0, bx = 0;
         for (int w = 0; w < kLossThreads / 32; ++w) { c += s_c[w]; bx += s_b[w]; }
-        A.partials[2 * (A.part_base + blockIdx.x)] = c;
-        A.partials[2 * (A.part_base + blockIdx.x) + 1] = bx;
+        const unsigned slot = blockIdx.y * gridDim.x + blockIdx.x;
+        A.partials[2 * (A.part_base + slot)] = c;
+        A.partials[2 * (A.part_base + slot) + 1] = bx;
         __threadfence();
         const unsigned done = atomicAdd(A.counter, 1u);
-        s_last = A.part_total > 0 && (done == gridDim.x - 1);
+        s_last = A.part_total > 0 && (done == gridDim.x * gridDim.y - 1);
     }
     __syncthreads();
     if (s_last) {
@@ -602,6 +604,143 @@ clear_keys_kernel(unsigned long long *keys, int32_t *pos, const unsigned *__rest
     }
 }
 
+
+// ---- channels_last inputs: a layout-agnostic stream + a per-anchor patch --------------------------------------
+// With [B, H, W, na*C] logits a thread's 16 bytes are four CLASSES of one anchor, not four positions of one class,
+// so the plane-walking items above do not apply.  The work splits instead into
+//   loss_flat_kernel  : every logit of every level as a NEGATIVE (target 0): sum of (1 - alpha) * softplus(x) and,
+//                       with gradients, (1 - alpha) / N * sigmoid(x) written in the same pass.  It needs no targets
+//                       and no layout: a level is one flat array.  Box gradients are zero-filled here.
+//   loss_patch_kernel : one thread per anchor; for the matched ones (a few hundred per image) the positive class'
+//                       term and gradient are corrected and the Huber box loss / gradient of its four codes is added.
+//                       Knows both layouts per level, so mixed batches of levels work too.  Finishes the reduction.
+template <int MODE, bool GRAD>
+__global__ void __launch_bounds__(kLossThreads, 4)
+loss_flat_kernel(const __grid_constant__ LossArgs A) {
+    const float nrm = __ldg(A.normalizer);
+    const float inv_n = 1.0f / nrm;
+    const float gneg = (1.0f - A.p.alpha) * inv_n;
+    const size_t stride = (size_t)gridDim.x * kLossThreads;
+    const size_t first = (size_t)blockIdx.x * kLossThreads + threadIdx.x;
+    double dsum = 0.0;
+    for (int l = 0; l < A.g.nlev; ++l) {
+        const size_t len = (size_t)A.B * A.g.na * A.C * A.g.hw[l];
+        const float *px = A.cls[l];
+        float *pg = GRAD ? A.gcls[l] : nullptr;
+        const bool vec4 = (((uintptr_t)px | (uintptr_t)pg) & 15) == 0;
+        const size_t n4 = vec4 ? len / 4 : 0;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, accx[4] = {0.f, 0.f, 0.f, 0.f};
+        int since = 0;
+        auto flush = [&]() {   // fp32 partial sums stay short: a few thousand terms each
+            float v = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { v += (MODE == kNewSmooth ? acc[j] - 0.5f * A.p.label_smoothing * accx[j] : acc[j]); acc[j] = 0.f; accx[j] = 0.f; }
+            dsum += (double)v;
+            since = 0;
+        };
+        size_t u = first;
+        for (; u + 3 * stride < n4; u += 4 * stride) {   // four independent 128-bit loads in flight
+            Vec<4> x0, x1, x2, x3;
+            x0.load_stream(px + u * 4);
+            x1.load_stream(px + (u + stride) * 4);
+            x2.load_stream(px + (u + 2 * stride) * 4);
+            x3.load_stream(px + (u + 3 * stride) * 4);
+            row_compute<4, MODE, GRAD>(A, x0, GRAD ? pg + u * 4 : nullptr, gneg, acc, accx);
+            row_compute<4, MODE, GRAD>(A, x1, GRAD ? pg + (u + stride) * 4 : nullptr, gneg, acc, accx);
+            row_compute<4, MODE, GRAD>(A, x2, GRAD ? pg + (u + 2 * stride) * 4 : nullptr, gneg, acc, accx);
+            row_compute<4, MODE, GRAD>(A, x3, GRAD ? pg + (u + 3 * stride) * 4 : nullptr, gneg, acc, accx);
+            if (++since == 256) flush();
+        }
+        for (; u < n4; u += stride) {
+            Vec<4> x0;
+            x0.load_stream(px + u * 4);
+            row_compute<4, MODE, GRAD>(A, x0, GRAD ? pg + u * 4 : nullptr, gneg, acc, accx);
+        }
+        flush();
+        float t1[1] = {0.f}, t1x[1] = {0.f};
+        for (size_t e = n4 * 4 + first; e < len; e += stride) {   // unaligned level, or the 1-3 elements past the last float4
+            Vec<1> x0;
+            x0.load_stream(px + e);
+            row_compute<1, MODE, GRAD>(A, x0, GRAD ? pg + e : nullptr, gneg, t1, t1x);
+        }
+        dsum += (double)(MODE == kNewSmooth ? t1[0] - 0.5f * A.p.label_smoothing * t1x[0] : t1[0]);
+        if (GRAD) {   // box gradients: zero everywhere, the patch kernel writes the matched anchors'
+            float *gb = A.gbox[l];
+            const size_t blen = (size_t)A.B * A.g.na * 4 * A.g.hw[l];
+            if (((uintptr_t)gb & 15) == 0) {
+                for (size_t q = first; q < blen / 4; q += stride) st_stream4(gb + q * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+            } else {
+                for (size_t q = first; q < blen; q += stride) gb[q] = 0.f;
+            }
+        }
+    }
+    finish_block(A, (float)0.f, 0.f, nrm, (1.0 - (double)A.p.alpha) * dsum);
+}
+
+template <int MODE, bool GRAD>
+__global__ void __launch_bounds__(kLossThreads)
+loss_patch_kernel(const __grid_constant__ LossArgs A) {
+    const Geo &g = A.g;
+    const float nrm = __ldg(A.normalizer);
+    const float inv_n = 1.0f / nrm;
+    float csum = 0.f, bsum = 0.f;
+    const long long total = (long long)A.B * g.Apad;   // persistent grid: a fixed number of partial sums, summed in a fixed order
+    for (long long idx = (long long)blockIdx.x * kLossThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kLossThreads) {
+        const int b = (int)(idx / g.Apad);
+        const int p = (int)(idx - (long long)b * g.Apad);   // planar anchor index
+        if (p >= g.A) continue;
+        {
+        const size_t mi = (size_t)b * g.Apad + p;
+        const int mt = A.p.match_is_key64 ? match_of_key(__ldg(reinterpret_cast<const unsigned long long *>(A.match) + mi))
+                                          : __ldg(A.match + mi);
+        if (mt >= 0) {
+            const int l = geo_level(g, p);
+            const int hw = g.hw[l], loc = p - g.off[l];
+            const int a = loc / hw, pos = loc - a * hw;
+            const int tc = __ldg(A.gt_labels + (size_t)b * A.Mmax + mt) - 1;
+            const float alpha = A.p.alpha, sm = A.p.label_smoothing, gamma = A.p.gamma;
+            if (tc >= 0 && tc < A.C) {
+                const size_t o = A.cls_nhwc[l] ? ((size_t)b * hw + pos) * (size_t)(g.na * A.C) + (size_t)a * A.C + tc
+                                               : ((size_t)(b * g.na + a) * A.C + tc) * hw + pos;
+                const float xp = __ldg(A.cls[l] + o);
+                float gpos;
+                if (MODE == kLegacy) {
+                    const float sp = fmaxf(xp, 0.f) + log1pf(expf(-fabsf(xp)));
+                    const float sg = 1.0f / (1.0f + expf(-xp));
+                    const float mod_n = expf(-gamma * (sp - xp)), mod_p = expf(-gamma * sp);
+                    const float bce_p = sp - xp;
+                    csum += alpha * mod_p * bce_p - (1.0f - alpha) * mod_n * sp;
+                    gpos = alpha * inv_n * mod_p * ((sg - 1.0f) - bce_p * gamma * sg);
+                } else {
+                    float e;
+                    const float sp = softplus_fast(xp, e);
+                    const float tp = MODE == kNewSmooth ? 1.0f - 0.5f * sm : 1.0f;
+                    const float tn = MODE == kNewSmooth ? 0.5f * sm : 0.0f;
+                    csum += alpha * (sp - tp * xp) - (1.0f - alpha) * (sp - tn * xp);
+                    gpos = alpha * inv_n * (sigmoid_from_e(xp, e) - tp);
+                }
+                if (GRAD) A.gcls[l][o] = gpos;
+            }
+            const float4 t4 = encode_ref(__ldg(A.gt_boxes + (size_t)b * A.Mmax + mt), __ldg(A.anchors + g.off[l] + pos * g.na + a));
+            const float tg[4] = {t4.x, t4.y, t4.z, t4.w};
+            const float delta = A.p.delta, gb = A.p.box_loss_weight * inv_n * 0.25f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const size_t o = A.box_nhwc[l] ? ((size_t)b * hw + pos) * (size_t)(g.na * 4) + (size_t)a * 4 + k
+                                               : ((size_t)(b * g.na + a) * 4 + k) * hw + pos;
+                const float tv = tg[k];
+                const float e = __ldg(A.box[l] + o) - tv;          // loss.py:108-112
+                const float ae = fabsf(e), qd = fminf(ae, delta);
+                const bool on = tv != 0.0f;                        // loss.py:177
+                bsum += on ? 0.5f * qd * qd + delta * (ae - qd) : 0.f;
+                if (GRAD) A.gbox[l][o] = on ? gb * (ae <= delta ? e : copysignf(delta, e)) : 0.f;
+            }
+        }
+        }
+    }
+    finish_block(A, csum, bsum, nrm, 0.0);
+}
+
 static int g_sms = 0;
 static int sm_count() {
     if (!g_sms) {
@@ -754,6 +893,46 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
     for (int l = num_levels; l <= ODK_MAX_LEVELS; ++l) { ring.item_off[l] = (unsigned)off_r; plain.item_off[l] = (unsigned)off_p; }
 
     cudaStream_t st = (cudaStream_t)stream;
+    int any_nhwc = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        a.cls_nhwc[l] = (params->layout >> l) & 1;
+        a.box_nhwc[l] = (params->layout >> (8 + l)) & 1;
+        any_nhwc |= a.cls_nhwc[l] | a.box_nhwc[l];
+    }
+    if (any_nhwc) {
+        // channels_last head outputs, read in place: a layout-agnostic stream over the logits + a per-anchor patch
+        if (!fused) return set_error(ODK_EUNSUPPORTED, "odk_loss: channels_last inputs need the labeler's match (targets given as tensors: pass NCHW)");
+        cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned), st);
+        if (e != cudaSuccess) return set_error((int)e, "odk_loss memset: %s", cudaGetErrorString(e));
+        const int mode = params->legacy_focal ? kLegacy : (params->label_smoothing > 0.0f ? kNewSmooth : kNew);
+        const int g_flat = sm_count() * 4, g_patch = sm_count() * 2;
+        LossArgs flat = a, patch = a;
+        flat.part_base = 0; flat.part_total = 0;
+        patch.part_base = g_flat; patch.part_total = g_flat + g_patch;
+        rc = -1;
+#define ODK_NHWC_CASE(M)                                                                   \
+        if (mode == M) {                                                                   \
+            if (grad) loss_flat_kernel<M, true><<<g_flat, kLossThreads, 0, st>>>(flat);    \
+            else loss_flat_kernel<M, false><<<g_flat, kLossThreads, 0, st>>>(flat);        \
+            rc = check_launch("odk_loss/loss_flat_kernel");                                \
+            if (rc) return rc;                                                             \
+            e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned), st);                       \
+            if (e != cudaSuccess) return set_error((int)e, "odk_loss memset: %s", cudaGetErrorString(e)); \
+            if (grad) loss_patch_kernel<M, true><<<g_patch, kLossThreads, 0, st>>>(patch); \
+            else loss_patch_kernel<M, false><<<g_patch, kLossThreads, 0, st>>>(patch);     \
+            rc = check_launch("odk_loss/loss_patch_kernel");                               \
+        }
+        ODK_NHWC_CASE(kNew)
+        ODK_NHWC_CASE(kNewSmooth)
+        ODK_NHWC_CASE(kLegacy)
+#undef ODK_NHWC_CASE
+        if (rc < 0) return set_error(ODK_EINVAL, "odk_loss: bad mode");
+        if (rc == ODK_OK && a.clr_cap > 0) {
+            clear_keys_kernel<<<B, 256, 0, st>>>(a.clr_keys, a.clr_pos, a.clr_touched, a.clr_done, a.g.Apad, a.clr_cap);
+            rc = check_launch("odk_loss/clear_keys_kernel");
+        }
+        return rc;
+    }
     // the counter must be zero on entry; the kernel re-zeroes it, but a fresh workspace is arbitrary
     cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned), st);
     if (e != cudaSuccess) return set_error((int)e, "odk_loss memset: %s", cudaGetErrorString(e));

@@ -315,7 +315,7 @@ static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned lo
     if (P.energy) {
         for (int q = warp; q < D; q += kPostWarps) {
             float e = 0.f, m = 0.f;
-            if (q < kept_n) ood_row(P.T.g, P.G.cls, b, P.T.C, (long long)fd_div(sflat[s_kept[q]], P.T.div_C), P.ood_T, lane, e, m);
+            if (q < kept_n) ood_row(P.T.g, P.G.cls, P.G.nhwc, b, P.T.C, (long long)fd_div(sflat[s_kept[q]], P.T.div_C), P.ood_T, lane, e, m);
             if (lane == 0) { P.energy[(size_t)b * D + q] = e; P.max_logit[(size_t)b * D + q] = m; }
         }
     }
@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_fused_kernel(const __gri
 }
 
 // ---- host ---------------------------------------------------------------------------------------------
-int make_stream_geo(StreamGeo *G, const Geo &g, const void *const *cls_levels, int C) {
+int make_stream_geo(StreamGeo *G, const Geo &g, const void *const *cls_levels, int C, int layout) {
     memset(G, 0, sizeof(*G));
     G->nlev = g.nlev; G->na = g.na; G->C = C;
     G->div_C = make_fastdiv((unsigned)C);
@@ -667,6 +667,7 @@ int make_stream_geo(StreamGeo *G, const Geo &g, const void *const *cls_levels, i
         G->lb[l] = (unsigned)lb;
         G->hw[l] = g.hw[l];
         G->off[l] = g.off[l];
+        G->nhwc[l] = (layout >> l) & 1;
         G->div_hw[l] = make_fastdiv((unsigned)g.hw[l]);
         G->task_off[l] = toff;
         const long long groups_max = (lb + 6) / 4;   // whatever the block's alignment is
@@ -738,7 +739,7 @@ int launch_detect_flagged(const float *cls_topk, const float *box_topk, const in
                           int N, const float *anchors, int64_t A, const float *img_scale, const float *img_size,
                           const odk_detect_params *params, float *dets, int32_t *count, int32_t *src, int64_t *det_anchor,
                           const unsigned *only_flag, cudaStream_t st);
-int launch_ood_flagged(const Geo &g, const void *const *cls_levels, int B, int C, const int64_t *anchor_idx, int D, float T,
+int launch_ood_flagged(const Geo &g, const void *const *cls_levels, int layout, int B, int C, const int64_t *anchor_idx, int D, float T,
                        float *energy, float *max_logit, const unsigned *only_flag, cudaStream_t st);
 
 }  // namespace odk
@@ -775,7 +776,7 @@ size_t odk_postprocess_timeline_offset(int B, int C, const int32_t *level_hw, in
 }
 
 int odk_postprocess(const void *const *cls_levels, const void *const *box_levels, int B, int C, const int32_t *level_hw,
-                    int num_levels, int na, int K, const float *anchors, const float *img_scale, const float *img_size,
+                    int num_levels, int na, int K, int layout, const float *anchors, const float *img_scale, const float *img_size,
                     const odk_detect_params *params, float temperature, float *dets, int32_t *count, int32_t *src,
                     int64_t *det_anchor, float *energy, float *max_logit, float *cls_topk, float *box_topk,
                     int64_t *indices, int64_t *classes, void *workspace, size_t workspace_bytes, void *stream) {
@@ -803,26 +804,15 @@ int odk_postprocess(const void *const *cls_levels, const void *const *box_levels
         return set_error(ODK_EINVAL, "odk_postprocess: the four top-k outputs go together");
     if (((uintptr_t)anchors | (uintptr_t)workspace | (uintptr_t)box_topk) & 15)
         return set_error(ODK_EINVAL, "odk_postprocess: anchors / box_topk / workspace must be 16-byte aligned");
-    rc = make_stream_geo(&P.G, a.g, cls_levels, C);
+    rc = make_stream_geo(&P.G, a.g, cls_levels, C, layout);
     if (rc) return rc;
     const PostWs w = post_ws_layout(P.G, B, K);
     if (!workspace || workspace_bytes < w.total)
         return set_error(ODK_EWORKSPACE, "odk_postprocess: workspace too small (%zu < %zu)", workspace_bytes, w.total);
-    a.B = B; a.C = C; a.K = K; a.planes = na * C;
-    a.div_C = make_fastdiv((unsigned)C);
+    a.B = B; a.C = C; a.K = K;
     int toff = 0;
-    for (int l = 0; l < num_levels; ++l) {   // per-plane task model of odk_topk.cu (the exact fallback uses it)
-        a.cls[l] = (const float *)cls_levels[l];
-        a.box[l] = (const float *)box_levels[l];
-        if (!a.box[l]) return set_error(ODK_EINVAL, "odk_postprocess: null box level pointer (level %d)", l);
-        a.vec[l] = (a.g.hw[l] % 4 == 0 && ((uintptr_t)a.cls[l] & 15) == 0) ? 4 : 1;
-        a.nvec[l] = a.g.hw[l] / a.vec[l];
-        a.nseg[l] = (a.nvec[l] + kSegVec - 1) / kSegVec;
-        a.div_nseg[l] = make_fastdiv((unsigned)a.nseg[l]);
-        a.task_off[l] = toff;
-        toff += a.planes * a.nseg[l];
-    }
-    for (int l = num_levels; l <= ODK_MAX_LEVELS; ++l) a.task_off[l] = toff;
+    rc = fill_topk_levels(&a, cls_levels, box_levels, na, layout, &toff, "odk_postprocess");   // (the collect / exact kernels' task model)
+    if (rc) return rc;
     char *ws = (char *)workspace;
     a.slots = (unsigned *)(ws + w.slots); a.thr = (unsigned *)(ws + w.thr); a.cnt = (unsigned *)(ws + w.cnt);
     a.flag = (unsigned *)(ws + w.flag); a.cand = (unsigned long long *)(ws + w.cand);
@@ -901,7 +891,7 @@ int odk_postprocess(const void *const *cls_levels, const void *const *box_levels
                                a.g.A, img_scale, img_size, params, dets, count, src, det_anchor, a.flag, st);
     if (rc) return rc;
     if (energy) {
-        rc = launch_ood_flagged(a.g, cls_levels, B, C, det_anchor, params->max_det, temperature, energy, max_logit, a.flag, st);
+        rc = launch_ood_flagged(a.g, cls_levels, layout, B, C, det_anchor, params->max_det, temperature, energy, max_logit, a.flag, st);
     }
     return rc;
 }

@@ -25,6 +25,7 @@ struct StreamGeo {
     FastDiv div_hw[ODK_MAX_LEVELS];
     FastDiv div_C, div_ntask;
     int nlev, na, C, ntask_img;
+    unsigned char nhwc[ODK_MAX_LEVELS];   // the level is stored channels_last: memory order is the reference's flat order
 };
 
 struct STask {
@@ -55,6 +56,7 @@ __device__ __forceinline__ STask stream_task(const StreamGeo &G, int b, int t) {
 
 // reference flat top-k index (anchor * C + class, bench.py:37,44) of element e of a level block
 __device__ __forceinline__ unsigned stream_flat(const StreamGeo &G, int l, unsigned e) {
+    if (G.nhwc[l]) return (unsigned)G.off[l] * (unsigned)G.C + e;
     const unsigned ch = fd_div(e, G.div_hw[l]);
     const unsigned pos = e - ch * (unsigned)G.hw[l];
     const unsigned a = fd_div(ch, G.div_C);
@@ -69,7 +71,9 @@ __device__ __forceinline__ unsigned stream_hash(unsigned b, unsigned t) {
 }
 
 // host side (odk_post.cu)
-int make_stream_geo(StreamGeo *G, const Geo &g, const void *const *cls_levels, int C);
+int make_stream_geo(StreamGeo *G, const Geo &g, const void *const *cls_levels, int C, int layout);
+int fill_topk_levels(TopkArgs *a, const void *const *cls_levels, const void *const *box_levels, int na, int layout, int *ntasks,
+                     const char *who);
 struct SampleLaunch {
     StreamGeo G;
     int B, K;

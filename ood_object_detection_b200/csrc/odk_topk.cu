@@ -42,12 +42,11 @@ __global__ void __launch_bounds__(kTopkThreads) topk_collect_kernel(const __grid
     const int ntasks = A.task_off[A.g.nlev];
     unsigned *cnt = A.cnt + b;
     unsigned long long *cand = A.cand + (size_t)b * kCap;
-    const unsigned stride = (unsigned)A.planes;
     for (int t = blockIdx.x * (kTopkThreads / 32) + (threadIdx.x >> 5); t < ntasks; t += W) {
         const Task k = decode_task(A, b, t);
         auto hit = [&](float x, int s) {
             if (x >= thr_f) {
-                const unsigned flat = k.fbase + (unsigned)s * stride;
+                const unsigned flat = k.fbase + (unsigned)s * k.fstride;
                 const unsigned long long key = ((unsigned long long)vkey_of(x) << 32) | (unsigned long long)(~flat);
                 const unsigned slot = atomicAdd(&s_nstage, 1u);
                 if (slot < (unsigned)kStage) {
@@ -118,7 +117,6 @@ topk_exact_kernel(const __grid_constant__ TopkArgs A) {
     const int W = kClusterSize * (kSelThreads / 32);
     const int wid = rank * (kSelThreads / 32) + (threadIdx.x >> 5);
     const int ntasks = A.task_off[A.g.nlev];
-    const unsigned stride = (unsigned)A.planes;
     if (threadIdx.x == 0) { s_prefix = 0ull; s_need = (unsigned)A.K; s_done = 0; }
     unsigned long long lower = 0ull;   // collect every key >= lower
     int shift = 64;
@@ -132,7 +130,7 @@ topk_exact_kernel(const __grid_constant__ TopkArgs A) {
         for (int t = wid; t < ntasks; t += W) {
             const Task k = decode_task(A, b, t);
             auto one = [&](float x, int s) {
-                const unsigned flat = k.fbase + (unsigned)s * stride;
+                const unsigned flat = k.fbase + (unsigned)s * k.fstride;
                 const unsigned long long key = ((unsigned long long)vkey_of(x) << 32) | (unsigned long long)(~flat);
                 const bool in = pshift >= 64 ? true : ((key >> pshift) == (prefix >> pshift));
                 if (in) atomicAdd(&s_hist[(unsigned)(key >> shift) & ((1u << bits) - 1u)], 1u);
@@ -174,7 +172,7 @@ topk_exact_kernel(const __grid_constant__ TopkArgs A) {
     for (int t = wid; t < ntasks; t += W) {
         const Task k = decode_task(A, b, t);
         auto one = [&](float x, int s) {
-            const unsigned flat = k.fbase + (unsigned)s * stride;
+            const unsigned flat = k.fbase + (unsigned)s * k.fstride;
             const unsigned long long key = ((unsigned long long)vkey_of(x) << 32) | (unsigned long long)(~flat);
             if (key >= lower) {
                 const unsigned pos = atomicAdd(A.cnt + b, 1u);
@@ -209,6 +207,36 @@ static TopkWs topk_ws_layout(const StreamGeo &G, int B) {
     w.cand = off; off = al(off + (size_t)B * kCap * sizeof(unsigned long long));
     w.total = off;
     return w;
+}
+
+// per-level task model of the collect / exact kernels: NCHW levels are na * C planes of hw elements, channels_last
+// levels ([B, H, W, channels], bit l of `layout`; bit 8 + l for the box levels) one run of hw * na * C elements
+int fill_topk_levels(TopkArgs *a, const void *const *cls_levels, const void *const *box_levels, int na, int layout, int *ntasks,
+                     const char *who) {
+    a->planes = na * a->C;
+    a->div_C = make_fastdiv((unsigned)a->C);
+    int toff = 0;
+    for (int l = 0; l < a->g.nlev; ++l) {
+        a->cls[l] = (const float *)cls_levels[l];
+        a->box[l] = (const float *)box_levels[l];
+        if (!a->cls[l] || !a->box[l]) return set_error(ODK_EINVAL, "%s: null level pointer (level %d)", who, l);
+        a->cls_nhwc[l] = (layout >> l) & 1;
+        a->box_nhwc[l] = (layout >> (8 + l)) & 1;
+        if (a->box_nhwc[l] && ((uintptr_t)a->box[l] & 15)) return set_error(ODK_EINVAL, "%s: channels_last box level %d must be 16-byte aligned", who, l);
+        a->nplanes[l] = a->cls_nhwc[l] ? 1 : a->planes;
+        const long long plen = a->cls_nhwc[l] ? (long long)a->g.hw[l] * a->planes : a->g.hw[l];
+        if (plen > 0x7fffffffll) return set_error(ODK_EUNSUPPORTED, "%s: level %d too large", who, l);
+        a->plane_len[l] = (int)plen;
+        a->vec[l] = (plen % 4 == 0 && ((uintptr_t)a->cls[l] & 15) == 0) ? 4 : 1;
+        a->nvec[l] = (int)(plen / a->vec[l]);
+        a->nseg[l] = (a->nvec[l] + kSegVec - 1) / kSegVec;
+        a->div_nseg[l] = make_fastdiv((unsigned)a->nseg[l]);
+        a->task_off[l] = toff;
+        toff += a->nplanes[l] * a->nseg[l];
+    }
+    for (int l = a->g.nlev; l <= ODK_MAX_LEVELS; ++l) a->task_off[l] = toff;
+    *ntasks = toff;
+    return ODK_OK;
 }
 
 // one co-resident wave of collect CTAs over the whole batch (per-plane task model)
@@ -252,7 +280,7 @@ size_t odk_topk_workspace_bytes(int B, int C, const int32_t *level_hw, int num_l
 }
 
 int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B, int C, const int32_t *level_hw,
-             int num_levels, int na, int K, float *cls_topk, float *box_topk, int64_t *indices, int64_t *classes,
+             int num_levels, int na, int K, int layout, float *cls_topk, float *box_topk, int64_t *indices, int64_t *classes,
              void *workspace, size_t workspace_bytes, void *stream) {
     using namespace odk;
     static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
@@ -271,23 +299,12 @@ int odk_topk(const void *const *cls_levels, const void *const *box_levels, int B
     if ((size_t)B * na * (size_t)C > 0x7fffffffull) return set_error(ODK_EUNSUPPORTED, "odk_topk: B*na*C overflows int");
     if (((uintptr_t)box_topk | (uintptr_t)workspace) & 15) return set_error(ODK_EINVAL, "odk_topk: box_topk / workspace must be 16-byte aligned");
     if (!workspace) return set_error(ODK_EWORKSPACE, "odk_topk: null workspace");
-    a.B = B; a.C = C; a.K = K; a.planes = na * C;
-    a.div_C = make_fastdiv((unsigned)C);
+    a.B = B; a.C = C; a.K = K;
     int toff = 0;
-    for (int l = 0; l < num_levels; ++l) {
-        a.cls[l] = (const float *)cls_levels[l];
-        a.box[l] = (const float *)box_levels[l];
-        if (!a.cls[l] || !a.box[l]) return set_error(ODK_EINVAL, "odk_topk: null level pointer (level %d)", l);
-        a.vec[l] = (a.g.hw[l] % 4 == 0 && ((uintptr_t)a.cls[l] & 15) == 0) ? 4 : 1;
-        a.nvec[l] = a.g.hw[l] / a.vec[l];
-        a.nseg[l] = (a.nvec[l] + kSegVec - 1) / kSegVec;
-        a.div_nseg[l] = make_fastdiv((unsigned)a.nseg[l]);
-        a.task_off[l] = toff;
-        toff += a.planes * a.nseg[l];
-    }
-    for (int l = num_levels; l <= ODK_MAX_LEVELS; ++l) a.task_off[l] = toff;
+    rc = fill_topk_levels(&a, cls_levels, box_levels, na, layout, &toff, "odk_topk");
+    if (rc) return rc;
     StreamGeo G;
-    rc = make_stream_geo(&G, a.g, cls_levels, C);
+    rc = make_stream_geo(&G, a.g, cls_levels, C, layout);
     if (rc) return rc;
     const TopkWs w = topk_ws_layout(G, B);
     if (workspace_bytes < w.total)

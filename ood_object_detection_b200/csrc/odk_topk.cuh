@@ -22,6 +22,9 @@ struct TopkArgs {
     Geo g;
     const float *cls[ODK_MAX_LEVELS];
     const float *box[ODK_MAX_LEVELS];
+    int nplanes[ODK_MAX_LEVELS];  // contiguous runs per image: na * C channel planes (NCHW) or 1 (channels_last: the whole block)
+    int plane_len[ODK_MAX_LEVELS];   // elements per run: hw (NCHW) or hw * na * C (channels_last)
+    unsigned char cls_nhwc[ODK_MAX_LEVELS], box_nhwc[ODK_MAX_LEVELS];   // the level is stored channels_last ([B, H, W, channels])
     int vec[ODK_MAX_LEVELS];      // 4 or 1
     int nvec[ODK_MAX_LEVELS];     // vector units per plane
     int nseg[ODK_MAX_LEVELS];     // task segments per plane
@@ -67,7 +70,8 @@ struct Task {
     const float *base;   // first element of the plane
     int u0, u1;          // vector-unit range of this segment
     int vec;
-    unsigned fbase;      // flat index of position 0 of this plane: (off_l + a) * C + c
+    unsigned fbase;      // flat index of element 0 of this run: (off_l + a) * C + c (NCHW plane) or off_l * C (channels_last)
+    unsigned fstride;    // flat-index step per element: na * C (NCHW: next position) or 1 (channels_last: memory order IS flat order)
 };
 
 __device__ __forceinline__ int task_level(const TopkArgs &A, int t) {
@@ -83,13 +87,19 @@ __device__ __forceinline__ Task decode_task(const TopkArgs &A, int b, int t) {
     const int local = t - A.task_off[l];
     const int ch = (int)fd_div((unsigned)local, A.div_nseg[l]);
     const int sg = local - ch * A.nseg[l];
-    const int a = (int)fd_div((unsigned)ch, A.div_C), c = ch - a * A.C;
     Task k;
-    k.base = A.cls[l] + ((size_t)b * A.planes + ch) * A.g.hw[l];
+    k.base = A.cls[l] + ((size_t)b * A.nplanes[l] + ch) * A.plane_len[l];
     k.vec = A.vec[l];
     k.u0 = sg * kSegVec;
     k.u1 = min(A.nvec[l], k.u0 + kSegVec);
-    k.fbase = (unsigned)(A.g.off[l] + a) * (unsigned)A.C + (unsigned)c;
+    if (A.cls_nhwc[l]) {   // [B, H, W, na*C]: element e of the image's block is flat index off_l * C + e (bench.py:37)
+        k.fbase = (unsigned)A.g.off[l] * (unsigned)A.C;
+        k.fstride = 1u;
+    } else {
+        const int a = (int)fd_div((unsigned)ch, A.div_C), c = ch - a * A.C;
+        k.fbase = (unsigned)(A.g.off[l] + a) * (unsigned)A.C + (unsigned)c;
+        k.fstride = (unsigned)A.planes;
+    }
     return k;
 }
 
@@ -303,6 +313,8 @@ __device__ __forceinline__ float4 gather_box(const TopkArgs &A, int b, int ancho
     const int l = geo_level(g, anchor);
     const int loc = anchor - g.off[l];
     const int sp = loc / g.na, a = loc - sp * g.na;
+    if (A.box_nhwc[l])   // [B, H, W, na*4]: the four codes of (position, shape) are one aligned 16-byte load
+        return __ldg(reinterpret_cast<const float4 *>(A.box[l] + ((size_t)b * g.hw[l] + sp) * (size_t)(g.na * 4)) + a);
     const float *bp = A.box[l] + ((size_t)(b * g.na + a) * 4) * g.hw[l] + sp;
     float4 r;
     r.x = __ldg(bp); r.y = __ldg(bp + g.hw[l]); r.z = __ldg(bp + 2 * (size_t)g.hw[l]); r.w = __ldg(bp + 3 * (size_t)g.hw[l]);

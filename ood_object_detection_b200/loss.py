@@ -52,8 +52,15 @@ class _DetectionLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, *outputs):
         n = meta['levels']
-        cls_out = [_as_f32c(t) for t in outputs[:n]]
-        box_out = [_as_f32c(t) for t in outputs[n:2 * n]]
+        layout = 0
+        if meta.get('label_batch') is not None:
+            # fused targets: channels_last head outputs (AMP / channels_last models) are read in place
+            cls_out, cmask = _lib.prep_levels(outputs[:n], n, 'loss input')
+            box_out, bmask = _lib.prep_levels(outputs[n:2 * n], n, 'loss input')
+            layout = cmask | (bmask << 8)
+        else:   # targets given as tensors (the reference's layout): the plane-walking kernel, NCHW only
+            cls_out = [_as_f32c(t) for t in outputs[:n]]
+            box_out = [_as_f32c(t) for t in outputs[n:2 * n]]
         dev = cls_out[0].device
         lib = _lib.lib()
         need_grad = any(ctx.needs_input_grad[1:])
@@ -85,7 +92,7 @@ class _DetectionLossFn(torch.autograd.Function):
         clear = use_keys and fused.transient and fused.workspace is not None
         exchange = meta.get('exchange')   # distributed.PeerMailbox.attach(...) descriptor, or None
         params = _lib.LossParams(meta['alpha'], meta['gamma'], meta['delta'], meta['box_loss_weight'],
-                                 meta['label_smoothing'], int(bool(meta['legacy_focal'])), int(use_keys), int(clear),
+                                 meta['label_smoothing'], int(bool(meta['legacy_focal'])), int(use_keys), int(clear), layout,
                                  _lib.ctypes.pointer(exchange) if exchange is not None else None)
         if fused is not None:
             match = fused.keys if use_keys else fused.match

@@ -15,11 +15,7 @@ def ood_scores(cls_outputs, anchor_idx, num_levels, num_classes, temperature: fl
     """cls_outputs: per-level NCHW logits; anchor_idx [B, D] int64 (negative = padding -> 0).
     Returns (energy [B, D], max_logit [B, D]) fp32."""
     lib = _lib.lib()
-    levels = []
-    for t in cls_outputs[:num_levels]:
-        _lib.require_cuda(t, 'class output')
-        t = t.float() if t.dtype != torch.float32 else t
-        levels.append(t if t.is_contiguous() else t.contiguous())
+    levels, layout = _lib.prep_levels(cls_outputs, num_levels, 'class output')   # channels_last is read in place
     dev = levels[0].device
     B = levels[0].shape[0]
     na = levels[0].shape[1] // int(num_classes)
@@ -29,7 +25,7 @@ def ood_scores(cls_outputs, anchor_idx, num_levels, num_classes, temperature: fl
     max_logit = torch.empty((B, D), dtype=torch.float32, device=dev)
     hw = [c.shape[2] * c.shape[3] for c in levels]
     with torch.cuda.device(dev):
-        _lib.check(lib.odk_ood(_lib.ptr_array(levels), B, int(num_classes), _lib.int_array(hw), num_levels, na,
+        _lib.check(lib.odk_ood(_lib.ptr_array(levels), B, int(num_classes), _lib.int_array(hw), num_levels, na, layout,
                                _lib.ptr(anchor_idx), D, float(temperature), _lib.ptr(energy), _lib.ptr(max_logit),
                                _lib.stream_ptr(dev)))
     return energy, max_logit

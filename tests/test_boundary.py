@@ -50,7 +50,7 @@ def test_abi_argument_errors_without_gpu():
     assert lib.odk_postprocess_workspace_bytes(0, 90, hw5, 5, 9, 5000) == 0
     # odk_postprocess validates sizes before any CUDA call
     args = [None] * 26
-    rc = lib.odk_postprocess(None, None, 1, 90, hw5, 5, 9, 5000, None, None, None, None, 1.0, None, None, None, None, None, None,
+    rc = lib.odk_postprocess(None, None, 1, 90, hw5, 5, 9, 5000, 0, None, None, None, None, 1.0, None, None, None, None, None, None,
                              None, None, None, None, None, 0, None)
     assert rc == -1 and b'null pointer' in lib.odk_last_error()
     assert lib.odk_assign_workspace_bytes(4, 100) >= 4 * 100 * 8

@@ -269,3 +269,43 @@ def test_loss_requires_cuda():
     with pytest.raises(RuntimeError):
         loss_fn(x, [torch.zeros(1, 36, 4, 4)], [torch.zeros(1, 4, 4, 9, dtype=torch.long)], [torch.zeros(1, 4, 4, 36)],
                 torch.ones(1), 1, 0.25, 1.5, 0.1, 50.0)
+
+
+@pytest.mark.parametrize('legacy,sm', [(False, 0.0), (False, 0.1), (True, 0.0)])
+def test_loss_channels_last_inputs_in_place(legacy, sm):
+    """channels_last head outputs ([B, H, W, C] in memory) go through the fused labeler + loss
+    without a layout copy (layout-agnostic stream + per-anchor patch kernels): same losses and gradients as the
+    NCHW path and the oracle, gradients returned in the inputs' own memory format; mixed layouts per level too
+    (D3: odd 7x7 level)."""
+    from ood_object_detection_b200.loss import loss_fn_fused
+    size, scale = synth.MODEL_SHAPES['d3']
+    B, C, m = 2, 90, 12
+    anc, lab = make_labeler(size, scale, C)
+    gb, gc = synth.gt_boxes(501, B, size, m, C)
+    co_np, bo_np = synth.head_outputs(502, B, size, C, tie_free=False)
+    kw = dict(num_classes=C, alpha=0.25, gamma=1.5, delta=0.1, box_loss_weight=50.0, label_smoothing=sm, legacy_focal=legacy)
+    oc, ob, onp, _, _ = orc.batch_label_anchors(anc.boxes.cpu().numpy(), list(gb), list(gc))
+    fhw = synth.feat_hw(size)
+    ref = orc.loss_fn(co_np, bo_np, orc.split_levels(oc, fhw), orc.split_levels(ob, fhw), onp, C, 0.25, 1.5, 0.1, 50.0, sm, legacy, want_grad=True)
+    n = float(np.sum(onp, dtype=np.float32)) + 1.0
+    w_cls = 0.75 / n * (2.5 if legacy else 1.0)
+    for pattern in ('all', 'mixed'):
+        def fmt(x, l, which):
+            cl = pattern == 'all' or (l + which) % 2 == 0
+            tt = t(x)
+            return (tt.contiguous(memory_format=torch.channels_last) if cl else tt).requires_grad_(True)
+        co = [fmt(x, l, 0) for l, x in enumerate(co_np)]
+        bo = [fmt(x, l, 1) for l, x in enumerate(bo_np)]
+        ptrs = [x.data_ptr() for x in co]
+        lb = lab.assign(torch.from_numpy(gb).to(dev()), torch.from_numpy(gc).to(dev()), transient=True)
+        tot, cl_, bl_ = loss_fn_fused(co, bo, lb, **kw)
+        np.testing.assert_allclose([tot.item(), cl_.item(), bl_.item()], ref[:3], rtol=RTOL)
+        tot.backward()
+        assert [x.data_ptr() for x in co] == ptrs
+        for l in range(5):
+            assert co[l].grad.stride() == co[l].stride() and bo[l].grad.stride() == bo[l].stride()
+            assert_grad_close(co[l].grad.cpu().numpy(), ref[3][l], w_cls, what=f'{pattern}: class grad level {l}')
+            assert_grad_close(bo[l].grad.cpu().numpy(), ref[4][l], 50.0 / (4.0 * n), what=f'{pattern}: box grad level {l}')
+    # the labeler's workspace came back zeroed from the transient batch: the next assignment is right without a memset
+    lb2 = lab.assign(torch.from_numpy(gb).to(dev()), torch.from_numpy(gc).to(dev()))
+    np.testing.assert_array_equal(lb2.num_positives.cpu().numpy(), onp)

@@ -338,3 +338,31 @@ def test_fused_postprocess_above_register_budget_uses_chain():
     anc = anchors_t(size)
     out = post_process_detect([t(x) for x in co], [t(x) for x in bo], anc, 5, C, FUSED_MAX_K + 1000, 100, False)
     assert out['detections'].shape == (B, 100, 6) and int(out['count'].min()) > 0
+
+
+@pytest.mark.parametrize('pipeline', PIPELINES)
+def test_channels_last_head_outputs_are_read_in_place(pipeline):
+    """head outputs in channels_last memory format ([B, H, W, C] in memory, what an AMP /
+    channels_last head writes, efficientdet.py:405-414) go through _post_process, odk_postprocess and the OOD
+    scores WITHOUT a layout copy and give bit-identical results; mixed layouts per level too (D3: its 7x7 level
+    has an odd plane size)."""
+    from ood_object_detection_b200 import _lib
+    from ood_object_detection_b200.bench import _post_process, post_process_detect
+    size, B, C, K, D = 896, 2, 90, 5000, 100
+    co, bo = synth.planted_outputs(350, B, size, C)
+    anc = anchors_t(size)
+    tc, tb = [t(x) for x in co], [t(x) for x in bo]
+    cl = [x.contiguous(memory_format=torch.channels_last) for x in tc]
+    bl = [x.contiguous(memory_format=torch.channels_last) for x in tb]
+    assert _lib.prep_levels(cl, 5)[1] == 0b11111 and all(a.data_ptr() == b_.data_ptr() for a, b_ in zip(_lib.prep_levels(cl, 5)[0], cl))
+    ref = _post_process(tc, tb, 5, C, K)
+    for cls_in, box_in in ((cl, bl), (cl, tb), ([cl[0], tc[1], cl[2], tc[3], cl[4]], [tb[0], bl[1], tb[2], bl[3], tb[4]])):
+        got = _post_process(cls_in, box_in, 5, C, K)
+        for r, g_ in zip(ref, got):
+            assert torch.equal(r, g_)
+    for soft in (False, True):
+        want = post_process_detect(tc, tb, anc, 5, C, K, D, soft, with_ood=True, pipeline=pipeline)
+        got = post_process_detect(cl, bl, anc, 5, C, K, D, soft, with_ood=True, pipeline=pipeline)
+        for key in ('detections', 'count', 'src', 'anchor', 'max_logit'):
+            assert torch.equal(want[key], got[key]), key
+        np.testing.assert_allclose(got['energy'].cpu().numpy(), want['energy'].cpu().numpy(), rtol=1e-6)
