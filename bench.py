@@ -287,7 +287,7 @@ class TrainWorkload:
         return (f'{model.upper()}-{size} A={synth.num_anchors(size)} C={NUM_CLASSES} B={B}/GPU M={M}: AnchorLabeler + fused '
                 f'focal/huber loss, forward + gradient')
 
-    def __init__(self, ctx, model, batch, num_gt, seed=1):
+    def __init__(self, ctx, model, batch, num_gt, seed=1, channels_last=False):
         import synth
         from ood_object_detection_b200.anchors import Anchors, AnchorLabeler
         torch = ctx.torch
@@ -297,6 +297,9 @@ class TrainWorkload:
         self.anchors = Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size)).to(ctx.dev)
         self.labeler = AnchorLabeler(self.anchors, NUM_CLASSES, match_threshold=0.5)
         self.cls, self.box = device_outputs(torch, ctx.dev, seed + ctx.rank, batch, size, NUM_CLASSES)
+        if channels_last:   # what a channels_last / AMP head writes: [B, H, W, C] in memory, read in place by the kernels
+            self.cls = [t.contiguous(memory_format=torch.channels_last) for t in self.cls]
+            self.box = [t.contiguous(memory_format=torch.channels_last) for t in self.box]
         for t in self.cls + self.box:
             t.requires_grad_(True)
         gb, gc_ = synth.gt_boxes(100 + seed + ctx.rank, batch, size, num_gt, NUM_CLASSES)
@@ -439,7 +442,7 @@ class TrainWorkload:
 class PostWorkload:
     """DetBenchPredict's post-process: top-k -> decode -> NMS / soft-NMS (-> OOD scores) for B images per rank."""
 
-    def __init__(self, ctx, model, batch_global, soft, ood, seed=3):
+    def __init__(self, ctx, model, batch_global, soft, ood, seed=3, channels_last=False):
         import synth
         from ood_object_detection_b200.anchors import Anchors
         from ood_object_detection_b200.distributed import shard_range
@@ -450,6 +453,9 @@ class PostWorkload:
         size, scale = synth.MODEL_SHAPES[model]
         self.anchors = Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size)).to(ctx.dev)
         self.cls, self.box = device_outputs(torch, ctx.dev, seed + ctx.rank, self.B, size, NUM_CLASSES)
+        if channels_last:
+            self.cls = [t.contiguous(memory_format=torch.channels_last) for t in self.cls]
+            self.box = [t.contiguous(memory_format=torch.channels_last) for t in self.box]
         self.A = self.anchors.boxes.shape[0]
         self.bytes = self.B * self.A * 4 * NUM_CLASSES               # A*4C bytes per image
         self.size = size
@@ -579,6 +585,12 @@ def record_post(ctx, model, batch, soft, ood, steps, warmup, with_cpu, pipelines
             ms2, _, _ = w.measure(steps, warmup, p)
             rec[f'pipeline_{p}'] = {'ms_per_step': ms2, 'images_per_s': batch / (ms2 * 1e-3), 'frac_of_peak': w.bytes / (ms2 * 1e-3) / 1e9 / ctx.peak}
         rec['e2e'] = w.e2e(max(2, min(steps, 5)))
+        del w
+        gc.collect()
+        ctx.torch.cuda.empty_cache()
+        w = PostWorkload(ctx, model, batch, soft, ood, channels_last=True)
+        ms3, _, _ = w.measure(steps, warmup, pipelines[0])
+        rec['channels_last'] = {'ms_per_step': ms3, 'images_per_s': batch / (ms3 * 1e-3), 'frac_of_peak': w.bytes / (ms3 * 1e-3) / 1e9 / ctx.peak}
     del w
     gc.collect()
     ctx.torch.cuda.empty_cache()
@@ -688,6 +700,19 @@ def run_ours(args):
     head.graph = None
     e2e = head.e2e(max(2, min(args.steps, 10)))
     bytes_fwd, workload, exchange = head.bytes_fwd, TrainWorkload.describe('d0', 64, 10), head.exchange
+    channels_last = None
+    if world == 1 and not args.only:   # the same step on channels_last head outputs (read in place, no layout copy)
+        del head
+        gc.collect()
+        torch.cuda.empty_cache()
+        head = TrainWorkload(ctx, 'd0', 64, 10, channels_last=True)
+        ms_cl, _ = head.measure(max(5, min(args.steps, 20)), args.warmup, grad=True)
+        ms_cl_fwd, _ = head.measure(max(5, min(args.steps, 20)), args.warmup, grad=False)
+        channels_last = {'ms_per_step': ms_cl, 'images_per_s': 64 / (ms_cl * 1e-3), 'frac_of_peak': 2 * bytes_fwd / (ms_cl * 1e-3) / 1e9 / ctx.peak,
+                         'forward_only_ms_per_step': ms_cl_fwd, 'forward_only_frac_of_peak': bytes_fwd / (ms_cl_fwd * 1e-3) / 1e9 / ctx.peak,
+                         'kernels': 'odk::loss_flat_kernel + odk::loss_patch_kernel (layout-agnostic stream + per-anchor patch)'}
+        head.drop_grads()
+        head.graph = None
     if world > 1:   # graphs / mailboxes that hold peer mappings go before the other workloads allocate
         torch.cuda.synchronize()
     del head
@@ -737,6 +762,7 @@ def run_ours(args):
             'clocks': clocks,
             'forward_only': {'ms_per_step': ms_fwd, 'images_per_s': world * 64 / (ms_fwd * 1e-3),
                              'frac_of_peak': bytes_fwd / (ms_fwd * 1e-3) / 1e9 / ctx.peak},
+            'channels_last': channels_last,
             'workloads': workloads,
         }
         print(json.dumps(line), flush=True)
