@@ -138,11 +138,13 @@ __global__ void __launch_bounds__(kDetThreads) detect_kernel(const __grid_consta
         }
         __syncthreads();
         // 5. suppression, first D survivors
-        if (A.p.soft_nms)
-            // the window needs non-increasing scores: true for top-k output (checked below for API inputs)
-            kept_n = soft_nms_rounds(S, n, true, A.p.soft_sigma, A.p.soft_iou, A.p.soft_score_thr, D, s_kept,
-                                     s_unsorted ? n : kDetFirstWindow, s_unsorted ? n : kDetThreads, s_unsorted ? kDetWarps : kSoftGroup,
+        if (A.p.soft_nms && s_unsorted)
+            kept_n = soft_nms_rounds(S, n, true, A.p.soft_sigma, A.p.soft_iou, A.p.soft_score_thr, D, s_kept, n, n, kDetWarps,
                                      [&](int q, int i, float sc) { s_keptscore[q] = sc; });
+        else if (A.p.soft_nms)
+            // the lazy window and the batches need non-increasing scores: true for top-k output (checked above for API inputs)
+            kept_n = soft_nms_batched(S, n, true, A.p.soft_sigma, A.p.soft_iou, A.p.soft_score_thr, D, s_kept,
+                                      kDetFirstWindow, kDetThreads, [&](int q, int i, float sc) { s_keptscore[q] = sc; });
         else
             kept_n = hard_nms_rounds(S, n, A.nms_thr_f, D, s_kept, reinterpret_cast<unsigned *>(s_raw + (size_t)A.cap * 24 + (size_t)(A.cap / 32) * 4 + 16));
         __syncthreads();

@@ -336,6 +336,293 @@ static __device__ int soft_nms_rounds(const DetSmem &S, int n, bool gaussian, fl
     return s_rounds;
 }
 
+// Batched Soft-NMS rounds for candidates in NON-INCREASING score order (the top-k output) -- same results as
+// soft_nms_rounds, bit for bit, with far fewer block-wide steps.  A round of the reference is a dependent chain
+// (arg-max -> IoU of everything alive with the pick -> decay -> next arg-max; ~0.5 us as a block-wide step), and
+// a picture needs max_rounds of them.  Here the kSoftBatch best alive candidates (the LEADERS) are taken out
+// together: their pairwise decay factors are computed at once, and one warp then replays the reference's rounds
+// among them in registers.  A pick is the global arg-max as long as its key beats the BOUND = the best key
+// outside the leader set when the batch was formed (those scores only decay) and the original score of the
+// first un-activated candidate of the lazy window; the batch stops at the first pick that does not.  Leaders
+// that no earlier leader touches keep their order, so that prefix is picked in ONE step; the rest goes one pick
+// at a time (arg-max by REDUX, decay = one multiply by a table entry).  The picks of the batch are then applied,
+// in pick order, to every other alive candidate in parallel -- the same fp32 multiplies in the same order as
+// the one-pick-at-a-time loop.  Dead candidates carry score -inf (no alive words here).
+//
+// Forming a batch must not cost O(prefix^2): a value t that at least kSoftBatch+1 candidates reach is taken from
+// the maxima of ~64-128 small groups of the prefix (their (kSoftBatch+1)-th largest), the candidates >= t are
+// compacted (a few dozen) and only those are ranked against each other.  If more than kSoftCompact reach t
+// (massive ties) the whole prefix is ranked instead.
+//
+// A batch is a handful of short phases (profiles/micro/barrier_micro.cu: ~450-600 cycles each even when trivial --
+// dependent LDS / SHFL / ALU latencies, not the barrier, which is 78 cycles for 1024 threads).  The phases can
+// be confined to the first G warps (named barrier; the others sleep at the block barrier that closes the batch
+// and pick the outcome up from shared memory).  Measured on D3 B=32: G = 8 for short prefixes is slightly SLOWER
+// than all 32 warps (dense 29-31 us vs 25-28 us per image, the pair table and the apply step have real work),
+// so kSoftSmallPrefix is 0 and the knob stays only for re-measurement.
+constexpr int kSoftBatch = 32;
+constexpr int kSoftCompact = 256;
+#ifndef ODK_SOFT_SMALL_PREFIX
+#define ODK_SOFT_SMALL_PREFIX 0
+#endif
+constexpr int kSoftSmallPrefix = ODK_SOFT_SMALL_PREFIX;   // prefixes up to this long are worked by kSoftSmallGroup warps
+constexpr int kSoftSmallGroup = 8;
+
+template <class Emit>
+static __device__ int soft_nms_batched(const DetSmem &S, int n, bool gaussian, float sigma, float iou_thr, float score_thr,
+                                       int max_rounds, int *picked, int window, int window_max, Emit emit) {
+    __shared__ int s_lead[kSoftBatch];                    // candidate index by rank among the alive
+    __shared__ float s_dec[kSoftBatch][kSoftBatch + 1];   // [a][b]: factor on leader b when leader a is picked
+    __shared__ unsigned s_touch[kSoftBatch];              // row a: bit b = leader a decays the LATER leader b
+    __shared__ __align__(16) float4 s_pbox[kSoftBatch];   // the batch's picks in order
+    __shared__ float s_parea[kSoftBatch];
+    __shared__ unsigned s_leadmask[kDetMaxN / 32];
+    __shared__ __align__(16) float s_val[kSoftCompact];   // group maxima, then the compacted scores
+    __shared__ int s_cidx[kSoftCompact];
+    __shared__ unsigned long long s_bound;
+    __shared__ float s_t;
+    __shared__ int s_m;
+    __shared__ int s_state[2], s_np[2];                   // per batch parity: 0 picks made, 1 window widened, 2 nothing alive
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int sig_e;
+    const bool sig_pow2 = frexpf(sigma, &sig_e) == 0.5f;
+    const float sig_inv = 1.0f / sigma;
+    auto overlap = [](float4 p, float4 q) { return (fminf(p.z, q.z) > fmaxf(p.x, q.x)) && (fminf(p.w, q.w) > fmaxf(p.y, q.y)); };
+    auto decay_of = [&](float4 p, float ap, float4 q) {
+        if (!overlap(p, q)) return 1.0f;                                      // disjoint extents -> iou 0 -> decay exactly 1
+        const float iou = iou_soft(p, ap, q);
+        if (gaussian) {                                                       // soft_nms.py:96
+            const float sq = -__fmul_rn(iou, iou);
+            return expf(sig_pow2 ? __fmul_rn(sq, sig_inv) : __fdiv_rn(sq, sigma));
+        }
+        return iou > iou_thr ? __fsub_rn(1.0f, iou) : 1.0f;                   // :98-100
+    };
+    auto area_of = [](float4 p) { return __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y)); };
+    auto key_of = [](float sc, int i) {   // order-preserving, never 0 for a finite score
+        const unsigned u = __float_as_uint(sc);
+        const unsigned vk = u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
+        return ((unsigned long long)vk << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+    };
+    auto before = [](float sj, int j, float si, int i) { return sj > si || (sj == si && j < i); };
+    int limit = min(n, window);
+    int count = 0, parity = 0;
+    // the whole-prefix ranking reads the scores four at a time: pad the last group
+    if (tid < 4 && n + tid < ((n + 3) & ~3)) S.score[n + tid] = -INFINITY;
+    __syncthreads();
+    while (count < max_rounds) {
+        const int G = limit <= kSoftSmallPrefix ? kSoftSmallGroup : kDetWarps;
+        if (warp < G) {
+            const int nthr = G * 32;
+            const int nwords = (limit + 31) / 32;
+            // A. the kSoftBatch + 1 best alive candidates of the prefix
+            if (tid < kSoftBatch) s_lead[tid] = -1;
+            for (int w = tid; w < nwords; w += nthr) s_leadmask[w] = 0u;
+            if (tid == 0) { s_bound = 0ull; s_m = 0; s_t = -INFINITY; }
+            // A1. maxima of groups of gs consecutive candidates (at most kSoftCompact groups)
+            int gs = 4;
+            while (gs < 32 && limit > gs * (kSoftCompact / 2)) gs <<= 1;
+            const int ngr = (limit + gs - 1) / gs;
+            for (int i0 = 0; i0 < limit; i0 += nthr) {
+                const int i = i0 + tid;
+                float v = i < limit ? S.score[i] : -INFINITY;
+                for (int o = 1; o < gs; o <<= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                if (i < limit && (lane & (gs - 1)) == 0) s_val[i / gs] = v;
+            }
+            group_sync(G);
+            // A2. t = the (kSoftBatch+1)-th largest group maximum (4 threads share a group)
+            if (ngr > kSoftBatch) {
+                for (int g0 = 0; g0 < ngr; g0 += nthr / 4) {
+                    const int g = g0 + (tid >> 2), part = tid & 3;
+                    const bool has = g < ngr;
+                    const float vg = has ? s_val[g] : 0.f;
+                    int r = 0;
+                    if (has)
+                        for (int h = part; h < ngr; h += 4) r += before(s_val[h], h, vg, g);
+                    r += __shfl_xor_sync(0xffffffffu, r, 1);
+                    r += __shfl_xor_sync(0xffffffffu, r, 2);
+                    if (has && part == 0 && r == kSoftBatch) s_t = vg;
+                }
+            }
+            group_sync(G);
+            // A3. compact the alive candidates that reach t
+            const float t = s_t;
+            for (int i0 = 0; i0 < limit; i0 += nthr) {
+                const int i = i0 + tid;
+                const float v = i < limit ? S.score[i] : -INFINITY;
+                const bool in = v > -INFINITY && v >= t;
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                int base = 0;
+                if (lane == 0 && bal) base = atomicAdd(&s_m, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int pos = base + __popc(bal & ((1u << lane) - 1u));
+                if (in && pos < kSoftCompact) { s_val[pos] = v; s_cidx[pos] = i; }
+            }
+            group_sync(G);
+            const int m = s_m;
+            if (m <= kSoftCompact) {
+                // A4. rank the compacted candidates among themselves (4 threads share one)
+                for (int a0 = 0; a0 < m; a0 += nthr / 4) {
+                    const int a = a0 + (tid >> 2), part = tid & 3;
+                    const bool has = a < m;
+                    const float sa = has ? s_val[a] : 0.f;
+                    const int ia = has ? s_cidx[a] : 0;
+                    int r = 0;
+                    if (has)
+                        for (int h = part; h < m; h += 4) r += before(s_val[h], s_cidx[h], sa, ia);
+                    r += __shfl_xor_sync(0xffffffffu, r, 1);
+                    r += __shfl_xor_sync(0xffffffffu, r, 2);
+                    if (has && part == 0) {
+                        if (r < kSoftBatch) { s_lead[r] = ia; atomicOr(&s_leadmask[ia >> 5], 1u << (ia & 31)); }
+                        else if (r == kSoftBatch) s_bound = key_of(sa, ia);
+                    }
+                }
+            } else {
+                // A4'. massive ties: rank the whole prefix (4 threads share a candidate, scores read four at a time)
+                const int ngroups = (limit + 3) >> 2;
+                for (int c0 = 0; c0 < limit; c0 += nthr / 4) {
+                    const int i = c0 + (tid >> 2), part = tid & 3;
+                    const float si = i < limit ? S.score[i] : -INFINITY;
+                    const bool live = si > -INFINITY;
+                    int r = 0;
+                    if (__any_sync(0xffffffffu, live)) {
+                        const float4 *sc4 = reinterpret_cast<const float4 *>(S.score);
+                        for (int g = part; g < ngroups; g += 4) {
+                            const float4 v = sc4[g];
+                            const int j = g * 4;
+                            r += before(v.x, j, si, i) + before(v.y, j + 1, si, i) + before(v.z, j + 2, si, i) + before(v.w, j + 3, si, i);
+                        }
+                    }
+                    r += __shfl_xor_sync(0xffffffffu, r, 1);
+                    r += __shfl_xor_sync(0xffffffffu, r, 2);
+                    if (live && part == 0) {
+                        if (r < kSoftBatch) { s_lead[r] = i; atomicOr(&s_leadmask[i >> 5], 1u << (i & 31)); }
+                        else if (r == kSoftBatch) s_bound = key_of(si, i);
+                    }
+                }
+            }
+            group_sync(G);
+            // B. the bound; widen the lazy window when the best leader does not beat the un-activated candidates
+            unsigned long long bound = s_bound;
+            const int lead0 = s_lead[0];
+            bool widen = false;
+            if (limit < n) {
+                const unsigned long long bk = key_of(S.score[limit], limit);
+                bound = bk > bound ? bk : bound;
+                widen = lead0 < 0 || !(key_of(S.score[lead0], lead0) > bk);
+            }
+            if (widen) {
+                const int new_limit = min(n, limit + min(2 * window, window_max));
+                for (int i = limit + tid; i < new_limit; i += nthr) {
+                    const float4 q = S.box[i];
+                    float sc = S.score[i];
+                    bool ok = true;
+                    for (int c = 0; c < count && ok; ++c) {
+                        const float4 p = S.box[picked[c]];
+                        const float d = decay_of(p, area_of(p), q);
+                        if (d != 1.0f) sc = __fmul_rn(sc, d);
+                        ok = sc > score_thr;
+                    }
+                    S.score[i] = ok ? sc : -INFINITY;
+                }
+                if (tid == 0) s_state[parity] = 1;
+            } else if (lead0 < 0) {
+                if (tid == 0) s_state[parity] = 2;
+            } else {
+                // C. pairwise decay factors of the leaders; row masks of who touches a later leader
+                for (int ra = warp; ra < kSoftBatch; ra += G) {
+                    const int a = s_lead[ra], b = s_lead[lane];
+                    float d = 1.0f;
+                    if (a >= 0 && b >= 0 && a != b) {
+                        const float4 p = S.box[a];
+                        d = decay_of(p, area_of(p), S.box[b]);
+                        s_dec[ra][lane] = d;
+                    }
+                    const unsigned touch = __ballot_sync(0xffffffffu, d != 1.0f && lane > ra);
+                    if (lane == 0) s_touch[ra] = touch;
+                }
+                group_sync(G);
+                // D. one warp replays the rounds among the leaders
+                if (warp == 0) {
+                    const int idx = s_lead[lane];
+                    float cur = idx >= 0 ? S.score[idx] : 0.f;
+                    const float4 mybox = idx >= 0 ? S.box[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    bool live = idx >= 0;
+                    const unsigned my_touch = s_touch[lane];
+                    // leaders before the first touched one keep their (descending) order: picked in one step
+                    const unsigned touched = __reduce_or_sync(0xffffffffu, my_touch);
+                    const unsigned stop = __ballot_sync(0xffffffffu, !live || !(key_of(cur, idx) > bound)) | touched;
+                    int np = min(stop ? __ffs(stop) - 1 : 32, max_rounds - count);
+                    if (lane < np) {
+                        emit(count + lane, idx, cur);
+                        picked[count + lane] = idx;
+                        s_pbox[lane] = mybox;
+                        s_parea[lane] = area_of(mybox);
+                        live = false;
+                    }
+                    for (int a = 0; a < np; ++a) {
+                        const unsigned row = __shfl_sync(0xffffffffu, my_touch, a);
+                        if (live && ((row >> lane) & 1u)) cur = __fmul_rn(cur, s_dec[a][lane]);
+                    }
+                    if (live && np > 0) live = cur > score_thr;               // :103-104
+                    // the others, one pick at a time
+                    while (count + np < max_rounds) {
+                        const unsigned long long key = live ? key_of(cur, idx) : 0ull;
+                        const unsigned long long pk = warp_max_u64(key);
+                        if (pk == 0ull || !(pk > bound)) break;
+                        const int p = __ffs(__ballot_sync(0xffffffffu, key == pk)) - 1;
+                        if (lane == p) {
+                            emit(count + np, idx, cur);
+                            picked[count + np] = idx;
+                            s_pbox[np] = mybox;
+                            s_parea[np] = area_of(mybox);
+                            live = false;
+                        } else if (live) {
+                            const float d = s_dec[p][lane];
+                            if (d != 1.0f) cur = __fmul_rn(cur, d);
+                            live = cur > score_thr;
+                        }
+                        ++np;
+                    }
+                    if (idx >= 0) S.score[idx] = live ? cur : -INFINITY;
+                    if (lane == 0) { s_np[parity] = np; s_state[parity] = 0; }
+                }
+                group_sync(G);
+                // E. the batch's picks, in order, on every other alive candidate of the prefix
+                const int np = s_np[parity];
+                if (count + np < max_rounds) {
+                    for (int i = tid; i < limit; i += nthr) {
+                        if ((s_leadmask[i >> 5] >> (i & 31)) & 1u) continue;
+                        float sc = S.score[i];
+                        if (!(sc > -INFINITY)) continue;
+                        const float4 q = S.box[i];
+                        bool ok = true, changed = false;
+                        for (int c = 0; c < np && ok; ++c) {
+                            const float4 p = s_pbox[c];
+                            if (!overlap(p, q)) continue;
+                            const float d = decay_of(p, s_parea[c], q);
+                            if (d != 1.0f) { sc = __fmul_rn(sc, d); ok = sc > score_thr; changed = true; }
+                        }
+                        ok = ok && sc > score_thr;
+                        if (changed || !ok) S.score[i] = ok ? sc : -INFINITY;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int state = s_state[parity];
+        parity ^= 1;
+        if (state == 2) break;
+        if (state == 1) {
+            window = min(2 * window, window_max);
+            limit = min(n, limit + window);
+            continue;
+        }
+        count += s_np[parity ^ 1];
+    }
+    __syncthreads();
+    return count;
+}
+
 // OOD scores of one anchor by one warp: energy = -T * logsumexp(row / T), max_logit = max(row) over the C raw
 // class logits of the anchor, read in place from the NCHW level (stride hw between classes).
 __device__ __forceinline__ void ood_row(const Geo &g, const float *const *levels, const unsigned char *nhwc, int b, int C, long long anc,

@@ -279,8 +279,8 @@ static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned lo
         DetSmem S;
         S.box = sbox; S.score = sscore; S.src = nullptr; S.alive = alive;
         if (P.p.soft_nms)
-            kept_n = soft_nms_rounds(S, n, true, P.p.soft_sigma, P.p.soft_iou, P.p.soft_score_thr, D, s_kept,
-                                     kDetFirstWindow, kDetThreads, kSoftGroup, [&](int q, int i, float s) { s_keptscore[q] = s; });
+            kept_n = soft_nms_batched(S, n, true, P.p.soft_sigma, P.p.soft_iou, P.p.soft_score_thr, D, s_kept,
+                                      kDetFirstWindow, kDetThreads, [&](int q, int i, float s) { s_keptscore[q] = s; });
         else
             kept_n = hard_nms_rounds(S, n, P.nms_thr_f, D, s_kept, alive + cap / 32 + 4);
         __syncthreads();
