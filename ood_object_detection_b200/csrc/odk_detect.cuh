@@ -369,7 +369,7 @@ constexpr int kSoftSmallPrefix = ODK_SOFT_SMALL_PREFIX;   // prefixes up to this
 constexpr int kSoftSmallGroup = 8;
 
 template <class Emit>
-static __device__ int soft_nms_batched(const DetSmem &S, int n, bool gaussian, float sigma, float iou_thr, float score_thr,
+static __device__ __noinline__ int soft_nms_batched(const DetSmem &S, int n, bool gaussian, float sigma, float iou_thr, float score_thr,
                                        int max_rounds, int *picked, int window, int window_max, Emit emit) {
     __shared__ int s_lead[kSoftBatch];                    // candidate index by rank among the alive
     __shared__ float s_dec[kSoftBatch][kSoftBatch + 1];   // [a][b]: factor on leader b when leader a is picked
@@ -625,23 +625,55 @@ static __device__ int soft_nms_batched(const DetSmem &S, int n, bool gaussian, f
 
 // OOD scores of one anchor by one warp: energy = -T * logsumexp(row / T), max_logit = max(row) over the C raw
 // class logits of the anchor, read in place from the NCHW level (stride hw between classes).
-__device__ __forceinline__ void ood_row(const Geo &g, const float *const *levels, const unsigned char *nhwc, int b, int C, long long anc,
-                                        float T, int lane, float &e, float &m) {
-    e = 0.f; m = 0.f;
-    if (anc < 0 || anc >= g.A) return;
+struct OodRow { const float *row; size_t cstride; };
+__device__ __forceinline__ OodRow ood_row_of(const Geo &g, const float *const *levels, const unsigned char *nhwc, int b, int C, long long anc) {
+    OodRow r;
+    r.row = nullptr; r.cstride = 0;
+    if (anc < 0 || anc >= g.A) return r;
     const int l = geo_level(g, (int)anc);
     const int loc = (int)anc - g.off[l];
     const int sp = loc / g.na, a = loc - sp * g.na;
     // NCHW: the row's classes are hw apart; channels_last: they are contiguous
-    const size_t cstride = nhwc[l] ? 1 : (size_t)g.hw[l];
-    const float *row = nhwc[l] ? levels[l] + ((size_t)b * g.hw[l] + sp) * (size_t)(g.na * C) + (size_t)a * C
-                               : levels[l] + ((size_t)(b * g.na + a) * C) * g.hw[l] + sp;
+    r.cstride = nhwc[l] ? 1 : (size_t)g.hw[l];
+    r.row = nhwc[l] ? levels[l] + ((size_t)b * g.hw[l] + sp) * (size_t)(g.na * C) + (size_t)a * C
+                    : levels[l] + ((size_t)(b * g.na + a) * C) * g.hw[l] + sp;
+    return r;
+}
+// energy / max-logit from the values a lane holds (class c = lane + 32 * k); same operation order as the two-pass loop
+template <int NV>
+__device__ __forceinline__ void ood_reduce(const float (&v)[NV], int C, float T, int lane, float &e, float &m) {
     float mx = -INFINITY;
-    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, __ldg(row + (size_t)c * cstride));
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+        if (lane + 32 * k < C) mx = fmaxf(mx, v[k]);
     mx = warp_max(mx);
     float s = 0.f;
     const float invT = 1.0f / T;
-    for (int c = lane; c < C; c += 32) s += expf((__ldg(row + (size_t)c * cstride) - mx) * invT);
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+        if (lane + 32 * k < C) s += expf((v[k] - mx) * invT);
+    s = warp_sum(s);
+    e = -T * (mx * invT + logf(s));
+    m = mx;
+}
+__device__ __forceinline__ void ood_row(const Geo &g, const float *const *levels, const unsigned char *nhwc, int b, int C, long long anc,
+                                        float T, int lane, float &e, float &m) {
+    e = 0.f; m = 0.f;
+    const OodRow r = ood_row_of(g, levels, nhwc, b, C, anc);
+    if (!r.row) return;
+    if (C <= 128) {   // one round of loads, everything in registers
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = lane + 32 * k < C ? __ldg(r.row + (size_t)(lane + 32 * k) * r.cstride) : 0.f;
+        ood_reduce(v, C, T, lane, e, m);
+        return;
+    }
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, __ldg(r.row + (size_t)c * r.cstride));
+    mx = warp_max(mx);
+    float s = 0.f;
+    const float invT = 1.0f / T;
+    for (int c = lane; c < C; c += 32) s += expf((__ldg(r.row + (size_t)c * r.cstride) - mx) * invT);
     s = warp_sum(s);
     e = -T * (mx * invT + logf(s));
     m = mx;

@@ -168,6 +168,7 @@ struct PostArgs {
 static inline size_t post_det_bytes(int cap) { return (size_t)cap * 26 + (size_t)(cap / 32) * 4 + 16 + kNmsMaskBytes; }
 
 // rows of one image out of the sorted keys each thread holds (rank = tid + k * 1024)
+template <bool SOFT>
 static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned long long (&keys)[kPostKeys],
                                      const int (&cpos)[kPostKeys], unsigned char *raw) {
     __shared__ int s_cnt[kPostKeys * kPostWarps + 1];
@@ -278,7 +279,7 @@ static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned lo
         // 4. suppression, first D survivors (the candidates are in descending score order by construction)
         DetSmem S;
         S.box = sbox; S.score = sscore; S.src = nullptr; S.alive = alive;
-        if (P.p.soft_nms)
+        if (SOFT)
             kept_n = soft_nms_batched(S, n, true, P.p.soft_sigma, P.p.soft_iou, P.p.soft_score_thr, D, s_kept,
                                       kDetFirstWindow, kDetThreads, [&](int q, int i, float s) { s_keptscore[q] = s; });
         else
@@ -302,7 +303,7 @@ static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned lo
             float4 o = decode_xyxy(__ldg(P.anchors + anchor), gather_box(P.T, b, (int)anchor), clip, lim_x, lim_y);
             if (has_scale) { o.x = __fmul_rn(o.x, scale); o.y = __fmul_rn(o.y, scale); o.z = __fmul_rn(o.z, scale); o.w = __fmul_rn(o.w, scale); }
             r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = o.w;
-            r[4] = P.p.soft_nms ? s_keptscore[q] : sscore[i];
+            r[4] = SOFT ? s_keptscore[q] : sscore[i];
             r[5] = (float)((flat - anchor * (unsigned)P.T.C) + 1u);
         }
 #pragma unroll
@@ -313,10 +314,37 @@ static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned lo
     if (tid == 0) P.count[b] = kept_n;
     // 6. OOD scores over the C raw logits of each detection's source anchor (one warp per detection)
     if (P.energy) {
-        for (int q = warp; q < D; q += kPostWarps) {
-            float e = 0.f, m = 0.f;
-            if (q < kept_n) ood_row(P.T.g, P.G.cls, P.G.nhwc, b, P.T.C, (long long)fd_div(sflat[s_kept[q]], P.T.div_C), P.ood_T, lane, e, m);
-            if (lane == 0) { P.energy[(size_t)b * D + q] = e; P.max_logit[(size_t)b * D + q] = m; }
+        if (P.T.C <= 128) {
+            // the scattered loads of four detections per warp are issued together (one exposed latency per 128 rows)
+            for (int q0 = warp; q0 < D; q0 += 4 * kPostWarps) {
+                float v[4][4];
+                bool ok[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int q = q0 + j * kPostWarps;
+                    OodRow r;
+                    r.row = nullptr; r.cstride = 0;
+                    if (q < kept_n) r = ood_row_of(P.T.g, P.G.cls, P.G.nhwc, b, P.T.C, (long long)fd_div(sflat[s_kept[q]], P.T.div_C));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        v[j][k] = (r.row && lane + 32 * k < P.T.C) ? __ldg(r.row + (size_t)(lane + 32 * k) * r.cstride) : 0.f;
+                    ok[j] = r.row != nullptr;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int q = q0 + j * kPostWarps;
+                    if (q >= D) continue;
+                    float e = 0.f, m = 0.f;
+                    if (ok[j]) ood_reduce(v[j], P.T.C, P.ood_T, lane, e, m);
+                    if (lane == 0) { P.energy[(size_t)b * D + q] = e; P.max_logit[(size_t)b * D + q] = m; }
+                }
+            }
+        } else {
+            for (int q = warp; q < D; q += kPostWarps) {
+                float e = 0.f, m = 0.f;
+                if (q < kept_n) ood_row(P.T.g, P.G.cls, P.G.nhwc, b, P.T.C, (long long)fd_div(sflat[s_kept[q]], P.T.div_C), P.ood_T, lane, e, m);
+                if (lane == 0) { P.energy[(size_t)b * D + q] = e; P.max_logit[(size_t)b * D + q] = m; }
+            }
         }
     }
     __syncthreads();   // shared memory is free again
@@ -334,6 +362,7 @@ __device__ __forceinline__ void load_sorted(const unsigned long long *s, const u
 }
 
 // everything of image b that is not streaming, by the whole CTA
+template <bool SOFT>
 static __device__ void run_tail(const PostArgs &P, int b, unsigned long long *s) {
     stamp(P.timeline, b, 2);
     __threadfence();   // acquire side of the done-counter hand-off: the candidates of every other SM are visible
@@ -369,14 +398,16 @@ static __device__ void run_tail(const PostArgs &P, int b, unsigned long long *s)
     }
     __syncthreads();   // the keys are in registers: the buffer becomes the detection arrays
     stamp(P.timeline, b, 4);
-    detect_sorted(P, b, keys, cpos, reinterpret_cast<unsigned char *>(s));
+    detect_sorted<SOFT>(P, b, keys, cpos, reinterpret_cast<unsigned char *>(s));
     stamp(P.timeline, b, 3);
 }
 
 // Staged pipeline: the tails of all images as one launch after the collect kernel of odk_topk.cu
+// (two instantiations: the suppressors are large, and each kernel's register allocation is better without the other)
+template <bool SOFT>
 __global__ void __launch_bounds__(kPostThreads, 1) post_tail_kernel(const __grid_constant__ PostArgs P) {
     extern __shared__ __align__(16) unsigned long long s_dyn[];
-    run_tail(P, (int)blockIdx.x, s_dyn);
+    run_tail<SOFT>(P, (int)blockIdx.x, s_dyn);
 }
 
 // Streaming warps only ever touch shared memory between tasks; everything that needs a global round trip is
@@ -397,6 +428,7 @@ constexpr int kStageBufs = 4;         // staging buffers per streaming warp: a b
 constexpr int kRecCap = 256;          // ring of task records (at most kStageBufs per streaming warp are outstanding)
 constexpr int kChunkRing = 16;        // published chunk bases (the bookkeeper is at most `ahead` + 1 chunks ahead)
 
+template <bool SOFT>
 __global__ void __launch_bounds__(kPostThreads, 1) post_fused_kernel(const __grid_constant__ PostArgs P) {
     extern __shared__ __align__(16) unsigned long long s_dyn[];
     // the staging buffers alias the head of the dynamic buffer: the CTA only meets for a tail once every record is
@@ -431,7 +463,7 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_fused_kernel(const __gri
     auto meet = [&](bool drained) {
         __syncthreads();   // all 32 warps are here: nobody is streaming, every record is flushed, the queue is stable
         const unsigned n1 = s_tail_n, d0 = s_tail_done;
-        for (unsigned i = d0; i != n1; ++i) run_tail(P, s_tailq[i & 63u], s_dyn);
+        for (unsigned i = d0; i != n1; ++i) run_tail<SOFT>(P, s_tailq[i & 63u], s_dyn);
         __syncthreads();
         if (tid == 0) { s_tail_done = n1; s_arrived = 0u; }
         return __syncthreads_and(drained ? 1 : 0) != 0;
@@ -865,22 +897,24 @@ int odk_postprocess(const void *const *cls_levels, const void *const *box_levels
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms < 1) sms = 148;
-        cudaError_t e = cudaFuncSetAttribute(post_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kernel = params->soft_nms ? post_fused_kernel<true> : post_fused_kernel<false>;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error((int)e, "odk_postprocess: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
         unsigned grid = (unsigned)sms;
         const unsigned useful = (P.total_tasks + kStreamWarps - 1) / kStreamWarps;
         if (grid > useful) grid = useful;
         if (grid < 1) grid = 1;
-        post_fused_kernel<<<grid, kPostThreads, smem, st>>>(P);
+        kernel<<<grid, kPostThreads, smem, st>>>(P);
         rc = check_launch("odk_postprocess/post_fused_kernel");
     } else {
         // staged: the one-wave collect kernel of odk_topk.cu streams the whole batch, then one CTA per image runs
         // the image's tail (with B <= #SMs both pipelines expose exactly one tail after the last logit is read)
         rc = launch_topk_collect(a, toff, st);
         if (rc) return rc;
-        cudaError_t e = cudaFuncSetAttribute(post_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kernel = params->soft_nms ? post_tail_kernel<true> : post_tail_kernel<false>;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error((int)e, "odk_postprocess: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
-        post_tail_kernel<<<B, kPostThreads, smem, st>>>(P);
+        kernel<<<B, kPostThreads, smem, st>>>(P);
         rc = check_launch("odk_postprocess/post_tail_kernel");
     }
     if (rc) return rc;

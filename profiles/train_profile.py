@@ -1,6 +1,6 @@
 """Small driver for profiling the training-target path (BASELINE.json configs[1]: D0 512^2, B=64, C=90,
 M=10): 3 iterations of labeler + fused loss (forward), then 3 of forward + gradient.  Run plain, then
-under ncu."""
+under ncu.  Second argument `cl`: the head outputs are channels_last (flat stream + patch kernels)."""
 import os
 import sys
 
@@ -22,9 +22,13 @@ g.manual_seed(1)
 feat = synth.feat_hw(size)
 cls_out = [torch.randn((B, 9 * C, h, w), generator=g, device=dev) * 1.5 - 4.6 for h, w in feat]
 box_out = [torch.randn((B, 36, h, w), generator=g, device=dev) * 0.2 for h, w in feat]
+if 'cl' in sys.argv[2:]:
+    cls_out = [t.contiguous(memory_format=torch.channels_last) for t in cls_out]
+    box_out = [t.contiguous(memory_format=torch.channels_last) for t in box_out]
 gb, gc = synth.gt_boxes(100, B, size, M, C)
 gb, gc = torch.from_numpy(gb).to(dev), torch.from_numpy(gc).to(dev)
 labeler = AnchorLabeler(Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size)).to(dev), C, match_threshold=0.5)
+TRANSIENT = 'transient' in sys.argv[2:]   # the bench's mode: the loss walks the labeler's list and clears the keys
 kw = dict(num_classes=C, alpha=0.25, gamma=1.5, delta=0.1, box_loss_weight=50.0)
 for grad in (False, True):
     for t in cls_out + box_out:
@@ -32,7 +36,7 @@ for grad in (False, True):
     for it in range(iters):
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
-        lb = labeler.assign(gb, gc)
+        lb = labeler.assign(gb, gc, transient=TRANSIENT)
         e1.record()
         with torch.set_grad_enabled(grad):
             tot, cl, bx = loss_fn_fused(cls_out, box_out, lb, **kw)

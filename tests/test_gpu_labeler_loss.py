@@ -309,3 +309,61 @@ def test_loss_channels_last_inputs_in_place(legacy, sm):
     # the labeler's workspace came back zeroed from the transient batch: the next assignment is right without a memset
     lb2 = lab.assign(torch.from_numpy(gb).to(dev()), torch.from_numpy(gc).to(dev()))
     np.testing.assert_array_equal(lb2.num_positives.cpu().numpy(), onp)
+
+
+@pytest.mark.parametrize('name,B,m', [('d0', 4, 10), ('d3', 2, 60)])
+def test_loss_stream_patch_modes_bitwise(name, B, m):
+    """The fused loss = a layout-agnostic stream over the logits + a patch of the matched anchors.  The patch either
+    walks the labeler's list of matched anchors (transient label batch: atomic-append order, and it zeroes the keys)
+    or scans the key / match row; its sums are fixed-point integers, so both modes, and repeated runs on lists in
+    different orders, give the SAME BITS -- losses and gradients.  The workspace is left clean for the next step."""
+    from ood_object_detection_b200.loss import loss_fn_fused
+    size, scale = synth.MODEL_SHAPES[name]
+    C = 90
+    anc, lab = make_labeler(size, scale, C)
+    gb, gc = synth.gt_boxes(910 + B, B, size, m, C)
+    co_np, bo_np = synth.head_outputs(911 + B, B, size, C, tie_free=False)
+    kw = dict(num_classes=C, alpha=0.25, gamma=1.5, delta=0.1, box_loss_weight=50.0)
+    gbt, gct = torch.from_numpy(gb).to(dev()), torch.from_numpy(gc).to(dev())
+
+    def run(transient):
+        co, bo = [t(x, True) for x in co_np], [t(x, True) for x in bo_np]
+        lb = lab.assign(gbt, gct, transient=transient)
+        tot, cl, bl = loss_fn_fused(co, bo, lb, **kw)
+        tot.backward()
+        return (np.array([tot.item(), cl.item(), bl.item()], np.float32), [x.grad.cpu().numpy() for x in co],
+                [x.grad.cpu().numpy() for x in bo])
+    ref = run(False)
+    for trial in range(3 if USE_GRID[0] else 1):   # (the list exists on the grid labeler only)
+        got = run(USE_GRID[0])
+        np.testing.assert_array_equal(got[0].view(np.uint32), ref[0].view(np.uint32))
+        for l in range(5):
+            np.testing.assert_array_equal(got[1][l], ref[1][l])
+            np.testing.assert_array_equal(got[2][l], ref[2][l])
+
+
+def test_loss_stream_agrees_with_plane_kernels(monkeypatch):
+    """ODK_LOSS_KERNEL=ring selects the plane-walking kernels (the round-1 path, still used for targets given as
+    tensors): same losses to 1e-6 (different summation order) and the same gradients bit for bit."""
+    from ood_object_detection_b200.loss import loss_fn_fused
+    size, scale = synth.MODEL_SHAPES['d3']
+    B, C, m = 2, 90, 25
+    anc, lab = make_labeler(size, scale, C)
+    gb, gc = synth.gt_boxes(920, B, size, m, C)
+    co_np, bo_np = synth.head_outputs(921, B, size, C, tie_free=False)
+    kw = dict(num_classes=C, alpha=0.25, gamma=1.5, delta=0.1, box_loss_weight=50.0)
+    out = {}
+    for which in ('stream', 'ring'):
+        if which == 'ring':
+            monkeypatch.setenv('ODK_LOSS_KERNEL', 'ring')
+        else:
+            monkeypatch.delenv('ODK_LOSS_KERNEL', raising=False)
+        co, bo = [t(x, True) for x in co_np], [t(x, True) for x in bo_np]
+        lb = lab.assign(torch.from_numpy(gb).to(dev()), torch.from_numpy(gc).to(dev()))
+        tot, cl, bl = loss_fn_fused(co, bo, lb, **kw)
+        tot.backward()
+        out[which] = ([tot.item(), cl.item(), bl.item()], [x.grad.cpu().numpy() for x in co], [x.grad.cpu().numpy() for x in bo])
+    np.testing.assert_allclose(out['stream'][0], out['ring'][0], rtol=1e-6)
+    for l in range(5):
+        np.testing.assert_array_equal(out['stream'][1][l], out['ring'][1][l])
+        np.testing.assert_array_equal(out['stream'][2][l], out['ring'][2][l])
