@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(kDetThreads) detect_kernel(const __grid_consta
         else if (A.p.soft_nms)
             // the lazy window and the batches need non-increasing scores: true for top-k output (checked above for API inputs)
             kept_n = soft_nms_batched(S, n, true, A.p.soft_sigma, A.p.soft_iou, A.p.soft_score_thr, D, s_kept,
-                                      kDetFirstWindow, kDetThreads, [&](int q, int i, float sc) { s_keptscore[q] = sc; });
+                                      kDetFirstWindow, kDetThreads, [&](int q, int i, float sc) { s_keptscore[q] = sc; },
+                                      s_raw + (size_t)A.cap * 24 + (size_t)(A.cap / 32) * 4 + 16);
         else
             kept_n = hard_nms_rounds(S, n, A.nms_thr_f, D, s_kept, reinterpret_cast<unsigned *>(s_raw + (size_t)A.cap * 24 + (size_t)(A.cap / 32) * 4 + 16));
         __syncthreads();

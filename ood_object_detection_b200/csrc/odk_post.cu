@@ -165,7 +165,7 @@ struct PostArgs {
     float ood_T;
 };
 
-static inline size_t post_det_bytes(int cap) { return (size_t)cap * 26 + (size_t)(cap / 32) * 4 + 16 + kNmsMaskBytes; }
+static inline size_t post_det_bytes(int cap) { return (size_t)cap * 26 + (size_t)(cap / 32) * 4 + 16 + kSoftScratchBytes; }   // (>= the hard-NMS masks)
 
 // rows of one image out of the sorted keys each thread holds (rank = tid + k * 1024)
 template <bool SOFT>
@@ -281,7 +281,8 @@ static __device__ void detect_sorted(const PostArgs &P, int b, const unsigned lo
         S.box = sbox; S.score = sscore; S.src = nullptr; S.alive = alive;
         if (SOFT)
             kept_n = soft_nms_batched(S, n, true, P.p.soft_sigma, P.p.soft_iou, P.p.soft_score_thr, D, s_kept,
-                                      kDetFirstWindow, kDetThreads, [&](int q, int i, float s) { s_keptscore[q] = s; });
+                                      kDetFirstWindow, kDetThreads, [&](int q, int i, float s) { s_keptscore[q] = s; },
+                                      reinterpret_cast<unsigned char *>(alive + cap / 32 + 4));
         else
             kept_n = hard_nms_rounds(S, n, P.nms_thr_f, D, s_kept, alive + cap / 32 + 4);
         __syncthreads();

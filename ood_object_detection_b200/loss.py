@@ -143,8 +143,10 @@ class _DetectionLossFn(torch.autograd.Function):
 
         s_cls = factor(g_total, g_cls)
         s_box = factor(g_total, None if g_box is None else g_box.float() / w)
+        # total.backward(): one factor for everything, one launch
+        groups = (((ctx.gcls + ctx.gbox), s_cls),) if (g_cls is None and g_box is None) else ((ctx.gcls, s_cls), (ctx.gbox, s_box))
         with torch.cuda.device(dev):
-            for bufs, sc in ((ctx.gcls, s_cls), (ctx.gbox, s_box)):
+            for bufs, sc in groups:
                 for lo in range(0, len(bufs), 16):
                     part = bufs[lo:lo + 16]
                     sizes = (_lib.c_int64 * len(part))(*[t.numel() for t in part])
