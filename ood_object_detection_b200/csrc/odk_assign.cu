@@ -610,13 +610,7 @@ int odk_assign(const float *anchors, const float *gt_boxes, const int32_t *gt_la
     if (e != cudaSuccess) return set_error((int)e, "odk_assign memset: %s", cudaGetErrorString(e));
     const int per_cta = kAssignThreads * kPerThread;
     const int ntiles = (g.Apad + per_cta - 1) / per_cta;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms < 1) sms = 148;
-    }
+    const int sms = device_sm_count();
     // One tile per CTA measured faster than a persistent walk (70 vs 88 us at D0, B=64): the kernel is
     // bound by dependent latency per warp, so more independent CTAs in flight win.  The tile loop in
     // the kernel stays for very large grids.

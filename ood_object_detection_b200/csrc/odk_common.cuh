@@ -170,4 +170,24 @@ __device__ __forceinline__ void st_stream1(float *p, float v) {
 }
 
 #endif  // __CUDACC__
+// SM count of the CURRENT device, cached per device ordinal (every cached launch parameter in this library is
+// keyed by the device: one process may drive several GPUs).
+constexpr int kMaxDevices = 64;
+static inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+static inline int device_sm_count() {
+    static int sms[kMaxDevices] = {0};
+    const int dev = current_device();
+    int v = sms[dev];
+    if (!v) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v < 1) v = 148;
+        sms[dev] = v;   // benign race: every thread computes the same value
+    }
+    return v;
+}
+
 }  // namespace odk

@@ -811,16 +811,7 @@ loss_patch_kernel(const __grid_constant__ LossArgs A) {
     finish_block(A, 0.f, 0.f, nrm, 0.0, true, ci, bi);
 }
 
-static int g_sms = 0;
-static int sm_count() {
-    if (!g_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sms < 1) g_sms = 148;
-    }
-    return g_sms;
-}
+static int sm_count() { return device_sm_count(); }
 
 static int grid_for(long long items, int blocks_per_sm) {
     long long need = (items + kLossThreads - 1) / kLossThreads;
@@ -832,14 +823,17 @@ static int grid_for(long long items, int blocks_per_sm) {
 
 template <int MODE, bool GRAD, bool FUSED>
 static int launch_loss(LossArgs &ring, LossArgs &plain, cudaStream_t st) {
-    static int occ_ring = 0, occ_plain = 0;
-    if (!occ_ring) {
+    static int occ_ring_dev[kMaxDevices] = {0}, occ_plain_dev[kMaxDevices] = {0};   // per device: the opt-in is per device too
+    const int dev = current_device();
+    if (!occ_ring_dev[dev]) {
+        int r = 0, pl = 0;
         cudaFuncSetAttribute(loss_kernel_ring<MODE, GRAD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes(GRAD));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ring, loss_kernel_ring<MODE, GRAD, FUSED>, kLossThreads, ring_bytes(GRAD));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_plain, loss_kernel<MODE, GRAD, FUSED>, kLossThreads, 0);
-        if (occ_ring < 1) occ_ring = 1;
-        if (occ_plain < 1) occ_plain = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, loss_kernel_ring<MODE, GRAD, FUSED>, kLossThreads, ring_bytes(GRAD));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pl, loss_kernel<MODE, GRAD, FUSED>, kLossThreads, 0);
+        occ_plain_dev[dev] = pl < 1 ? 1 : pl;
+        occ_ring_dev[dev] = r < 1 ? 1 : r;
     }
+    const int occ_ring = occ_ring_dev[dev], occ_plain = occ_plain_dev[dev];
     const long long n_ring = ring.item_off[ring.g.nlev], n_plain = plain.item_off[plain.g.nlev];
     // The finishing launch sums every partial slot; the other one (if any) runs first on the stream.
     int g_plain = 0, g_ring = 0;
