@@ -239,7 +239,7 @@ class Ctx:
                 for _ in range(2):
                     fn()
                 gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=side):
+                with torch.cuda.graph(gr, stream=side, capture_error_mode='thread_local'):
                     out = fn()
             torch.cuda.current_stream().wait_stream(side)
             for _ in range(3):
@@ -363,9 +363,12 @@ class TrainWorkload:
             self.step(grad)
         self.drop_grads()
         ctx.sync_all()
-        gr = None
-        if not (ctx.world > 1 and self.mailbox is None):   # (the NCCL fallback exchange stays outside graphs)
-            gr, _ = ctx.capture(lambda: self.step(grad))
+        gr, _ = ctx.capture(lambda: self.step(grad))       # (the NCCL fallback exchange, when used, is captured too)
+        if ctx.world > 1:                                  # every rank replays a graph or none does
+            flag = ctx.torch.tensor([1 if gr is not None else 0], device=ctx.dev)
+            ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                gr = None
         mode = 'cuda_graph' if gr is not None else 'eager'
         drain = None
         if self.mailbox is not None:     # the last step's record is still in the mailboxes: inside the timed region
@@ -482,9 +485,13 @@ class PostWorkload:
             for _ in range(max(warmup, 3)):
                 self.step(pipeline=pipeline)
             ctx.sync_all()
-            gr = None
-            if ctx.world == 1:           # NCCL collectives stay outside graphs here
-                gr, _ = ctx.capture(lambda: self.step(pipeline=pipeline))
+            # (N > 1: the NCCL all-gather of the detections is captured with the kernels; eager if capture fails)
+            gr, _ = ctx.capture(lambda: self.step(pipeline=pipeline))
+            if ctx.world > 1:            # every rank replays a graph or none does
+                flag = ctx.torch.tensor([1 if gr is not None else 0], device=ctx.dev)
+                ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN)
+                if int(flag.item()) == 0:
+                    gr = None
             ms = ctx.timed(gr.replay if gr is not None else (lambda: self.step(pipeline=pipeline)), steps)
             worst = 0.0
             if ctx.world == 1:           # the slowest single call (allocator stalls, clock ramps show up here)

@@ -112,6 +112,10 @@ int odk_targets(const float *anchors, const float *gt_boxes, const int32_t *gt_l
  *   grad_cls_levels / grad_box_levels: HOST arrays of DEVICE pointers (same shapes as the
  *   inputs) receiving d total / d input, or NULL for forward only.
  * Workspace: odk_loss_workspace_bytes().
+ * With `match` the work is a layout-agnostic stream over the class logits (every element as a negative)
+ * plus a patch of the matched anchors; the loss sums are bit-reproducible from call to call.  The
+ * environment variable ODK_LOSS_KERNEL=ring selects the plane-walking kernels instead (NCHW only; they
+ * also serve targets given as tensors).
  */
 #define ODK_MAILBOX_MAX_WORLD 32
 /* Optional fused exchange of the loss partial sums between data-parallel ranks (see the mailbox

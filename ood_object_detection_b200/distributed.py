@@ -250,7 +250,12 @@ def gather_detections(dets: torch.Tensor, count: torch.Tensor, extras: Optional[
     out = []
     for t in tensors:
         t = t.contiguous()
-        parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t, group=group)
-        out.append(torch.cat(parts, dim=0))
+        whole = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        try:      # one collective straight into the result (rank order), capturable in a CUDA graph
+            dist.all_gather_into_tensor(whole, t, group=group)
+        except (RuntimeError, NotImplementedError, AttributeError):   # a backend without the flat form
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t, group=group)
+            whole = torch.cat(parts, dim=0)
+        out.append(whole)
     return out
