@@ -74,10 +74,13 @@ int odk_assign(const float *anchors, const float *gt_boxes, const int32_t *gt_la
  *   plane_desc  DEVICE [num_levels*na][12] fp32, plane k = level*na + shape:
  *               cy0, cx0 (centre of cell (0,0)), sy, sx (cell pitch), hy, hx (half sizes), area,
  *               W, H, off_l, shape, level
+ *   plane_gen   DEVICE [num_levels*na][6] fp64 or NULL: the generator of the same grids -- cy0, cx0, sy, sx,
+ *               half_y, half_x exactly as anchors.py:264-299 computes them in float64.  When given, a cell's anchor is
+ *               recomputed from it (bit-identical to the table, see odk_anchor_table) instead of gathered.
  * match_thr must be > 0.  Workspace: odk_assign_grid_workspace_bytes(B, A). */
 size_t odk_assign_grid_workspace_bytes(int B, int64_t A);
 #define ODK_ASSIGN_WS_CLEAN 1   /* flags: the workspace is all zero (fresh, or left so by odk_loss' clear_keys): no memset */
-int odk_assign_grid(const float *anchors, const float *plane_desc, int num_planes, const float *gt_boxes,
+int odk_assign_grid(const float *anchors, const float *plane_desc, const double *plane_gen, int num_planes, const float *gt_boxes,
                     const int32_t *gt_labels, const int32_t *gt_count, int B, int Mmax, const int32_t *level_hw,
                     int num_levels, int na, float match_thr, int filter_valid, int32_t *match, float *num_pos,
                     float *normalizer, int flags, void *workspace, size_t workspace_bytes, void *stream);
@@ -86,6 +89,10 @@ int odk_assign_grid(const float *anchors, const float *plane_desc, int num_plane
  * odk_loss consumes directly (odk_loss_params.match_is_key64) and odk_keys_to_match converts on
  * demand.  `normalizer` (nullable) receives sum(num_pos) + 1 (loss.py:261) as one fp32. */
 int odk_keys_to_match(const void *keys, int B, int64_t A, int32_t *match, void *stream);
+/* The anchor table [A,4] (yxyx fp32, reference order) from plane_desc + plane_gen: what Anchors._generate_boxes
+ * (anchors.py:264-299) produces on the host, bit for bit. */
+int odk_anchor_table(const float *plane_desc, const double *plane_gen, int num_planes, const int32_t *level_hw, int num_levels,
+                     int na, float *anchors_out, void *stream);
 
 /* Pairwise IoU matrix out[n,m] of yxyx boxes: IouSimilarity.compare
  * (region_similarity_calculator.py:59-101), same fp32 operation order. */

@@ -47,7 +47,8 @@ SIGNATURES = {
     'odk_assign_workspace_bytes': (c_size_t, [c_int, c_int]),
     'odk_assign': (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, c_size_t, _P]),
     'odk_assign_grid_workspace_bytes': (c_size_t, [c_int, c_int64]),
-    'odk_assign_grid': (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, c_int, _P, c_size_t,
+    'odk_anchor_table': (c_int, [_P, _P, c_int, _P, c_int, c_int, _P, _P]),
+    'odk_assign_grid': (c_int, [_P, _P, _P, c_int, _P, _P, _P, c_int, c_int, _P, c_int, c_int, c_float, c_int, _P, _P, _P, c_int, _P, c_size_t,
                                 _P]),
     'odk_keys_to_match': (c_int, [_P, c_int, c_int64, _P, _P]),
     'odk_iou_matrix': (c_int, [_P, c_int, _P, c_int, _P, _P]),

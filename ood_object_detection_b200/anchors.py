@@ -58,6 +58,7 @@ class Anchors(nn.Module):
         self.register_buffer('boxes', self._generate_boxes())
         # not persistent: the reference's Anchors has only `boxes` in its state_dict, and checkpoints must stay interchangeable
         self.register_buffer('plane_desc', self._generate_plane_desc(), persistent=False)
+        self.register_buffer('plane_gen', self._generate_plane_gen(), persistent=False)
 
     @classmethod
     def from_config(cls, config, img_size=None, min_level=0):
@@ -101,6 +102,22 @@ class Anchors(nn.Module):
 
     def get_anchors_per_location(self):
         return self.num_scales * len(self.aspect_ratios)
+
+    def _generate_plane_gen(self):
+        """[levels*na, 6] float64: cy0, cx0, sy, sx, half_y, half_x of every (level, shape) grid -- the numbers
+        _generate_boxes builds the table from, so the labeler kernel can recompute an anchor instead of gathering it."""
+        rows = []
+        for level_cfg in self.config.values():
+            for stride, octave_scale, aspect, anchor_scale in level_cfg:
+                size_x = anchor_scale * stride[1] * 2 ** octave_scale
+                size_y = anchor_scale * stride[0] * 2 ** octave_scale
+                if isinstance(aspect, Sequence):
+                    ax, ay = aspect[0], aspect[1]
+                else:
+                    ax = np.sqrt(aspect)
+                    ay = 1.0 / ax
+                rows.append([stride[0] / 2, stride[1] / 2, float(stride[0]), float(stride[1]), size_y * ay / 2.0, size_x * ax / 2.0])
+        return torch.tensor(rows, dtype=torch.float64)
 
     def _generate_plane_desc(self):
         """[levels*na, 12] fp32 description of every (level, shape) anchor grid for odk_assign_grid:
@@ -196,6 +213,9 @@ class AnchorLabeler(object):
         # gt-centric kernel (odk_assign_grid) for the regular pyramid grids; the dense kernel
         # (odk_assign) is kept for arbitrary anchor sets and non-positive thresholds
         self.use_grid_kernel = True
+        # recompute anchors from the float64 generator (Anchors.plane_gen) instead of gathering them from the table:
+        # bit-identical (odk_anchor_table), measured equally fast (the kernel is a chain of short phases, not gather-bound)
+        self.use_anchor_generator = False
 
     # ---- helpers ---------------------------------------------------------------------------
     def _device(self):
@@ -216,14 +236,15 @@ class AnchorLabeler(object):
         return torch.device('cuda', torch.cuda.current_device())
 
     def _anchor_tables(self, dev):
-        """(boxes, plane_desc) on ``dev`` (cached copies when the module itself lives on the host)."""
+        """(boxes, plane_desc, plane_gen) on ``dev`` (cached copies when the module itself lives on the host)."""
         if self.anchors.boxes.device == dev:
-            return self.anchors.boxes, getattr(self.anchors, 'plane_desc', None)
+            return self.anchors.boxes, getattr(self.anchors, 'plane_desc', None), getattr(self.anchors, 'plane_gen', None)
         key = (dev, self.anchors.boxes.data_ptr())
         if self._dev_tables.get('key') != key:
-            desc = getattr(self.anchors, 'plane_desc', None)
-            self._dev_tables = {'key': key, 'boxes': self.anchors.boxes.to(dev), 'desc': None if desc is None else desc.to(dev)}
-        return self._dev_tables['boxes'], self._dev_tables['desc']
+            desc, gen = getattr(self.anchors, 'plane_desc', None), getattr(self.anchors, 'plane_gen', None)
+            self._dev_tables = {'key': key, 'boxes': self.anchors.boxes.to(dev), 'desc': None if desc is None else desc.to(dev),
+                                'gen': None if gen is None else gen.to(dev)}
+        return self._dev_tables['boxes'], self._dev_tables['desc'], self._dev_tables['gen']
 
     def _pack(self, gt_boxes, gt_classes, filter_valid):
         """-> gt_boxes [B,M,4] fp32, labels [B,M] int32, count [B] int32 or None, on device.  Ragged lists (the
@@ -314,7 +335,9 @@ class AnchorLabeler(object):
         dev = boxes.device
         B, M = boxes.shape[0], boxes.shape[1]
         lib = _lib.lib()
-        anc, desc = self._anchor_tables(dev)
+        anc, desc, gen = self._anchor_tables(dev)
+        if gen is not None and (gen.dtype != torch.float64 or not self.use_anchor_generator):
+            gen = None
         A = anc.shape[0]
         apad = lib.odk_planar_stride(A)
         num_pos = torch.empty((B,), dtype=torch.float32, device=dev)
@@ -332,7 +355,7 @@ class AnchorLabeler(object):
                 normalizer = torch.empty((1,), dtype=torch.float32, device=dev) if normalizer_out is None else normalizer_out
                 if normalizer.dtype != torch.float32 or normalizer.numel() != 1 or normalizer.device != dev:
                     raise ValueError('normalizer_out must be one float32 element on the gt device')
-                _lib.check(lib.odk_assign_grid(_lib.ptr(anc), _lib.ptr(desc), desc.shape[0], _lib.ptr(boxes),
+                _lib.check(lib.odk_assign_grid(_lib.ptr(anc), _lib.ptr(desc), _lib.ptr(gen), desc.shape[0], _lib.ptr(boxes),
                                                _lib.ptr(labels), _lib.ptr(count), B, M, _lib.int_array(hw), len(hw), na,
                                                thr, int(bool(filter_valid)), None, _lib.ptr(num_pos),
                                                _lib.ptr(normalizer), flags, _lib.ptr(ws), ws.numel() * 8,
@@ -361,7 +384,7 @@ class AnchorLabeler(object):
         cls_flat = torch.empty((B * A,), dtype=torch.int64, device=dev)
         box_flat = torch.empty((B * A * 4,), dtype=torch.float32, device=dev)
         hw = self.anchors.level_hw()
-        anc, _ = self._anchor_tables(dev)
+        anc = self._anchor_tables(dev)[0]
         with torch.cuda.device(dev):
             _lib.check(lib.odk_targets(_lib.ptr(anc), _lib.ptr(lb.gt_boxes), _lib.ptr(lb.gt_labels), B, M,
                                        _lib.int_array(hw), len(hw), na, _lib.ptr(lb.match), _lib.ptr(cls_flat),

@@ -330,14 +330,27 @@ constexpr int kMaxPlanes = ODK_MAX_LEVELS * 16;
 constexpr int kCellsInFlight = 4;
 constexpr int kDescFloats = 12;   // cy0, cx0, sy, sx, hy, hx, area, W, H, off, a, level
 
+// `gen` (nullable): the grids' generator in float64 -- cy0, cx0, sy, sx, half_y, half_x per plane, the very numbers
+// the anchor table was built from (anchors.py:264-299).  With it a cell's anchor is RECOMPUTED, bit for bit what the
+// table holds: the centre cy0 + y*sy is exact in double (small integers and halves), centre -/+ half size is one
+// IEEE double operation each, like numpy's, and the cast rounds to nearest like `.float()`
+// (odk_anchor_table + test_anchor_table_from_generator compare every anchor of every model shape).  That takes the
+// dependent anchor gather -- an L2 round trip per group of cells -- out of the enumeration loop.
+constexpr int kGenDoubles = 6;
+__device__ __forceinline__ float4 anchor_from_gen(const double *gk, int yy, int xx) {
+    const double cy = fma((double)yy, gk[2], gk[0]), cx = fma((double)xx, gk[3], gk[1]);   // exact
+    return make_float4(__double2float_rn(__dsub_rn(cy, gk[4])), __double2float_rn(__dsub_rn(cx, gk[5])),
+                       __double2float_rn(__dadd_rn(cy, gk[4])), __double2float_rn(__dadd_rn(cx, gk[5])));
+}
+
 __device__ __forceinline__ void assign_one_gt(const Geo &g, const float4 *__restrict__ anchors, const float *__restrict__ desc,
-                                              int nplanes, const float4 *__restrict__ gt_boxes,
+                                              const double *__restrict__ gen, int nplanes, const float4 *__restrict__ gt_boxes,
                                               const int32_t *__restrict__ gt_labels, const int32_t *__restrict__ gt_count,
                                               int Mmax, float thr, int filter_valid, unsigned long long *keys,
                                               int32_t *pos_count, unsigned *touched, int touched_cap) {
     __shared__ int s_off[kMaxPlanes + 1], s_x0[kMaxPlanes], s_nx[kMaxPlanes], s_y0[kMaxPlanes];
     __shared__ int s_w[kMaxPlanes], s_base[kMaxPlanes], s_sh[kMaxPlanes], s_hw[kMaxPlanes];
-    __shared__ unsigned char s_done[kMaxPlanes];
+    __shared__ double s_gen[kMaxPlanes][kGenDoubles];
     __shared__ unsigned long long s_red[kGtcThreads / 32];
     __shared__ unsigned long long s_best;
     const int b = blockIdx.y, i = blockIdx.x;
@@ -351,9 +364,10 @@ __device__ __forceinline__ void assign_one_gt(const Geo &g, const float4 *__rest
     if (tid == 0) s_best = 0ull;
     for (int k = tid; k < nplanes; k += kGtcThreads) {
         const float *d = desc + (size_t)k * kDescFloats;
-        s_done[k] = 0;
         s_w[k] = (int)d[7]; s_base[k] = (int)d[9]; s_sh[k] = (int)d[10]; s_hw[k] = g.hw[(int)d[11]];
     }
+    if (gen)
+        for (int e = tid; e < nplanes * kGenDoubles; e += kGtcThreads) (&s_gen[0][0])[e] = __ldg(gen + e);
     __syncthreads();
     unsigned long long *krow = keys + (size_t)b * g.Apad;
 
@@ -363,19 +377,29 @@ __device__ __forceinline__ void assign_one_gt(const Geo &g, const float4 *__rest
         for (int k = tid; k < nplanes; k += kGtcThreads) {
             const float *d = desc + (size_t)k * kDescFloats;
             int nx = 0, ny = 0, x0 = 0, y0 = 0;
-            if (!s_done[k] && qa > 0.0f) {
+            if (qa > 0.0f) {
                 const float pa = d[6];
                 const float bound = fminf(pa, qa) / fmaxf(pa, qa) * 1.00001f;   // >= any IoU in this plane
-                const bool want = pass == 0 ? (bound >= thr) : (bound > best_so_far);
+                // pass 1 (the gt matched nothing: the forced match needs the true arg-max) looks at every overlapping cell
+                // of every plane that can still beat the best so far, pass-0 planes included
+                const bool want = pass == 0 ? (bound >= thr) : (best_so_far < thr && bound > best_so_far);
                 if (want) {
                     const int W = (int)d[7], H = (int)d[8];
-                    // centres strictly inside (g0 - h, g1 + h) can overlap; widen by one cell for rounding
-                    const float ylo = (q.x - d[4] - d[0]) / d[2], yhi = (q.z + d[4] - d[0]) / d[2];
-                    const float xlo = (q.y - d[5] - d[1]) / d[3], xhi = (q.w + d[5] - d[1]) / d[3];
+                    // Centres strictly inside (g0 - h, g1 + h) can overlap.  Pass 0 only needs the cells that can reach
+                    // IoU >= thr: inter >= thr * union >= thr * max(areas), and inter = ih * iw with iw <= min(widths),
+                    // so ih >= thr * max(areas) / min(widths) =: ih_min, and ih <= (ha + hg) / 2 - |dy|: the centre range
+                    // shrinks by ih_min on both sides (likewise in x) -- about 4x fewer cells at thr = 0.5.  A 0.1 %
+                    // slack on the bound and the one-cell widening below absorb the rounding.
+                    // (pass 1 the same with the best IoU so far in place of thr: only a cell that can beat it matters)
+                    const float need = pass == 0 ? thr : best_so_far;
+                    const float amax = fmaxf(pa, qa) * need * 0.999f;
+                    const float shy = amax / fminf(2.0f * d[5], q.w - q.y);
+                    const float shx = amax / fminf(2.0f * d[4], q.z - q.x);
+                    const float ylo = (q.x - d[4] + shy - d[0]) / d[2], yhi = (q.z + d[4] - shy - d[0]) / d[2];
+                    const float xlo = (q.y - d[5] + shx - d[1]) / d[3], xhi = (q.w + d[5] - shx - d[1]) / d[3];
                     const int ya = max((int)floorf(ylo) - 1, 0), yb = min((int)ceilf(yhi) + 1, H - 1);
                     const int xa = max((int)floorf(xlo) - 1, 0), xb = min((int)ceilf(xhi) + 1, W - 1);
-                    if (yb >= ya && xb >= xa) { ny = yb - ya + 1; nx = xb - xa + 1; y0 = ya; x0 = xa; }
-                    s_done[k] = 1;
+                    if (yb >= ya && xb >= xa && yhi >= ylo && xhi >= xlo) { ny = yb - ya + 1; nx = xb - xa + 1; y0 = ya; x0 = xa; }
                 }
             }
             s_x0[k] = x0; s_y0[k] = y0; s_nx[k] = nx;
@@ -413,7 +437,7 @@ __device__ __forceinline__ void assign_one_gt(const Geo &g, const float4 *__rest
         // kCellsInFlight cells per iteration (independent anchor gathers)
         unsigned long long best = 0ull;
         int kcur = 0;
-        auto locate = [&](int c, int &k, int &r, int &p, bool &ok) {
+        auto locate = [&](int c, int &k, int &r, int &p, bool &ok, float4 &a) {
             ok = c < total;
             r = 0; p = 0;
             if (!ok) return;
@@ -424,6 +448,7 @@ __device__ __forceinline__ void assign_one_gt(const Geo &g, const float4 *__rest
             const int cell = yy * s_w[k] + xx;
             r = s_base[k] + cell * g.na + s_sh[k];
             p = s_base[k] + s_sh[k] * s_hw[k] + cell;
+            if (gen) a = anchor_from_gen(s_gen[k], yy, xx);
         };
         auto visit = [&](float4 a, int r, int p) {
             const float h = __fsub_rn(fminf(q.z, a.z), fmaxf(q.x, a.x));
@@ -453,9 +478,11 @@ __device__ __forceinline__ void assign_one_gt(const Geo &g, const float4 *__rest
             bool ok[kCellsInFlight];
             float4 a[kCellsInFlight];
 #pragma unroll
-            for (int u = 0; u < kCellsInFlight; ++u) locate(c + u * kGtcThreads, kcur, r[u], p[u], ok[u]);
+            for (int u = 0; u < kCellsInFlight; ++u) locate(c + u * kGtcThreads, kcur, r[u], p[u], ok[u], a[u]);
+            if (!gen) {
 #pragma unroll
-            for (int u = 0; u < kCellsInFlight; ++u) a[u] = __ldg(anchors + r[u]);   // r = 0 when out of range: a harmless, cached read
+                for (int u = 0; u < kCellsInFlight; ++u) a[u] = __ldg(anchors + r[u]);   // r = 0 when out of range: a harmless, cached read
+            }
 #pragma unroll
             for (int u = 0; u < kCellsInFlight; ++u)
                 if (ok[u]) visit(a[u], r[u], p[u]);
@@ -511,14 +538,14 @@ __device__ __forceinline__ void finish_counts(int B, const int32_t *pos_count, f
 
 // One CTA per (gt row, image); the CTA that finishes last turns the counters into num_positives and
 // the normaliser, so the loss kernel can follow without another launch.
-__global__ void __launch_bounds__(kGtcThreads)
-assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *__restrict__ desc, int nplanes,
+__global__ void __launch_bounds__(kGtcThreads, 5)   // 5 CTAs/SM: B*M = 640 CTAs at D0 B=64 M=10 are one resident wave
+assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *__restrict__ desc, const double *__restrict__ gen, int nplanes,
                  const float4 *__restrict__ gt_boxes, const int32_t *__restrict__ gt_labels,
                  const int32_t *__restrict__ gt_count, int Mmax, float thr, int filter_valid,
                  unsigned long long *keys, int32_t *pos_count, unsigned *touched, int touched_cap, unsigned *done, int B,
                  float *num_pos, float *normalizer) {
     __shared__ bool s_last;
-    assign_one_gt(g, anchors, desc, nplanes, gt_boxes, gt_labels, gt_count, Mmax, thr, filter_valid, keys, pos_count, touched,
+    assign_one_gt(g, anchors, desc, gen, nplanes, gt_boxes, gt_labels, gt_count, Mmax, thr, filter_valid, keys, pos_count, touched,
                   touched_cap);
     __threadfence();   // this thread's counter updates are visible before the CTA reports in
     __syncthreads();
@@ -533,6 +560,20 @@ assign_gt_kernel(const Geo g, const float4 *__restrict__ anchors, const float *_
 __global__ void __launch_bounds__(kGtcThreads)
 finish_counts_kernel(int B, const int32_t *__restrict__ pos_count, float *__restrict__ num_pos, float *__restrict__ normalizer) {
     finish_counts<false>(B, pos_count, num_pos, normalizer);
+}
+
+// the anchor table from its generator (reference order r = off_l + (y*W + x)*na + a): one thread per anchor
+__global__ void __launch_bounds__(256)
+anchor_table_kernel(const Geo g, const float *__restrict__ desc, const double *__restrict__ gen, float4 *__restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= g.A) return;
+    const int l = geo_level(g, r);
+    const int loc = r - g.off[l];
+    const int cell = loc / g.na, a = loc - cell * g.na;
+    const int k = l * g.na + a;
+    const int W = (int)__ldg(desc + (size_t)k * kDescFloats + 7);
+    const int yy = cell / W, xx = cell - yy * W;
+    out[r] = anchor_from_gen(gen + (size_t)k * kGenDoubles, yy, xx);
 }
 
 __global__ void __launch_bounds__(256)
@@ -649,7 +690,21 @@ int odk_keys_to_match(const void *keys, int B, int64_t A, int32_t *match, void *
     return check_launch("odk_keys_to_match");
 }
 
-int odk_assign_grid(const float *anchors, const float *plane_desc, int num_planes, const float *gt_boxes,
+int odk_anchor_table(const float *plane_desc, const double *plane_gen, int num_planes, const int32_t *level_hw, int num_levels,
+                     int na, float *anchors_out, void *stream) {
+    using namespace odk;
+    Geo g;
+    int rc = make_geo(&g, level_hw, num_levels, na);
+    if (rc) return rc;
+    if (!plane_desc || !plane_gen || !anchors_out || ((uintptr_t)anchors_out & 15))
+        return set_error(ODK_EINVAL, "odk_anchor_table: null pointer / anchors_out not 16-byte aligned");
+    if (num_planes != num_levels * na) return set_error(ODK_EINVAL, "odk_anchor_table: need one descriptor per (level, shape)");
+    if (g.A == 0) return ODK_OK;
+    anchor_table_kernel<<<(unsigned)((g.A + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, plane_desc, plane_gen, (float4 *)anchors_out);
+    return check_launch("odk_anchor_table");
+}
+
+int odk_assign_grid(const float *anchors, const float *plane_desc, const double *plane_gen, int num_planes, const float *gt_boxes,
                     const int32_t *gt_labels, const int32_t *gt_count, int B, int Mmax, const int32_t *level_hw,
                     int num_levels, int na, float match_thr, int filter_valid, int32_t *match, float *num_pos,
                     float *normalizer, int flags, void *workspace, size_t workspace_bytes, void *stream) {
@@ -682,7 +737,7 @@ int odk_assign_grid(const float *anchors, const float *plane_desc, int num_plane
     }
     if (Mmax > 0) {
         dim3 grid(Mmax, B);
-        assign_gt_kernel<<<grid, kGtcThreads, 0, st>>>(g, (const float4 *)anchors, plane_desc, num_planes,
+        assign_gt_kernel<<<grid, kGtcThreads, 0, st>>>(g, (const float4 *)anchors, plane_desc, plane_gen, num_planes,
                                                        (const float4 *)gt_boxes, gt_labels, gt_count, Mmax, match_thr,
                                                        filter_valid, keys, pos, touched, w.touched_cap, done, B, num_pos,
                                                        normalizer);

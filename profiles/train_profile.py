@@ -29,6 +29,7 @@ gb, gc = synth.gt_boxes(100, B, size, M, C)
 gb, gc = torch.from_numpy(gb).to(dev), torch.from_numpy(gc).to(dev)
 labeler = AnchorLabeler(Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size)).to(dev), C, match_threshold=0.5)
 TRANSIENT = 'transient' in sys.argv[2:]   # the bench's mode: the loss walks the labeler's list and clears the keys
+labeler.use_anchor_generator = os.environ.get('ODK_TEST_ANCHOR_GEN', '1') == '1'
 kw = dict(num_classes=C, alpha=0.25, gamma=1.5, delta=0.1, box_loss_weight=50.0)
 for grad in (False, True):
     for t in cls_out + box_out:

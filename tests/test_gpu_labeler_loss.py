@@ -367,3 +367,34 @@ def test_loss_stream_agrees_with_plane_kernels(monkeypatch):
     for l in range(5):
         np.testing.assert_array_equal(out['stream'][1][l], out['ring'][1][l])
         np.testing.assert_array_equal(out['stream'][2][l], out['ring'][2][l])
+
+
+def test_anchor_table_from_generator():
+    """odk_anchor_table: the labeler kernel's recomputed anchors (float64 generator -> fp32) against the table, every
+    anchor of every model shape, bit for bit -- the precondition for use_anchor_generator to leave assignments
+    untouched (they are additionally compared with the oracle's in every labeler test, which run with it on)."""
+    from ood_object_detection_b200 import _lib
+    from ood_object_detection_b200.anchors import Anchors
+    lib = _lib.lib()
+    for name, (size, scale) in synth.MODEL_SHAPES.items():
+        anc = Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size)).to(dev())
+        out = torch.empty_like(anc.boxes)
+        hw = anc.level_hw()
+        with torch.cuda.device(dev()):
+            _lib.check(lib.odk_anchor_table(_lib.ptr(anc.plane_desc), _lib.ptr(anc.plane_gen), anc.plane_desc.shape[0], _lib.int_array(hw),
+                                            len(hw), anc.get_anchors_per_location(), _lib.ptr(out), _lib.stream_ptr(dev())))
+        assert torch.equal(out, anc.boxes), name
+
+
+def test_labeler_gather_and_generator_paths_agree():
+    """The same assignment with the anchors gathered from the table (use_anchor_generator = False) and recomputed."""
+    size, scale = synth.MODEL_SHAPES['d3']
+    anc, lab = make_labeler(size, scale, 90)
+    gb, gc = synth.gt_boxes(931, 3, size, 40, 90)
+    gbt, gct = torch.from_numpy(gb).to(dev()), torch.from_numpy(gc).to(dev())
+    res = []
+    for use in (True, False):
+        lab.use_anchor_generator = use
+        lb = lab.assign(gbt, gct)
+        res.append((lb.match.clone(), lb.num_positives.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

@@ -267,3 +267,23 @@ def test_match_detections_golden(golden, case):
     label, corloc = orc.match_detections(det, scores, cls, gtb, gtc, C, dif, gof, 0.5, nms_iou, nms_max)
     assert_eval_matches_golden(g, tag, C, scores, cls, label, corloc)
     assert (label == 1).sum() > 0 and (label == 0).sum() > 0
+
+
+def test_anchor_generator_reproduces_the_table():
+    """`Anchors.plane_gen` (float64 centre origin, pitch and half sizes per (level, shape) grid) is what the labeler
+    kernel recomputes anchors from instead of gathering them: float32(cy0 + y*sy -/+ half) must equal the table bit
+    for bit, for every anchor of every model shape (the same IEEE operations in numpy as in the kernel)."""
+    from ood_object_detection_b200.anchors import Anchors
+    for name, (size, scale) in synth.MODEL_SHAPES.items():
+        anc = Anchors(3, 7, 3, synth.ASPECTS, scale, (size, size))
+        gen, desc, na = anc.plane_gen.numpy(), anc.plane_desc.numpy(), anc.get_anchors_per_location()
+        assert gen.dtype == np.float64 and gen.shape == (desc.shape[0], 6)
+        table = anc.boxes.numpy()
+        for k in range(gen.shape[0]):
+            W, H, off, a = int(desc[k, 7]), int(desc[k, 8]), int(desc[k, 9]), int(desc[k, 10])
+            cy0, cx0, sy, sx, hy, hx = gen[k]
+            yy, xx = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing='ij')
+            cy, cx = cy0 + yy.ravel() * sy, cx0 + xx.ravel() * sx
+            got = np.stack([cy - hy, cx - hx, cy + hy, cx + hx], 1).astype(np.float32)
+            rows = off + np.arange(H * W) * na + a
+            np.testing.assert_array_equal(got, table[rows], err_msg=f'{name} plane {k}')
