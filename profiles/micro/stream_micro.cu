@@ -64,12 +64,14 @@ __global__ void __launch_bounds__(256, MINB) k_tile(const float *__restrict__ x,
 
 // TMA bulk copies both ways: global -> shared (mbarrier), arithmetic in place in shared memory, shared -> global
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-template <bool MATH, int TILE_F4, int STAGES, int MINB>
+template <bool MATH, int TILE_F4, int STAGES, int MINB, bool HINT = false>
 __global__ void __launch_bounds__(256, MINB) k_tma(const float *__restrict__ x, float *__restrict__ y, size_t n4, float g, float *out) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long full[STAGES];
     constexpr unsigned kTileBytes = TILE_F4 * 16;
     float4 *buf = reinterpret_cast<float4 *>(smem);
+    unsigned long long pol = 0;
+    if (HINT) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     const size_t ntiles = n4 / TILE_F4;
     const size_t my = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     if (threadIdx.x == 0) {
@@ -81,6 +83,12 @@ __global__ void __launch_bounds__(256, MINB) k_tma(const float *__restrict__ x, 
         const int s = (int)(i % STAGES);
         const float *src = x + (blockIdx.x + i * gridDim.x) * (size_t)TILE_F4 * 4;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(kTileBytes) : "memory");
+        if (HINT)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                             smem_u32(buf + (size_t)s * TILE_F4)),
+                         "l"(src), "r"(kTileBytes), "r"(smem_u32(&full[s])), "l"(pol)
+                         : "memory");
+        else
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          smem_u32(buf + (size_t)s * TILE_F4)),
                      "l"(src), "r"(kTileBytes), "r"(smem_u32(&full[s]))
@@ -110,6 +118,9 @@ __global__ void __launch_bounds__(256, MINB) k_tma(const float *__restrict__ x, 
         __syncthreads();
         if (threadIdx.x == 0) {
             float *dst = y + (blockIdx.x + i * gridDim.x) * (size_t)TILE_F4 * 4;
+            if (HINT)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(smem_u32(t)), "r"(kTileBytes), "l"(pol) : "memory");
+            else
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(t)), "r"(kTileBytes) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -147,6 +158,13 @@ int main() {
     RUN(k_tile, false, 4, 4); RUN(k_tile, false, 4, 8); RUN(k_tile, false, 8, 4);
     RUN(k_stride, true, 4, 4); RUN(k_stride, true, 4, 6); RUN(k_stride, true, 4, 8); RUN(k_stride, true, 8, 4); RUN(k_stride, true, 2, 8);
     RUN(k_tile, true, 4, 4); RUN(k_tile, true, 4, 6); RUN(k_tile, true, 4, 8); RUN(k_tile, true, 8, 4); RUN(k_tile, true, 2, 8);
+#define RUNTH(MATH, TILE, ST, MINB)                                                                             \
+    {                                                                                                           \
+        auto kf = k_tma<MATH, TILE, ST, MINB, true>;                                                            \
+        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16 * ST);                  \
+        rep("k_tma+evict_first math=" #MATH " tile_f4=" #TILE " stages=" #ST " ctas/SM=" #MINB,                 \
+            timed([&] { kf<<<148 * MINB, 256, TILE * 16 * ST>>>(x, y, n4, 0.5f, out); }));                      \
+    }
 #define RUNT(MATH, TILE, ST, MINB)                                                                              \
     {                                                                                                           \
         auto kf = k_tma<MATH, TILE, ST, MINB>;                                                                  \
@@ -155,6 +173,7 @@ int main() {
             timed([&] { kf<<<148 * MINB, 256, TILE * 16 * ST>>>(x, y, n4, 0.5f, out); }));                      \
     }
     RUNT(false, 1024, 4, 2); RUNT(false, 1024, 3, 3); RUNT(false, 512, 4, 4); RUNT(false, 2048, 3, 2);
+    RUNTH(false, 2048, 3, 2); RUNTH(true, 2048, 3, 2); RUNTH(true, 1024, 3, 3); RUNT(true, 1536, 4, 2); RUNT(true, 3072, 2, 2); RUNT(true, 2048, 2, 3);
     RUNT(true, 1024, 4, 2); RUNT(true, 1024, 3, 3); RUNT(true, 512, 4, 4); RUNT(true, 2048, 3, 2); RUNT(true, 1024, 6, 2);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
