@@ -10,9 +10,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-fi
     python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_ncu_launch.log 2>&1
 # training step (D0 B=64): third forward iteration, third forward+gradient iteration
 python profiles/train_profile.py 3 transient > gpurun_out/${T}_train_plain.log 2>&1 || exit 1
-$NCU -k regex:'assign_gt_kernel|loss_flat_kernel|loss_patch_kernel' -s 6 -c 3 -o gpurun_out/${T}_train_fwd \
+$NCU -k regex:'assign_gt_kernel|loss_flat|loss_patch_kernel' -s 6 -c 3 -o gpurun_out/${T}_train_fwd \
     python profiles/train_profile.py 3 transient > gpurun_out/${T}_ncu_train.log 2>&1
-$NCU -k regex:'assign_gt_kernel|loss_flat_kernel|loss_patch_kernel' -s 15 -c 3 -o gpurun_out/${T}_train_grad \
+$NCU -k regex:'assign_gt_kernel|loss_flat|loss_patch_kernel' -s 15 -c 3 -o gpurun_out/${T}_train_grad \
     python profiles/train_profile.py 3 transient >> gpurun_out/${T}_ncu_train.log 2>&1
 # post-process (D3 B=32): sample + collect + tail of the fused entry point, hard then soft suppression
 ODK_SHOW_TIMELINE=1 python profiles/pp_fused_profile.py d3 32 10 dense,planted staged > gpurun_out/${T}_pp_plain.log 2>&1 || exit 1

@@ -100,9 +100,9 @@ B, A, C = 64, 49104, 90
 rt = {
     'git_sha': sha,
     'source': f'profiles/{tag}_summary.md sections 3-7 (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch each)',
-    'loss_fwd_kernel_dram_bytes_per_launch': pick('train_fwd', 'loss_flat_kernel'),
+    'loss_fwd_kernel_dram_bytes_per_launch': pick('train_fwd', 'loss_flat'),
     'loss_fwd_kernel_algorithmic_bytes_per_launch': B * A * (4 * C + 16),
-    'loss_grad_kernel_dram_bytes_per_launch': pick('train_grad', 'loss_flat_kernel'),
+    'loss_grad_kernel_dram_bytes_per_launch': pick('train_grad', 'loss_flat'),
     'loss_grad_kernel_algorithmic_bytes_per_launch': 2 * B * A * (4 * C + 16),
     'loss_patch_kernel_dram_bytes_per_launch': pick('train_grad', 'loss_patch_kernel'),
     'assign_gt_kernel_dram_bytes_per_launch': pick('train_grad', 'assign_gt_kernel'),
