@@ -21,6 +21,8 @@
 // exact cluster radix select of odk_topk.cu and the stand-alone detect kernel pick them up afterwards.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "odk_stream.cuh"
 #include "odk_detect.cuh"
 
@@ -779,6 +781,54 @@ int launch_ood_flagged(const Geo &g, const void *const *cls_levels, int layout, 
 
 extern "C" {
 
+// ---- a forked lane beside the caller's stream ------------------------------------------------------------------
+// Per device: one non-blocking side stream and a ring of event pairs (an event may be re-recorded while an older wait on
+// it is still pending: a wait captures the record that precedes it).  Works eagerly and under stream capture, where the
+// record / wait pairs become the fork and join edges of the graph.
+struct SideLane { cudaStream_t side; cudaEvent_t fork, join; };
+static int fork_side(cudaStream_t st, SideLane *lane) {
+    constexpr int kRing = 32;
+    struct PerDevice { cudaStream_t side; cudaEvent_t ev[2 * kRing]; unsigned next; bool ready; };
+    static PerDevice devs[odk::kMaxDevices];
+    static std::mutex mu;
+    const int dev = odk::current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    PerDevice &d = devs[dev];
+    if (!d.ready) {
+        cudaError_t e = cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 * kRing && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&d.ev[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) return odk::set_error((int)e, "odk_postprocess: side stream: %s", cudaGetErrorString(e));
+        d.next = 0; d.ready = true;
+    }
+    const unsigned slot = d.next++ % kRing;
+    lane->side = d.side; lane->fork = d.ev[2 * slot]; lane->join = d.ev[2 * slot + 1];
+    cudaError_t e = cudaEventRecord(lane->fork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(lane->side, lane->fork, 0);
+    if (e != cudaSuccess) return odk::set_error((int)e, "odk_postprocess: fork: %s", cudaGetErrorString(e));
+    return ODK_OK;
+}
+static int join_side(cudaStream_t st, const SideLane &lane) {
+    cudaError_t e = cudaEventRecord(lane.join, lane.side);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, lane.join, 0);
+    if (e != cudaSuccess) return odk::set_error((int)e, "odk_postprocess: join: %s", cudaGetErrorString(e));
+    return ODK_OK;
+}
+
+// flagged images only (none for real score distributions): exact select, then their detections / OOD scores
+static int flagged_path(const odk::TopkArgs &a, int B, int K, const float *anchors, const float *img_scale, const float *img_size,
+                        const odk_detect_params *params, float *dets, int32_t *count, int32_t *src, int64_t *det_anchor,
+                        const void *const *cls_levels, int layout, int C, float temperature, float *energy, float *max_logit,
+                        cudaStream_t st) {
+    using namespace odk;
+    int rc = launch_topk_exact_flagged(a, st);
+    if (rc) return rc;
+    rc = launch_detect_flagged(a.out_val, a.out_box, (const int64_t *)a.out_idx, (const int64_t *)a.out_cls, B, K, anchors, a.g.A,
+                               img_scale, img_size, params, dets, count, src, det_anchor, a.flag, st);
+    if (rc) return rc;
+    if (energy) rc = launch_ood_flagged(a.g, cls_levels, layout, B, C, det_anchor, params->max_det, temperature, energy, max_logit, a.flag, st);
+    return rc;
+}
+
 static int post_ws_for(int B, int C, const int32_t *level_hw, int num_levels, int na, int K, odk::PostWs *w) {
     using namespace odk;
     Geo g;
@@ -915,20 +965,26 @@ int odk_postprocess(const void *const *cls_levels, const void *const *box_levels
         auto kernel = params->soft_nms ? post_tail_kernel<true> : post_tail_kernel<false>;
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error((int)e, "odk_postprocess: %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+        // Which images the sampled path cannot take is known from the candidate counts once the collect kernel is done,
+        // so the flagged-image kernels (exact select -> detections -> OOD scores; they exit at once when nothing is flagged,
+        // which is every real score distribution) run on a forked stream BESIDE the tail kernel instead of behind it:
+        // three dependent launches (~9 us) leave the critical path.
+        SideLane lane;
+        rc = fork_side(st, &lane);
+        if (rc) return rc;
         kernel<<<B, kPostThreads, smem, st>>>(P);
         rc = check_launch("odk_postprocess/post_tail_kernel");
+        if (rc) return rc;
+        a.fused = 2;
+        a.force_exact = P.debug_skip_tails;
+        rc = flagged_path(a, B, K, anchors, img_scale, img_size, params, dets, count, src, det_anchor, cls_levels, layout, C, temperature,
+                          energy, max_logit, lane.side);
+        const int rj = join_side(st, lane);
+        return rc ? rc : rj;
     }
     if (rc) return rc;
-    // flagged images only (none for real score distributions): exact select, then their detections / OOD scores
-    rc = launch_topk_exact_flagged(a, st);
-    if (rc) return rc;
-    rc = launch_detect_flagged(a.out_val, a.out_box, (const int64_t *)a.out_idx, (const int64_t *)a.out_cls, B, K, anchors,
-                               a.g.A, img_scale, img_size, params, dets, count, src, det_anchor, a.flag, st);
-    if (rc) return rc;
-    if (energy) {
-        rc = launch_ood_flagged(a.g, cls_levels, layout, B, C, det_anchor, params->max_det, temperature, energy, max_logit, a.flag, st);
-    }
-    return rc;
+    return flagged_path(a, B, K, anchors, img_scale, img_size, params, dets, count, src, det_anchor, cls_levels, layout, C, temperature,
+                        energy, max_logit, st);
 }
 
 }  // extern "C"

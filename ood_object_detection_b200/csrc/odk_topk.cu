@@ -108,7 +108,15 @@ topk_exact_kernel(const __grid_constant__ TopkArgs A) {
     cg::cluster_group cluster = cg::this_cluster();
     const int b = blockIdx.x / kClusterSize;
     const unsigned rank = cluster.block_rank();
-    if (A.flag[b] == 0u) {   // uniform across the cluster: the select kernel did this image, its box rows are left
+    if (A.fused == 2) {
+        // staged odk_postprocess: this kernel runs BESIDE the tail kernel (forked stream), so it decides by itself which
+        // images the sampled path cannot take -- the same test on the final candidate count as run_tail -- and publishes
+        // the flag for the flagged-image kernels that follow it
+        const unsigned n = __ldcg(A.cnt + b);
+        const bool flagged = n < (unsigned)A.K || n > (unsigned)kCap || A.force_exact;
+        if (!flagged) return;
+        if (rank == 0 && threadIdx.x == 0) A.flag[b] = 1u;
+    } else if (A.flag[b] == 0u) {   // uniform across the cluster: the select kernel did this image, its box rows are left
         if (!A.fused) gather_selected_boxes(A, b, rank);   // (behind odk_postprocess the image is complete already)
         return;
     }

@@ -44,7 +44,8 @@ struct TopkArgs {
     float *out_box;               // [B][K][4]
     long long *out_idx;           // [B][K]
     long long *out_cls;           // [B][K]
-    int fused;                    // called behind odk_postprocess: unflagged images are already complete
+    int fused;                    // called behind odk_postprocess: unflagged images are already complete (2: beside the tail kernel)
+    int force_exact;              // diagnostics (ODK_POST_SKIP_TAILS=1): every image goes the exact way
     unsigned long long *stamp;    // diagnostics: [B][kStampSlots] %globaltimer marks (odk_postprocess), or null
 };
 
