@@ -353,17 +353,24 @@ __device__ __forceinline__ void assign_one_gt(const Geo &g, const float4 *__rest
     __shared__ double s_gen[kMaxPlanes][kGenDoubles];
     __shared__ unsigned long long s_red[kGtcThreads / 32];
     __shared__ unsigned long long s_best;
+    __shared__ unsigned s_bmax;
+    __shared__ unsigned char s_done[kMaxPlanes];
+    __shared__ float s_desc[kMaxPlanes][kDescFloats];
     const int b = blockIdx.y, i = blockIdx.x;
-    int M = Mmax;
-    if (gt_count) M = min(max(__ldg(gt_count + b), 0), Mmax);
-    if (i >= M) return;
-    if (filter_valid && __ldg(gt_labels + (size_t)b * Mmax + i) < 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // everything the CTA needs from global memory is requested at once (one exposed latency, not four dependent ones)
+    const int cnt_raw = gt_count ? __ldg(gt_count + b) : Mmax;
+    const int label = __ldg(gt_labels + (size_t)b * Mmax + i);
     const float4 q = __ldg(gt_boxes + (size_t)b * Mmax + i);
+    for (int e = tid; e < nplanes * kDescFloats; e += kGtcThreads) (&s_desc[0][0])[e] = __ldg(desc + e);
+    const int M = min(max(cnt_raw, 0), Mmax);
+    if (i >= M) return;
+    if (filter_valid && label < 0) return;
     const float qa = area_ref(q.x, q.y, q.z, q.w);
     if (tid == 0) s_best = 0ull;
+    __syncthreads();
     for (int k = tid; k < nplanes; k += kGtcThreads) {
-        const float *d = desc + (size_t)k * kDescFloats;
+        const float *d = s_desc[k];
         s_w[k] = (int)d[7]; s_base[k] = (int)d[9]; s_sh[k] = (int)d[10]; s_hw[k] = g.hw[(int)d[11]];
     }
     if (gen)
@@ -371,19 +378,39 @@ __device__ __forceinline__ void assign_one_gt(const Geo &g, const float4 *__rest
     __syncthreads();
     unsigned long long *krow = keys + (size_t)b * g.Apad;
 
-    for (int pass = 0; pass < 2; ++pass) {
+    // Passes: 0 = the planes whose area bound reaches the threshold, cells that can reach it (these hold every match).
+    // If the gt matched nothing the forced match needs the TRUE arg-max over all anchors: pass 1 looks at the planes
+    // whose bound is at least half the best bound of any plane (the anchors most like the gt), cells that can beat the
+    // best IoU so far; pass 2 at whatever plane can still beat the best after that -- for a small gt, whose only
+    // similar anchors are the smallest ones, usually none (one pass over every overlapping cell of every plane cost
+    // such a gt 3-4 k cells and made its CTA the kernel's critical path: 16 us against a median of 7.6).
+    // A plane enumerated in pass 1 is complete for pass 2 (the best only grows); pass-0 planes are not (need = thr).
+    if (tid == 0) s_bmax = 0u;
+    for (int k = tid; k < nplanes; k += kGtcThreads) s_done[k] = 0;
+    __syncthreads();
+    for (int pass = 0; pass < 3; ++pass) {
         // ---- which planes, which cells ----
         const float best_so_far = __uint_as_float((unsigned)(s_best >> 32));
+        if (pass > 0 && !(best_so_far < thr)) break;   // uniform: the gt has its match(es), the arg-max is among them
+        const float bmax = __uint_as_float(s_bmax);     // (pass 0 writes it below; read after that pass's barriers)
         for (int k = tid; k < nplanes; k += kGtcThreads) {
-            const float *d = desc + (size_t)k * kDescFloats;
+            const float *d = s_desc[k];
             int nx = 0, ny = 0, x0 = 0, y0 = 0;
             if (qa > 0.0f) {
                 const float pa = d[6];
-                const float bound = fminf(pa, qa) / fmaxf(pa, qa) * 1.00001f;   // >= any IoU in this plane
-                // pass 1 (the gt matched nothing: the forced match needs the true arg-max) looks at every overlapping cell
-                // of every plane that can still beat the best so far, pass-0 planes included
-                const bool want = pass == 0 ? (bound >= thr) : (best_so_far < thr && bound > best_so_far);
+                // Two upper bounds on any IoU in this plane: min/max of the areas, and the tighter one from the dimensions (the
+                // intersection is at most min(heights) * min(widths); for a long thin gt it rules out the square anchors of the
+                // same area).  Pass 0 selects by the AREA bound on purpose: for a gt that ends up unmatched its planes are the
+                // cheap first look (cells that could reach thr only) that gives passes 1-2 a best IoU to prune and shrink with
+                // (measured: selecting pass 0 by the tight bound costs 1 us at D0 M=10 and 6 % at D7 M=100).
+                const float bound = fminf(pa, qa) / fmaxf(pa, qa) * 1.00001f;
+                const float imax = fminf(2.0f * d[4], q.z - q.x) * fminf(2.0f * d[5], q.w - q.y);
+                const float tight = imax / fmaxf(pa + qa - imax, 1e-30f) * 1.0001f;
+                if (pass == 0) atomicMax(&s_bmax, __float_as_uint(bound));      // positive floats order like their bits
+                const bool want = pass == 0 ? (bound >= thr)
+                                            : (!s_done[k] && tight > best_so_far && (pass == 2 || bound >= 0.5f * bmax));
                 if (want) {
+                    if (pass > 0) s_done[k] = 1;
                     const int W = (int)d[7], H = (int)d[8];
                     // Centres strictly inside (g0 - h, g1 + h) can overlap.  Pass 0 only needs the cells that can reach
                     // IoU >= thr: inter >= thr * union >= thr * max(areas), and inter = ih * iw with iw <= min(widths),

@@ -1,5 +1,6 @@
 // Shared host/device helpers for libodk (sm_100a).  See include/odk.h for the ABI.
 #pragma once
+#include <mutex>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -189,5 +190,40 @@ static inline int device_sm_count() {
     }
     return v;
 }
+
+// ---- a forked lane beside the caller's stream ------------------------------------------------------------------
+// Per device: one non-blocking side stream and a ring of event pairs (an event may be re-recorded while an older wait on
+// it is still pending: a wait captures the record that precedes it).  Works eagerly and under stream capture, where the
+// record / wait pairs become the fork and join edges of the graph.
+struct SideLane { cudaStream_t side; cudaEvent_t fork, join; };
+static inline int fork_side(cudaStream_t st, SideLane *lane) {
+    constexpr int kRing = 32, kSides = 8;   // concurrent calls on one device (threads, captures) get different side streams
+    struct PerDevice { cudaStream_t side[kSides]; cudaEvent_t ev[2 * kRing]; unsigned next; bool ready; };
+    static PerDevice devs[kMaxDevices];
+    static std::mutex mu;
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    PerDevice &d = devs[dev];
+    if (!d.ready) {
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < kSides && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&d.side[i], cudaStreamNonBlocking);
+        for (int i = 0; i < 2 * kRing && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&d.ev[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) return set_error((int)e, "side stream: %s", cudaGetErrorString(e));
+        d.next = 0; d.ready = true;
+    }
+    const unsigned slot = d.next++ % kRing;
+    lane->side = d.side[slot % kSides]; lane->fork = d.ev[2 * slot]; lane->join = d.ev[2 * slot + 1];
+    cudaError_t e = cudaEventRecord(lane->fork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(lane->side, lane->fork, 0);
+    if (e != cudaSuccess) return set_error((int)e, "stream fork: %s", cudaGetErrorString(e));
+    return ODK_OK;
+}
+static inline int join_side(cudaStream_t st, const SideLane &lane) {
+    cudaError_t e = cudaEventRecord(lane.join, lane.side);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, lane.join, 0);
+    if (e != cudaSuccess) return set_error((int)e, "stream join: %s", cudaGetErrorString(e));
+    return ODK_OK;
+}
+
 
 }  // namespace odk

@@ -66,6 +66,7 @@ struct LossArgs {
     int part_base;        // first partial slot of this launch
     int part_total;       // slots the finishing launch sums (0: this launch does not finish)
     int part_int_from;    // > 0: slots from here on hold fixed-point integer pairs (patch kernel)
+    int finish_ctas;      // > 0: CTAs (of several concurrent launches) that report to the counter before the reduction is finished
     unsigned *counter;
     float *out;
     // optional fused exchange of the partial sums with the other data-parallel ranks (xworld == 0: off)
@@ -433,7 +434,7 @@ __device__ __forceinline__ void finish_block(const LossArgs &A, float csum, floa
         if (A.part_total > 0) {   // (a launch that does not finish the reduction leaves the counter alone)
             __threadfence();
             const unsigned done = atomicAdd(A.counter, 1u);
-            s_last = done == gridDim.x * gridDim.y - 1;
+            s_last = done == (A.finish_ctas > 0 ? (unsigned)A.finish_ctas : gridDim.x * gridDim.y) - 1;
         }
     }
     __syncthreads();
@@ -1136,6 +1137,19 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
         }
         const int g_tma = sm_count() * 2;
         if (tma) { patch.part_base = g_tma; patch.part_total = g_tma + g_patch; patch.part_int_from = g_tma; }
+        // Forward only: the patch writes nothing the stream touches, so it runs on a forked stream BESIDE it (~10 us of
+        // dependent loads off the critical path); whichever CTA of the two launches reports last finishes the reduction.
+        // (With gradients the patch overwrites elements the stream has written and must follow it.)
+        const bool beside = !grad;
+        SideLane lane;
+        if (beside) {
+            flat.part_total = patch.part_total; flat.part_int_from = patch.part_int_from;
+            flat.finish_ctas = patch.finish_ctas = g_flat + g_patch;
+            flat.clr_in_patch = patch.clr_in_patch;   // (only the finishing code looks at it in the stream kernel)
+            rc = fork_side(st, &lane);
+            if (rc) return rc;
+        }
+        cudaStream_t st_patch = beside ? lane.side : st;
         rc = -1;
 #define ODK_STREAM_CASE(M)                                                                 \
         if (mode == M) {                                                                   \
@@ -1148,8 +1162,8 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
             else loss_flat_kernel<M, false><<<g_flat, kLossThreads, 0, st>>>(flat);        \
             rc = check_launch("odk_loss/loss_flat_kernel");                                \
             if (rc) return rc;                                                             \
-            if (grad) loss_patch_kernel<M, true><<<g_patch, kLossThreads, 0, st>>>(patch); \
-            else loss_patch_kernel<M, false><<<g_patch, kLossThreads, 0, st>>>(patch);     \
+            if (grad) loss_patch_kernel<M, true><<<g_patch, kLossThreads, 0, st_patch>>>(patch); \
+            else loss_patch_kernel<M, false><<<g_patch, kLossThreads, 0, st_patch>>>(patch);     \
             rc = check_launch("odk_loss/loss_patch_kernel");                               \
         }
         ODK_STREAM_CASE(kNew)
@@ -1157,6 +1171,10 @@ int odk_loss(const void *const *cls_levels, const void *const *box_levels, int B
         ODK_STREAM_CASE(kLegacy)
 #undef ODK_STREAM_CASE
         if (rc < 0) return set_error(ODK_EINVAL, "odk_loss: bad mode");
+        if (beside) {
+            const int rj = join_side(st, lane);
+            if (!rc) rc = rj;
+        }
         return rc;
     }
     // the counter must be zero on entry; the kernel re-zeroes it, but a fresh workspace is arbitrary

@@ -21,8 +21,6 @@
 // exact cluster radix select of odk_topk.cu and the stand-alone detect kernel pick them up afterwards.
 #include <stdlib.h>
 
-#include <mutex>
-
 #include "odk_stream.cuh"
 #include "odk_detect.cuh"
 
@@ -780,39 +778,6 @@ int launch_ood_flagged(const Geo &g, const void *const *cls_levels, int layout, 
 }  // namespace odk
 
 extern "C" {
-
-// ---- a forked lane beside the caller's stream ------------------------------------------------------------------
-// Per device: one non-blocking side stream and a ring of event pairs (an event may be re-recorded while an older wait on
-// it is still pending: a wait captures the record that precedes it).  Works eagerly and under stream capture, where the
-// record / wait pairs become the fork and join edges of the graph.
-struct SideLane { cudaStream_t side; cudaEvent_t fork, join; };
-static int fork_side(cudaStream_t st, SideLane *lane) {
-    constexpr int kRing = 32;
-    struct PerDevice { cudaStream_t side; cudaEvent_t ev[2 * kRing]; unsigned next; bool ready; };
-    static PerDevice devs[odk::kMaxDevices];
-    static std::mutex mu;
-    const int dev = odk::current_device();
-    std::lock_guard<std::mutex> lock(mu);
-    PerDevice &d = devs[dev];
-    if (!d.ready) {
-        cudaError_t e = cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking);
-        for (int i = 0; i < 2 * kRing && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&d.ev[i], cudaEventDisableTiming);
-        if (e != cudaSuccess) return odk::set_error((int)e, "odk_postprocess: side stream: %s", cudaGetErrorString(e));
-        d.next = 0; d.ready = true;
-    }
-    const unsigned slot = d.next++ % kRing;
-    lane->side = d.side; lane->fork = d.ev[2 * slot]; lane->join = d.ev[2 * slot + 1];
-    cudaError_t e = cudaEventRecord(lane->fork, st);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(lane->side, lane->fork, 0);
-    if (e != cudaSuccess) return odk::set_error((int)e, "odk_postprocess: fork: %s", cudaGetErrorString(e));
-    return ODK_OK;
-}
-static int join_side(cudaStream_t st, const SideLane &lane) {
-    cudaError_t e = cudaEventRecord(lane.join, lane.side);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, lane.join, 0);
-    if (e != cudaSuccess) return odk::set_error((int)e, "odk_postprocess: join: %s", cudaGetErrorString(e));
-    return ODK_OK;
-}
 
 // flagged images only (none for real score distributions): exact select, then their detections / OOD scores
 static int flagged_path(const odk::TopkArgs &a, int B, int K, const float *anchors, const float *img_scale, const float *img_size,
