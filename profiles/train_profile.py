@@ -48,4 +48,4 @@ for grad in (False, True):
         e2.record()
         torch.cuda.synchronize()
         print(f'd0 B={B} grad={grad} iter {it}: assign {e0.elapsed_time(e1):.3f} ms, loss {e1.elapsed_time(e2):.3f} ms, '
-              f'total {float(tot):.4f}')
+              f'total {float(tot.detach()):.4f}')

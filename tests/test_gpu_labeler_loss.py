@@ -248,7 +248,7 @@ def test_loss_gradients_vs_fp64():
         box_loss = ((0.5 * q * q + delta * (ae - q)) * (tg != 0.0)).sum() / (n * 4.0)
         total64 = total64 + cls_loss + w * box_loss
     total64.backward()
-    assert abs(tot.item() - float(total64)) <= 1e-5 * abs(float(total64))
+    assert abs(tot.detach().item() - float(total64)) <= 1e-5 * abs(float(total64))
     w_cls = max(alpha, 1.0 - alpha) / float(n)
     worst_rel = worst_bar = 0.0
     for l in range(5):
