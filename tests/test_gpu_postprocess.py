@@ -366,3 +366,21 @@ def test_channels_last_head_outputs_are_read_in_place(pipeline):
         for key in ('detections', 'count', 'src', 'anchor', 'max_logit'):
             assert torch.equal(want[key], got[key]), key
         np.testing.assert_allclose(got['energy'].cpu().numpy(), want['energy'].cpu().numpy(), rtol=1e-6)
+
+
+@pytest.mark.parametrize('pipeline', PIPELINES)
+def test_fused_postprocess_more_images_than_sms(pipeline):
+    """B = 180 images (> 148 SMs): the tail kernel needs more than one wave, the collect grid has a single CTA per
+    image, the persistent pipeline queues tails.  Fused entry point == the stage chain (itself checked against the
+    oracle above), bit for bit, hard and soft."""
+    from ood_object_detection_b200.anchors import detect_batch
+    from ood_object_detection_b200.bench import _post_process, post_process_detect
+    size, B, C, K, D = 128, 180, 8, 500, 20
+    co, bo = synth.head_outputs(350, B, size, C)
+    tc, tb, ta = [t(x) for x in co], [t(x) for x in bo], anchors_t(size)
+    cls_k, box_k, idx, klass = _post_process(tc, tb, 5, C, K)
+    for soft in (False, True):
+        dets, count, src = detect_batch(cls_k, box_k, ta, idx, klass, None, None, D, soft)
+        out = post_process_detect(tc, tb, ta, 5, C, K, D, soft, with_ood=True, pipeline=pipeline)
+        assert torch.equal(out['count'], count) and torch.equal(out['src'], src) and torch.equal(out['detections'], dets)
+        assert int(count.min()) > 0
