@@ -344,7 +344,8 @@ def test_loss_stream_patch_modes_bitwise(name, B, m):
 
 def test_loss_stream_agrees_with_plane_kernels(monkeypatch):
     """ODK_LOSS_KERNEL=ring selects the plane-walking kernels (the round-1 path, still used for targets given as
-    tensors): same losses to 1e-6 (different summation order) and the same gradients bit for bit."""
+    tensors), ODK_LOSS_TMA=0 the LDG/STG tile stream for the gradient pass instead of the TMA bulk tiles: same losses
+    to 1e-6 (different summation order) and the same gradients bit for bit."""
     from ood_object_detection_b200.loss import loss_fn_fused
     size, scale = synth.MODEL_SHAPES['d3']
     B, C, m = 2, 90, 25
@@ -353,20 +354,23 @@ def test_loss_stream_agrees_with_plane_kernels(monkeypatch):
     co_np, bo_np = synth.head_outputs(921, B, size, C, tie_free=False)
     kw = dict(num_classes=C, alpha=0.25, gamma=1.5, delta=0.1, box_loss_weight=50.0)
     out = {}
-    for which in ('stream', 'ring'):
+    for which in ('stream', 'stream_ldg', 'ring'):   # TMA bulk tiles (default) | LDG/STG tiles | plane-walking kernels
+        monkeypatch.delenv('ODK_LOSS_KERNEL', raising=False)
+        monkeypatch.delenv('ODK_LOSS_TMA', raising=False)
         if which == 'ring':
             monkeypatch.setenv('ODK_LOSS_KERNEL', 'ring')
-        else:
-            monkeypatch.delenv('ODK_LOSS_KERNEL', raising=False)
+        elif which == 'stream_ldg':
+            monkeypatch.setenv('ODK_LOSS_TMA', '0')
         co, bo = [t(x, True) for x in co_np], [t(x, True) for x in bo_np]
         lb = lab.assign(torch.from_numpy(gb).to(dev()), torch.from_numpy(gc).to(dev()))
         tot, cl, bl = loss_fn_fused(co, bo, lb, **kw)
         tot.backward()
         out[which] = ([tot.item(), cl.item(), bl.item()], [x.grad.cpu().numpy() for x in co], [x.grad.cpu().numpy() for x in bo])
-    np.testing.assert_allclose(out['stream'][0], out['ring'][0], rtol=1e-6)
-    for l in range(5):
-        np.testing.assert_array_equal(out['stream'][1][l], out['ring'][1][l])
-        np.testing.assert_array_equal(out['stream'][2][l], out['ring'][2][l])
+    for other in ('stream_ldg', 'ring'):
+        np.testing.assert_allclose(out['stream'][0], out[other][0], rtol=1e-6)
+        for l in range(5):
+            np.testing.assert_array_equal(out['stream'][1][l], out[other][1][l])
+            np.testing.assert_array_equal(out['stream'][2][l], out[other][2][l])
 
 
 def test_anchor_table_from_generator():
